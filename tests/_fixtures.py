@@ -1,0 +1,41 @@
+"""Load the committed sample-molecule fixtures (tests/golden/*.npz) into the oracle's System type."""
+import json
+import os
+
+import numpy as np
+
+from oracle import afesp_oracle as orc
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden():
+    with open(os.path.join(GOLDEN_DIR, "golden.json")) as f:
+        return json.load(f)
+
+
+def load_system(name, calc_type=None):
+    z = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
+    sysm = orc.System()
+    for k, v in orc.parse_els_in(str(z["els_in"])).items():
+        if hasattr(sysm, k):
+            setattr(sysm, k, v)
+    if calc_type is not None:
+        sysm.calc_type = calc_type
+    sysm.ovlp = z["ovlp"]
+    sysm.hcore = z["ke"] + z["en"]
+    sysm.eri = z["eri"]
+    sysm.nbasis = sysm.ovlp.shape[0]
+    geom = z["geom"]
+    zz = geom[:, 0].astype(int)
+    xyz = geom[:, 1:]
+    sysm.nel = int(zz.sum())
+    sysm.nocc = sysm.nel // 2
+    e_nuc = 0.0
+    for j in range(1, len(zz)):
+        for i in range(j):
+            e_nuc += zz[i] * zz[j] / np.linalg.norm(xyz[i] - xyz[j])
+    sysm.e_nuc = e_nuc
+    if sysm.scf_read_guess and z["guess"].size:
+        sysm.guess = z["guess"]
+    return sysm
