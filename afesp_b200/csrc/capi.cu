@@ -1,0 +1,488 @@
+// C ABI of the engine (include/afesp_gpu.h): argument checking, host<->device copies, status codes.
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstring>
+
+#include "../../include/afesp_gpu.h"
+#include "ccsd.cuh"
+
+using namespace afesp;
+
+namespace {
+
+// ---- NCCL through dlopen: the library must load on hosts without NCCL and must share the copy a host process
+//      (e.g. a torchrun launcher) has already loaded.
+struct NcclId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) { err = "NCCL not found (dlopen libnccl.so.2)"; return false; }
+    GetUniqueId = (int (*)(NcclId*))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (int (*)(NcclComm*, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (int (*)(NcclComm))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "NCCL symbols missing"; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+constexpr int kNcclDouble = 8;  // ncclFloat64
+constexpr int kNcclSum = 0;
+
+struct Handle {
+  int device = 0;
+  CCState s;
+  DBuf eri_ao, coeff;
+  int n_ao = 0;
+  std::string err;
+  int rank = 0, nranks = 1;
+  NcclComm comm = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double last_ms = 0.0;
+  long long launches0 = 0;
+  double flops0 = 0.0;
+};
+
+std::string g_open_error;
+
+struct StageTimer {  // device time of one API stage, on the stream the kernels run on
+  Handle* h;
+  explicit StageTimer(Handle* hh) : h(hh) { cudaEventRecord(h->ev0, h->s.eng.stream); }
+  void stop() {
+    cudaEventRecord(h->ev1, h->s.eng.stream);
+    cudaEventSynchronize(h->ev1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->last_ms = ms;
+  }
+};
+
+template <class F>
+int guarded(afesp_handle hv, F&& f) {
+  Handle* h = static_cast<Handle*>(hv);
+  if (!h) return 1;
+  try {
+    AFESP_CUDA_CHECK(cudaSetDevice(h->device));
+    f(*h);
+    return 0;
+  } catch (const Error& e) {
+    h->err = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    h->err = e.what();
+    return 1;
+  }
+}
+
+void assemble_finalize_checks(Handle& h) {
+  AFESP_REQUIRE(h.s.t2.size() > 0, "CCSD state not initialised (call afesp_gpu_ccsd_init first)");
+}
+
+// Register-resident DMMA loop: every warp keeps 8 independent accumulator pairs in flight.
+__global__ void k_dmma_peak(double* out, int iters) {
+  double c[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c[i] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(c[2 * i]), "+d"(c[2 * i + 1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i];
+  if (s == 12345.678) out[0] = s;  // keep the loop alive
+}
+
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int afesp_gpu_open(int device, afesp_handle* out) {
+  if (!out) return 1;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_open_error = std::string("afesp_gpu_open: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback";
+    return 2;
+  }
+  if (device < 0 || device >= ndev) { g_open_error = "afesp_gpu_open: device index out of range"; return 1; }
+  cudaDeviceProp prop;
+  cudaSetDevice(device);
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major < 10) {
+    g_open_error = "afesp_gpu_open: kernels are built for sm_100a (Blackwell) only; found compute capability " +
+                   std::to_string(prop.major) + "." + std::to_string(prop.minor);
+    return 2;
+  }
+  Handle* h = new Handle();
+  h->device = device;
+  if (cudaStreamCreate(&h->s.eng.stream) != cudaSuccess || cudaEventCreate(&h->ev0) != cudaSuccess ||
+      cudaEventCreate(&h->ev1) != cudaSuccess) {
+    g_open_error = "afesp_gpu_open: stream/event creation failed";
+    delete h;
+    return 2;
+  }
+  h->launches0 = g_launch_count;
+  h->flops0 = g_gemm_flops;
+  *out = h;
+  return 0;
+}
+
+int afesp_gpu_close(afesp_handle hv) {
+  Handle* h = static_cast<Handle*>(hv);
+  if (!h) return 1;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  cudaStream_t st = h->s.eng.stream;
+  delete h;
+  if (st) cudaStreamDestroy(st);
+  return 0;
+}
+
+const char* afesp_gpu_last_error(afesp_handle hv) {
+  Handle* h = static_cast<Handle*>(hv);
+  return h ? h->err.c_str() : g_open_error.c_str();
+}
+
+int afesp_gpu_set_option(afesp_handle hv, const char* key, double value) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(key != nullptr, "set_option: null key");
+    std::string k(key);
+    Options& o = h.s.opt;
+    if (k == "q1_transposed_foo") o.q1_transposed_foo = value != 0.0;
+    else if (k == "q3a_truncated_e") o.q3a_truncated_e = value != 0.0;
+    else if (k == "q3b_stale_intermediates") o.q3b_stale_intermediates = value != 0.0;
+    else if (k == "triples_ijk_symmetry") o.triples_ijk_symmetry = value != 0.0;
+    else if (k == "triples_batch_bytes") o.triples_batch_bytes = (long long)value;
+    else throw Error(1, "set_option: unknown key " + k);
+  });
+}
+
+int afesp_gpu_counters(afesp_handle hv, long long* launches, double* gemm_flops) {
+  return guarded(hv, [&](Handle& h) {
+    if (launches) *launches = g_launch_count - h.launches0;
+    if (gemm_flops) *gemm_flops = g_gemm_flops - h.flops0;
+  });
+}
+
+int afesp_gpu_ao2mo(afesp_handle hv, int n, const double* eri_ao, const double* coeff, double* eri_mo) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(n > 0, "ao2mo: nbasis must be positive");
+    const long long np = npacked_of(n);
+    cudaStream_t st = h.s.eng.stream;
+    if (eri_ao || coeff) {
+      AFESP_REQUIRE(eri_ao && coeff, "ao2mo: pass both eri_ao and coeff, or neither to reuse the resident copies");
+      if ((long long)h.eri_ao.n != np) h.eri_ao.alloc((size_t)np);
+      if ((long long)h.coeff.n != (long long)n * n) h.coeff.alloc((size_t)n * n);
+      AFESP_CUDA_CHECK(cudaMemcpyAsync(h.eri_ao.p, eri_ao, np * 8, cudaMemcpyHostToDevice, st));
+      AFESP_CUDA_CHECK(cudaMemcpyAsync(h.coeff.p, coeff, (size_t)n * n * 8, cudaMemcpyHostToDevice, st));
+      h.n_ao = n;
+    } else {
+      AFESP_REQUIRE(h.n_ao == n && h.eri_ao.p, "ao2mo: no resident AO integrals for this nbasis");
+    }
+    if ((long long)h.s.eri_mo.n != np) h.s.eri_mo.alloc((size_t)np);
+    h.s.n = n;
+    StageTimer tm(&h);
+    ao2mo_packed(h.s.eng, n, h.eri_ao.p, h.coeff.p, h.s.eri_mo.p);
+    tm.stop();
+    if (eri_mo) {
+      AFESP_CUDA_CHECK(cudaMemcpyAsync(eri_mo, h.s.eri_mo.p, np * 8, cudaMemcpyDeviceToHost, st));
+      AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+  });
+}
+
+int afesp_gpu_set_eri_mo(afesp_handle hv, int n, const double* eri_mo) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(n > 0 && eri_mo, "set_eri_mo: bad arguments");
+    const long long np = npacked_of(n);
+    if ((long long)h.s.eri_mo.n != np) h.s.eri_mo.alloc((size_t)np);
+    AFESP_CUDA_CHECK(cudaMemcpyAsync(h.s.eri_mo.p, eri_mo, np * 8, cudaMemcpyHostToDevice, h.s.eng.stream));
+    AFESP_CUDA_CHECK(cudaStreamSynchronize(h.s.eng.stream));
+    h.s.n = n;
+  });
+}
+
+static void upload_eps(Handle& h, const double* eps) {
+  const int n = h.s.n;
+  AFESP_REQUIRE(eps != nullptr, "eps must not be null");
+  if ((int)h.s.eps.n != n) h.s.eps.alloc(n);
+  h.s.eps_host.assign(eps, eps + n);
+  AFESP_CUDA_CHECK(cudaMemcpyAsync(h.s.eps.p, eps, n * 8, cudaMemcpyHostToDevice, h.s.eng.stream));
+  AFESP_CUDA_CHECK(cudaStreamSynchronize(h.s.eng.stream));
+}
+
+int afesp_gpu_mp2_energy(afesp_handle hv, int nocc, const double* eps, double* e_mp2) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(h.s.n > 0 && h.s.eri_mo.p, "mp2_energy: no MO integrals on the device");
+    AFESP_REQUIRE(nocc > 0 && nocc < h.s.n && e_mp2, "mp2_energy: bad arguments");
+    upload_eps(h, eps);
+    if (h.s.red_out.n < 16) h.s.red_out.alloc(16);
+    StageTimer tm(&h);
+    mp2_energy(h.s.eng, h.s.n, nocc, h.s.eri_mo.p, h.s.eps.p, h.s.red_out.p);
+    tm.stop();
+    AFESP_CUDA_CHECK(cudaMemcpy(e_mp2, h.s.red_out.p, 8, cudaMemcpyDeviceToHost));
+  });
+}
+
+int afesp_gpu_ccsd_init(afesp_handle hv, int nocc, int restricted, const double* eps, int diis_n, double* e_mp1,
+                        double* rmst2) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(h.s.n > 0 && h.s.eri_mo.p, "ccsd_init: no MO integrals on the device");
+    AFESP_REQUIRE(nocc > 0 && nocc < h.s.n, "ccsd_init: bad nocc");
+    upload_eps(h, eps);
+    h.s.nocc_spatial = nocc;
+    h.s.T.clear();
+    StageTimer tm(&h);
+    if (restricted) ccsd_spatial_init(h.s, diis_n);
+    else ccsd_spinorb_init(h.s, diis_n);
+    cc_update_energy(h.s);  // the "MP1" line (src/ccsd.f90:325-331)
+    tm.stop();
+    if (e_mp1) *e_mp1 = h.s.energy;
+    if (rmst2) *rmst2 = h.s.rms;
+  });
+}
+
+int afesp_gpu_ccsd_iterate(afesp_handle hv, double* e_cc, double* rmst2) {
+  return guarded(hv, [&](Handle& h) {
+    assemble_finalize_checks(h);
+    AFESP_REQUIRE(!h.s.finalized, "ccsd_iterate: state already finalised");
+    StageTimer tm(&h);
+    cc_diis_stash(h.s);
+    if (h.s.restricted) ccsd_spatial_iterate(h.s);
+    else ccsd_spinorb_iterate(h.s);
+    cc_update_energy(h.s);
+    tm.stop();
+    if (e_cc) *e_cc = h.s.energy;
+    if (rmst2) *rmst2 = h.s.rms;
+  });
+}
+
+int afesp_gpu_ccsd_diis(afesp_handle hv) {
+  return guarded(hv, [&](Handle& h) {
+    assemble_finalize_checks(h);
+    StageTimer tm(&h);
+    cc_diis_update(h.s);
+    tm.stop();
+  });
+}
+
+int afesp_gpu_ccsd_finalize(afesp_handle hv, int want_cr, double* t1_diag, double* t1, double* t2) {
+  return guarded(hv, [&](Handle& h) {
+    assemble_finalize_checks(h);
+    CCState& s = h.s;
+    StageTimer tm(&h);
+    if (t1_diag) {
+      // sqrt(sum t1^2)/sqrt(nel), nel = number of electrons (src/ccsd.f90:372)
+      *t1_diag = std::sqrt(cc_t1_norm2(s)) / std::sqrt((double)(2 * s.nocc_spatial));
+    }
+    if (want_cr && !s.have_cr) {
+      AFESP_REQUIRE(s.restricted, "CR intermediates exist only in the spin-free formulation");
+      ccsd_spatial_cr_intermediates(s);
+    }
+    // release what the (T) stage does not need (the reference's cc_int goes out of scope, src/ccsd.f90:386-392)
+    s.diis = CCDiis();
+    for (const char* nm : {"v_vvvv", "W_efab", "vvvv", "ovvv", "W_vvov", "I_oooo", "I_ovov", "I_voov", "I_ooov_p",
+                           "x_voov", "c_oovv", "A_oovv", "W_ijmn", "W_ovvo", "tau", "tau_tilde"})
+      s.drop(nm);
+    s.t1n.free(); s.t2n.free(); s.t2_old.free();
+    s.eng.pool.clear();
+    s.finalized = true;
+    tm.stop();
+    if (t1) AFESP_CUDA_CHECK(cudaMemcpy(t1, s.t1.p(), s.t1.size() * 8, cudaMemcpyDeviceToHost));
+    if (t2) AFESP_CUDA_CHECK(cudaMemcpy(t2, s.t2.p(), s.t2.size() * 8, cudaMemcpyDeviceToHost));
+  });
+}
+
+static void allreduce_sum(Handle& h, double* vals, int n) {
+  if (!h.comm || h.nranks == 1) return;
+  if (h.s.red_out.n < 16) h.s.red_out.alloc(16);
+  AFESP_REQUIRE(n <= 16, "allreduce: too many values");
+  cudaStream_t st = h.s.eng.stream;
+  AFESP_CUDA_CHECK(cudaMemcpyAsync(h.s.red_out.p, vals, n * 8, cudaMemcpyHostToDevice, st));
+  int rc = g_nccl.AllReduce(h.s.red_out.p, h.s.red_out.p, (size_t)n, kNcclDouble, kNcclSum, h.comm, st);
+  if (rc != 0) throw Error(4, std::string("ncclAllReduce failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+  AFESP_CUDA_CHECK(cudaMemcpyAsync(vals, h.s.red_out.p, n * 8, cudaMemcpyDeviceToHost, st));
+  AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+int afesp_gpu_ccsd_t_spatial(afesp_handle hv, int paren, int renorm, int comp_renorm, double sums[6],
+                             double* denominator_constant) {
+  return guarded(hv, [&](Handle& h) {
+    assemble_finalize_checks(h);
+    AFESP_REQUIRE(sums != nullptr, "ccsd_t: sums must not be null");
+    StageTimer tm(&h);
+    triples_spatial(h.s, paren != 0, renorm != 0, comp_renorm != 0, h.rank, h.nranks, sums);
+    allreduce_sum(h, sums, 6);
+    double c = 0.0;
+    if (renorm || comp_renorm) c = triples_denominator_constant(h.s);
+    tm.stop();
+    if (denominator_constant) *denominator_constant = c;
+  });
+}
+
+int afesp_gpu_ccsd_t_spinorb(afesp_handle hv, double* e_T) {
+  return guarded(hv, [&](Handle& h) {
+    assemble_finalize_checks(h);
+    AFESP_REQUIRE(e_T != nullptr, "ccsd_t: e_T must not be null");
+    StageTimer tm(&h);
+    triples_spinorb(h.s, h.rank, h.nranks, e_T);
+    allreduce_sum(h, e_T, 1);
+    tm.stop();
+  });
+}
+
+int afesp_gpu_comm_unique_id(char id[128]) {
+  std::string err;
+  if (!id || !g_nccl.load(err)) { g_open_error = err; return 4; }
+  NcclId nid;
+  if (g_nccl.GetUniqueId(&nid) != 0) { g_open_error = "ncclGetUniqueId failed"; return 4; }
+  std::memcpy(id, nid.internal, 128);
+  return 0;
+}
+
+int afesp_gpu_comm_init(afesp_handle hv, int rank, int nranks, const char id[128]) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks && id, "comm_init: bad arguments");
+    std::string err;
+    if (!g_nccl.load(err)) throw Error(4, err);
+    NcclId nid;
+    std::memcpy(nid.internal, id, 128);
+    int rc = g_nccl.CommInitRank(&h.comm, nranks, nid, rank);
+    if (rc != 0) throw Error(4, std::string("ncclCommInitRank failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    h.rank = rank; h.nranks = nranks;
+  });
+}
+
+int afesp_gpu_set_partition(afesp_handle hv, int rank, int nranks) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "set_partition: bad arguments");
+    AFESP_REQUIRE(h.comm == nullptr, "set_partition: a communicator is attached");
+    h.rank = rank; h.nranks = nranks;
+  });
+}
+
+int afesp_gpu_triples_partition(int nocc_active, int symmetric, int strict, int nranks, long long* counts) {
+  if (nocc_active < 0 || nranks < 1 || !counts) return 1;
+  triples_partition_counts(nocc_active, symmetric != 0, strict != 0, nranks, counts);
+  return 0;
+}
+
+int afesp_gpu_dgemm_wrapper(afesp_handle hv, char ta, char tb, int M, int N, int K, const double* A, const double* B,
+                            double* C, double alpha, double beta) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(M >= 0 && N >= 0 && K >= 0 && C, "dgemm_wrapper: bad arguments");
+    const bool tA = (ta == 'T' || ta == 't'), tB = (tb == 'T' || tb == 't');
+    const long long lda = tA ? K : M, ldb = tB ? N : K;  // src/linalg.fpp:69-79
+    const size_t na = (size_t)M * K, nb = (size_t)K * N, nc = (size_t)M * N;
+    cudaStream_t st = h.s.eng.stream;
+    DBuf dA(std::max<size_t>(na, 1)), dB(std::max<size_t>(nb, 1)), dC(std::max<size_t>(nc, 1));
+    if (na) AFESP_CUDA_CHECK(cudaMemcpyAsync(dA.p, A, na * 8, cudaMemcpyHostToDevice, st));
+    if (nb) AFESP_CUDA_CHECK(cudaMemcpyAsync(dB.p, B, nb * 8, cudaMemcpyHostToDevice, st));
+    if (nc && beta != 0.0) AFESP_CUDA_CHECK(cudaMemcpyAsync(dC.p, C, nc * 8, cudaMemcpyHostToDevice, st));
+    StageTimer tm(&h);
+    dgemm(st, ta, tb, M, N, K, alpha, dA.p, std::max<long long>(lda, 1), dB.p, std::max<long long>(ldb, 1), beta, dC.p,
+          std::max(M, 1));
+    tm.stop();
+    if (nc) AFESP_CUDA_CHECK(cudaMemcpyAsync(C, dC.p, nc * 8, cudaMemcpyDeviceToHost, st));
+    AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int afesp_gpu_omp_reshape(afesp_handle hv, double* out_arr, const double* in_arr, const int in_dims[4],
+                          const char arr_order[4], int has_beta, double beta) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(out_arr && in_arr && in_dims && arr_order, "omp_reshape: null argument");
+    int perm[4], dims[4];
+    size_t total = 1;
+    for (int d = 0; d < 4; ++d) {
+      AFESP_REQUIRE(arr_order[d] >= '1' && arr_order[d] <= '4', "omp_reshape: arr_order must be a permutation of 1234");
+      perm[d] = arr_order[d] - '1';  // out axis d takes in axis perm[d]  (src/linalg.fpp:133-147)
+      dims[d] = in_dims[d];
+      AFESP_REQUIRE(dims[d] >= 0, "omp_reshape: negative extent");
+      total *= (size_t)dims[d];
+    }
+    if (total == 0) return;
+    cudaStream_t st = h.s.eng.stream;
+    DBuf din(total), dout(total);
+    AFESP_CUDA_CHECK(cudaMemcpyAsync(din.p, in_arr, total * 8, cudaMemcpyHostToDevice, st));
+    const double b = has_beta ? beta : 0.0;
+    if (b != 0.0) AFESP_CUDA_CHECK(cudaMemcpyAsync(dout.p, out_arr, total * 8, cudaMemcpyHostToDevice, st));
+    StageTimer tm(&h);
+    permute(st, 4, dims, perm, 1.0, din.p, b, dout.p);
+    tm.stop();
+    AFESP_CUDA_CHECK(cudaMemcpyAsync(out_arr, dout.p, total * 8, cudaMemcpyDeviceToHost, st));
+    AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int afesp_gpu_bench_dgemm(afesp_handle hv, char ta, char tb, int M, int N, int K, int reps, double* ms) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(M > 0 && N > 0 && K > 0 && reps > 0 && ms, "bench_dgemm: bad arguments");
+    const bool tA = (ta == 'T' || ta == 't'), tB = (tb == 'T' || tb == 't');
+    const long long lda = tA ? K : M, ldb = tB ? N : K;
+    cudaStream_t st = h.s.eng.stream;
+    DBuf dA((size_t)M * K), dB((size_t)K * N), dC((size_t)M * N);
+    fill(st, (long long)M * K, 1.0 / 3.0, dA.p);
+    fill(st, (long long)K * N, 3.0 / 7.0, dB.p);
+    dgemm(st, ta, tb, M, N, K, 1.0, dA.p, lda, dB.p, ldb, 0.0, dC.p, M);  // warm-up
+    AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
+    StageTimer tm(&h);
+    for (int r = 0; r < reps; ++r) dgemm(st, ta, tb, M, N, K, 1.0, dA.p, lda, dB.p, ldb, 0.0, dC.p, M);
+    tm.stop();
+    AFESP_CUDA_CHECK(cudaGetLastError());
+    *ms = h.last_ms / reps;
+  });
+}
+
+int afesp_gpu_dmma_peak(afesp_handle hv, double* tflops) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(tflops != nullptr, "dmma_peak: null output");
+    int sms = 0;
+    AFESP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h.device));
+    cudaStream_t st = h.s.eng.stream;
+    DBuf out(8);
+    const int iters = 20000, threads = 256, blocks = sms * 4;
+    k_dmma_peak<<<blocks, threads, 0, st>>>(out.p, 100);
+    AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
+    StageTimer tm(&h);
+    k_dmma_peak<<<blocks, threads, 0, st>>>(out.p, iters);
+    count_launch(2);
+    tm.stop();
+    AFESP_CUDA_CHECK(cudaGetLastError());
+    const double flops = 2.0 * 256.0 * 8.0 * iters * (threads / 32.0) * blocks;
+    *tflops = flops / (h.last_ms * 1e-3) / 1e12;
+  });
+}
+
+int afesp_gpu_last_stage_ms(afesp_handle hv, double* ms) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(ms != nullptr, "last_stage_ms: null output");
+    *ms = h.last_ms;
+  });
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,83 @@
+// Shared declarations for the AFESP B200 coupled-cluster engine (device side, sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace afesp {
+
+// ---- error handling: every failure becomes a C++ exception, turned into a status code at the C-ABI ----
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define AFESP_CUDA_CHECK(expr)                                                                    \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      throw ::afesp::Error(2, std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + \
+                                  __FILE__ + ":" + std::to_string(__LINE__));                     \
+  } while (0)
+
+#define AFESP_REQUIRE(cond, msg)                                                               \
+  do {                                                                                         \
+    if (!(cond))                                                                               \
+      throw ::afesp::Error(1, std::string(msg) + " (" #cond ") at " + __FILE__ + ":" +         \
+                                  std::to_string(__LINE__));                                   \
+  } while (0)
+
+// ---- launch accounting (bench.py reports gpu_launches from this counter) ----
+extern long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += n; }
+
+// ---- device buffer with ownership ----
+struct DBuf {
+  double* p = nullptr;
+  size_t n = 0;
+  DBuf() = default;
+  explicit DBuf(size_t count) { alloc(count); }
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DBuf& operator=(DBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DBuf() { release(); }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) AFESP_CUDA_CHECK(cudaMalloc(&p, count * sizeof(double)));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+};
+
+// ---- GEMM (gemm.cu): C = alpha*op(A)*op(B) + beta*C, column-major, FP64 DMMA tiles ----
+struct GemmBatch {
+  int count = 1;
+  long long strideA = 0, strideB = 0, strideC = 0;          // strided batching
+  const double* const* Aptr = nullptr;                      // or device pointer arrays (override strides)
+  const double* const* Bptr = nullptr;
+  double* const* Cptr = nullptr;
+  bool ptr_aligned16 = false;  // caller guarantees every A/B pointer in the arrays is 16-byte aligned
+};
+void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, double alpha, const double* A,
+           long long lda, const double* B, long long ldb, double beta, double* C, long long ldc,
+           const GemmBatch* batch = nullptr);
+// Executed DMMA flop counter (2*M*N*K per gemm), for "% of FP64 tensor peak" from executed flops.
+extern double g_gemm_flops;
+
+// ---- permute (permute.cu): out = alpha * permute(in) + beta * out for rank <= 6 ----
+// perm[d] = which input axis becomes output axis d (numpy transpose convention), dims = input extents,
+// column-major (axis 0 fastest) on both sides.
+void permute(cudaStream_t st, int rank, const int* dims, const int* perm, double alpha, const double* in,
+             double beta, double* out);
+
+}  // namespace afesp

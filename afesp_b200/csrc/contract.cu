@@ -1,0 +1,211 @@
+// einsum front end: lowers a pairwise tensor contraction to permutes + one FP64 DMMA GEMM.
+//
+// The reference hand-codes every contraction of src/ccsd.f90 as "omp_reshape, dgemm_wrapper, omp_reshape" or as a
+// naive OpenMP loop nest.  Here each one is a single labelled statement; operands that are
+// already laid out as a GEMM matrix (possibly transposed) are consumed in place, so e.g. the particle-particle
+// ladder c(ij,ef)*v(ef,ab) runs with no data movement besides the GEMM itself.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+
+#include "tensor.cuh"
+
+namespace afesp {
+
+// ---------------------------------------------------------------- Pool
+double* Pool::get(size_t n) {
+  if (n == 0) n = 1;
+  auto it = free_.lower_bound(n);
+  if (it != free_.end() && it->first <= 2 * n + 1024) {
+    double* p = it->second;
+    live_[p] = it->first;
+    free_.erase(it);
+    return p;
+  }
+  double* p = nullptr;
+  cudaError_t err = cudaMalloc(&p, n * sizeof(double));
+  if (err != cudaSuccess) {
+    cudaGetLastError();
+    for (auto& kv : free_) { cudaFree(kv.second); held_ -= kv.first * sizeof(double); }
+    free_.clear();
+    AFESP_CUDA_CHECK(cudaMalloc(&p, n * sizeof(double)));
+  }
+  held_ += n * sizeof(double);
+  live_[p] = n;
+  return p;
+}
+
+void Pool::put(double* p) {
+  auto it = live_.find(p);
+  if (it == live_.end()) return;
+  free_.emplace(it->second, p);
+  live_.erase(it);
+}
+
+void Pool::clear() {
+  for (auto& kv : free_) cudaFree(kv.second);
+  for (auto& kv : live_) cudaFree(kv.first);
+  free_.clear();
+  live_.clear();
+  held_ = 0;
+}
+
+// ---------------------------------------------------------------- helpers
+namespace {
+
+std::string filter(const std::string& s, const std::string& set) {
+  std::string r;
+  for (char c : s) if (set.find(c) != std::string::npos) r.push_back(c);
+  return r;
+}
+
+void split_spec(const char* spec, std::vector<std::string>& ins, std::string& out) {
+  std::string s(spec);
+  s.erase(std::remove(s.begin(), s.end(), ' '), s.end());
+  size_t arrow = s.find("->");
+  AFESP_REQUIRE(arrow != std::string::npos, "einsum spec needs '->'");
+  out = s.substr(arrow + 2);
+  std::string lhs = s.substr(0, arrow);
+  size_t pos = 0;
+  while (true) {
+    size_t c = lhs.find(',', pos);
+    ins.push_back(lhs.substr(pos, c == std::string::npos ? std::string::npos : c - pos));
+    if (c == std::string::npos) break;
+    pos = c + 1;
+  }
+}
+
+void do_permute(Engine& e, const std::string& from, const std::string& to, const std::vector<int>& dims_from,
+                double alpha, const double* in, double beta, double* out) {
+  int rank = (int)from.size();
+  AFESP_REQUIRE(to.size() == from.size(), "transpose: label count mismatch");
+  if (rank == 0) {  // scalar
+    int one = 1, zero = 0;
+    permute(e.stream, 1, &one, &zero, alpha, in, beta, out);
+    return;
+  }
+  int perm[6], dims[6];
+  AFESP_REQUIRE(rank <= 6, "transpose: rank > 6");
+  for (int d = 0; d < rank; ++d) {
+    size_t k = from.find(to[d]);
+    AFESP_REQUIRE(k != std::string::npos, "transpose: unknown output label");
+    perm[d] = (int)k;
+    dims[d] = dims_from[d];
+  }
+  permute(e.stream, rank, dims, perm, alpha, in, beta, out);
+}
+
+}  // namespace
+
+void transpose(Engine& e, const char* spec, double alpha, const TView& in, double beta, const TView& out) {
+  std::vector<std::string> ins;
+  std::string so;
+  split_spec(spec, ins, so);
+  AFESP_REQUIRE(ins.size() == 1, "transpose: exactly one input");
+  AFESP_REQUIRE(ins[0].size() == in.dims.size() && so.size() == out.dims.size(), "transpose: rank mismatch");
+  for (size_t d = 0; d < so.size(); ++d) {
+    size_t k = ins[0].find(so[d]);
+    AFESP_REQUIRE(k != std::string::npos && in.dims[k] == out.dims[d], "transpose: extent mismatch");
+  }
+  do_permute(e, ins[0], so, in.dims, alpha, in.p, beta, out.p);
+}
+
+void einsum(Engine& e, const char* spec, double alpha, const TView& A_, const TView& B_, double beta,
+            const TView& C) {
+  std::vector<std::string> ins;
+  std::string sc;
+  split_spec(spec, ins, sc);
+  AFESP_REQUIRE(ins.size() == 2, "einsum: exactly two inputs");
+  std::string sa = ins[0], sb = ins[1];
+  TView A = A_, B = B_;
+  AFESP_REQUIRE(sa.size() == A.dims.size() && sb.size() == B.dims.size() && sc.size() == C.dims.size(),
+                std::string("einsum rank mismatch in ") + spec);
+  int ext[256];
+  std::memset(ext, 0, sizeof(ext));
+  auto reg = [&](const std::string& s, const std::vector<int>& d) {
+    for (size_t i = 0; i < s.size(); ++i) {
+      unsigned char c = (unsigned char)s[i];
+      AFESP_REQUIRE(ext[c] == 0 || ext[c] == d[i], std::string("einsum extent mismatch in ") + spec);
+      ext[c] = d[i];
+    }
+  };
+  reg(sa, A.dims); reg(sb, B.dims); reg(sc, C.dims);
+  std::string I, J, K;
+  for (char c : sa) {
+    bool inb = sb.find(c) != std::string::npos, inc = sc.find(c) != std::string::npos;
+    AFESP_REQUIRE(inb != inc, std::string("einsum: label must be in exactly two tensors: ") + spec);
+    (inc ? I : K).push_back(c);
+  }
+  for (char c : sb) {
+    bool ina = sa.find(c) != std::string::npos, inc = sc.find(c) != std::string::npos;
+    AFESP_REQUIRE(ina != inc, std::string("einsum: label must be in exactly two tensors: ") + spec);
+    if (inc) J.push_back(c);
+  }
+  AFESP_REQUIRE(I.size() + J.size() == sc.size(), std::string("einsum: output labels unmatched: ") + spec);
+
+  std::string cI = filter(sc, I), cJ = filter(sc, J);
+  bool direct = (sc == cI + cJ);
+  if (!direct && sc == cJ + cI) {  // C is (J,I): solve the transposed problem C^T = B^T A^T
+    std::swap(A, B); std::swap(sa, sb); std::swap(I, J); std::swap(cI, cJ);
+    direct = true;
+  }
+  std::string Iord = direct ? cI : filter(sa, I);
+  std::string Jord = direct ? cJ : filter(sb, J);
+  auto prod = [&](const std::string& s) { long long p = 1; for (char c : s) p *= ext[(unsigned char)c]; return p; };
+  const long long M = prod(Iord), N = prod(Jord), Kd = prod(K);
+  AFESP_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && Kd < (1LL << 31), "einsum: matrix extent overflows int32");
+
+  std::string kA = filter(sa, K), kB = filter(sb, K), Kord = kA;
+  auto a_ok = [&](const std::string& ko) { return sa == Iord + ko || sa == ko + Iord; };
+  auto b_ok = [&](const std::string& ko) { return sb == ko + Jord || sb == Jord + ko; };
+  {
+    long long costA = (a_ok(kA) ? 0 : A.size()) + (b_ok(kA) ? 0 : B.size());
+    long long costB = (a_ok(kB) ? 0 : A.size()) + (b_ok(kB) ? 0 : B.size());
+    if (costB < costA) Kord = kB;
+  }
+
+  // operand A as (I x K): 'N' when stored (I,K), 'T' when stored (K,I), otherwise permuted into (I,K)
+  char ta = 'N';
+  long long lda = M;
+  const double* pa = A.p;
+  std::unique_ptr<Scratch> sA, sB, sT;
+  const bool a_nk = (sa == Iord + Kord), a_kn = (sa == Kord + Iord);
+  if (a_kn && (M == 1 || !a_nk)) {
+    ta = 'T'; lda = Kd;
+  } else if (a_nk) {
+    ta = 'N'; lda = M;
+  } else {
+    sA.reset(new Scratch(e.pool, (size_t)A.size()));
+    do_permute(e, sa, Iord + Kord, A.dims, 1.0, A.p, 0.0, sA->p);
+    pa = sA->p; ta = 'N'; lda = M;
+  }
+  // operand B as (K x J): 'N' when stored (K,J), 'T' when stored (J,K), otherwise permuted into (K,J)
+  char tb = 'N';
+  long long ldb = Kd;
+  const double* pb = B.p;
+  const bool b_kn = (sb == Kord + Jord), b_nk = (sb == Jord + Kord);
+  if (b_kn && !(Kd == 1 && b_nk)) {
+    tb = 'N'; ldb = Kd;
+  } else if (b_nk) {
+    tb = 'T'; ldb = N;
+  } else {
+    sB.reset(new Scratch(e.pool, (size_t)B.size()));
+    do_permute(e, sb, Kord + Jord, B.dims, 1.0, B.p, 0.0, sB->p);
+    pb = sB->p; tb = 'N'; ldb = Kd;
+  }
+  if (lda < 1) lda = 1;
+  if (ldb < 1) ldb = 1;
+
+  if (direct) {
+    dgemm(e.stream, ta, tb, (int)M, (int)N, (int)Kd, alpha, pa, lda, pb, ldb, beta, C.p, M);
+  } else {
+    sT.reset(new Scratch(e.pool, (size_t)(M * N)));
+    dgemm(e.stream, ta, tb, (int)M, (int)N, (int)Kd, alpha, pa, lda, pb, ldb, 0.0, sT->p, M);
+    std::string st = Iord + Jord;
+    std::vector<int> tdims;
+    for (char c : st) tdims.push_back(ext[(unsigned char)c]);
+    do_permute(e, st, sc, tdims, 1.0, sT->p, beta, C.p);
+  }
+}
+
+}  // namespace afesp

@@ -1,0 +1,354 @@
+// FP64 tensor-core GEMM for sm_100a:  C = alpha * op(A) * op(B) + beta * C   (column-major, BLAS semantics)
+//
+// Replaces the reference's dgemm_wrapper -> OpenBLAS dgemm (src/linalg.fpp:58-89) for every dense contraction
+// of the coupled-cluster path (call-site list: SURVEY.md §2.3).
+//
+// Hardware mapping.  On Blackwell the FP64 tensor path is the warp-level DMMA: ptxas lowers every
+// mma.sync .f64 shape (m16n8k4/8/16 included) to DMMA.8x8x4 on sm_100a, so the kernel issues the native
+// m8n8k4 shape directly.  tcgen05/TMEM have no f64 kind.  One DMMA.8x8x4 = 256 FMA per warp instruction.
+//
+// Tiling.  A CTA owns a BM x BN tile of C; its warps own WM x WN sub-tiles made of 8x8 DMMA accumulators
+// kept in registers.  Operand tiles (BM x BK and BK x BN doubles) are staged global -> shared by an
+// asynchronous-copy ring of STAGES slots so that loads of tile k+STAGES-1 overlap the DMMAs of tile k.
+// Shared tiles keep the operand's own contiguous direction ("MN-major" for A^N / B^T, "K-major" for A^T / B^N)
+// and are padded so that the row stride is 4 (mod 16) 8-byte words: a DMMA fragment load by a half-warp
+// (4 groups x 4 lanes) then touches 16 distinct banks -- conflict-free for both orientations.
+//
+// Skinny problems (M*N tile count below the SM count with a long K) are split along K into a workspace and
+// reduced by a second kernel, deterministically (no atomics).
+#include "common.cuh"
+
+namespace afesp {
+
+long long g_launch_count = 0;
+double g_gemm_flops = 0.0;
+
+namespace {
+
+constexpr int PAD = 4;  // doubles of row padding -> row stride = 4 (mod 16) words
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Shared-memory operand tile: logical (mn, k), mn in [0,BMN), k in [0,BK).
+template <int BMN, int BK, bool KMAJOR>
+struct Tile {
+  static constexpr int LD = KMAJOR ? (BK + PAD) : (BMN + PAD);
+  static constexpr int SIZE = KMAJOR ? (BMN * LD) : (BK * LD);
+  __device__ static __forceinline__ int off(int mn, int k) { return KMAJOR ? (mn * LD + k) : (k * LD + mn); }
+};
+
+// Asynchronous copy of one operand tile.  X(mn,k) lives at X[mn*1 + k*ld] (MN-major) or X[k*1 + mn*ld]
+// (K-major).  Out-of-range elements are zero-filled by the copy unit (src-size 0).  VEC=2 moves 16-byte
+// chunks and requires a 16-byte aligned base and an even ld; VEC=1 is the any-alignment path.
+template <int BMN, int BK, bool KMAJOR, int VEC, int NT>
+__device__ __forceinline__ void load_tile(double* smem, const double* __restrict__ X, long long ld, int mn0, int k0,
+                                          int MN, int Kend, int tid) {
+  using T = Tile<BMN, BK, KMAJOR>;
+  constexpr int ROWLEN = KMAJOR ? BK : BMN;       // contiguous extent of one tile row
+  constexpr int NROWS = KMAJOR ? BMN : BK;
+  constexpr int CPR = ROWLEN / VEC;               // chunks per row
+  constexpr int TOTAL = CPR * NROWS;
+  static_assert(TOTAL % NT == 0, "tile copy must divide evenly over the CTA");
+#pragma unroll
+  for (int i = 0; i < TOTAL / NT; ++i) {
+    int c = tid + i * NT;
+    int r = c / CPR;
+    int cc = (c % CPR) * VEC;
+    int mn = KMAJOR ? (mn0 + r) : (mn0 + cc);
+    int k = KMAJOR ? (k0 + cc) : (k0 + r);
+    int lim_c = KMAJOR ? (Kend - k) : (MN - mn);    // valid elements along the contiguous direction
+    bool row_ok = KMAJOR ? (mn < MN) : (k < Kend);
+    int valid = row_ok ? (lim_c < 0 ? 0 : (lim_c > VEC ? VEC : lim_c)) : 0;
+    const double* src = valid ? (KMAJOR ? (X + (long long)mn * ld + k) : (X + (long long)k * ld + mn)) : X;
+    double* dst = smem + r * T::LD + cc;
+    if (VEC == 2) cp_async16(dst, src, valid * 8);
+    else cp_async8(dst, src, valid * 8);
+  }
+}
+
+struct Params {
+  const double* A;
+  const double* B;
+  double* C;
+  int M, N, K;
+  long long lda, ldb, ldc;
+  double alpha, beta;
+  long long sA, sB, sC;  // batch strides
+  const double* const* Ap;
+  const double* const* Bp;
+  double* const* Cp;
+  int splitk;            // >1: write raw partials to ws[split][M*N]
+  int kchunk;            // K extent per split (multiple of BK)
+  double* ws;
+};
+
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool AK, bool BKM, int VEC>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) gemm_f64_dmma(const Params p) {
+  constexpr int NT = (BM / WM) * (BN / WN) * 32;
+  using TA = Tile<BM, BK, AK>;
+  using TB = Tile<BN, BK, BKM>;
+  constexpr int STAGE_DOUBLES = TA::SIZE + TB::SIZE;
+  extern __shared__ __align__(16) double smem[];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int wm0 = (warp % (BM / WM)) * WM;
+  const int wn0 = (warp / (BM / WM)) * WN;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  int batch = blockIdx.z, split = 0;
+  if (p.splitk > 1) { split = blockIdx.z % p.splitk; batch = blockIdx.z / p.splitk; }
+  const double* A = p.Ap ? p.Ap[batch] : p.A + batch * p.sA;
+  const double* B = p.Bp ? p.Bp[batch] : p.B + batch * p.sB;
+  double* C = p.Cp ? p.Cp[batch] : p.C + batch * p.sC;
+
+  const int kbeg = split * p.kchunk;
+  const int kend = (p.splitk > 1) ? min(p.K, kbeg + p.kchunk) : p.K;
+  const int nk = (kend - kbeg + BK - 1) / BK;
+
+  constexpr int MT = WM / 8, NTL = WN / 8;
+  double acc[MT][NTL][2];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NTL; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  auto issue = [&](int kt) {
+    if (kt < nk) {
+      double* sa = smem + (kt % STAGES) * STAGE_DOUBLES;
+      double* sb = sa + TA::SIZE;
+      load_tile<BM, BK, AK, VEC, NT>(sa, A, p.lda, m0, kbeg + kt * BK, p.M, kend, tid);
+      load_tile<BN, BK, BKM, VEC, NT>(sb, B, p.ldb, n0, kbeg + kt * BK, p.N, kend, tid);
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) issue(s);
+
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    issue(kt + STAGES - 1);  // refills the slot consumed in iteration kt-1 (all warps are past it)
+    const double* sa = smem + (kt % STAGES) * STAGE_DOUBLES;
+    const double* sb = sa + TA::SIZE;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double af[MT], bf[NTL];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) af[i] = sa[TA::off(wm0 + 8 * i + gid, kk + tig)];
+#pragma unroll
+      for (int j = 0; j < NTL; ++j) bf[j] = sb[TB::off(wn0 + 8 * j + gid, kk + tig)];
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // Epilogue straight from the accumulator fragments: thread holds C(row = gid, cols = 2*tig, 2*tig+1).
+  if (p.splitk > 1) {
+    double* W = p.ws + ((long long)batch * p.splitk + split) * (long long)p.M * p.N;
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      int m = m0 + wm0 + 8 * i + gid;
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < NTL; ++j) {
+        int n = n0 + wn0 + 8 * j + 2 * tig;
+        if (n < p.N) W[m + (long long)n * p.M] = acc[i][j][0];
+        if (n + 1 < p.N) W[m + (long long)(n + 1) * p.M] = acc[i][j][1];
+      }
+    }
+    return;
+  }
+  const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    int m = m0 + wm0 + 8 * i + gid;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < NTL; ++j) {
+      int n = n0 + wn0 + 8 * j + 2 * tig;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (n + e < p.N) {
+          double* c = C + m + (long long)(n + e) * p.ldc;
+          double v = alpha * acc[i][j][e];
+          if (beta != 0.0) v += beta * (*c);
+          *c = v;
+        }
+      }
+    }
+  }
+}
+
+// C = alpha * sum_s W[s] + beta * C  (split-K reduction; fixed summation order)
+__global__ void splitk_reduce(const double* __restrict__ W, int splitk, int M, int N, double alpha, double beta,
+                              double* __restrict__ C, long long ldc) {
+  long long MN = (long long)M * N;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < MN;
+       idx += (long long)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < splitk; ++k) s += W[k * MN + idx];
+    int m = (int)(idx % M);
+    long long n = idx / M;
+    double* c = C + m + n * ldc;
+    double v = alpha * s;
+    if (beta != 0.0) v += beta * (*c);
+    *c = v;
+  }
+}
+
+// C = beta * C for the degenerate K == 0 / alpha == 0 case
+__global__ void scale_c(double* C, int M, int N, long long ldc, double beta) {
+  long long MN = (long long)M * N;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < MN;
+       idx += (long long)gridDim.x * blockDim.x) {
+    double* c = C + (idx % M) + (idx / M) * ldc;
+    *c = (beta == 0.0) ? 0.0 : beta * (*c);
+  }
+}
+
+int g_num_sms = 0;
+DBuf g_ws;  // split-K workspace, grown on demand
+
+int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    AFESP_CUDA_CHECK(cudaGetDevice(&dev));
+    AFESP_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return g_num_sms;
+}
+
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool AK, bool BKM, int VEC>
+void launch_cfg(cudaStream_t st, const Params& p, int nbatch) {
+  constexpr int NT = (BM / WM) * (BN / WN) * 32;
+  constexpr size_t SMEM = (size_t)STAGES * (Tile<BM, BK, AK>::SIZE + Tile<BN, BK, BKM>::SIZE) * sizeof(double);
+  auto kern = gemm_f64_dmma<BM, BN, BK, WM, WN, STAGES, AK, BKM, VEC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AFESP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    attr_set = true;
+  }
+  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, nbatch * (p.splitk > 1 ? p.splitk : 1));
+  AFESP_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm grid too large");
+  kern<<<grid, NT, SMEM, st>>>(p);
+  count_launch();
+  AFESP_CUDA_CHECK(cudaGetLastError());
+}
+
+template <int BM, int BN, int WM, int WN, int STAGES>
+void launch_tile(cudaStream_t st, const Params& p, int nbatch, bool ak, bool bk, bool vec2) {
+  constexpr int BK = 16;
+#define AFESP_GEMM_CASE(AKv, BKv, V) launch_cfg<BM, BN, BK, WM, WN, STAGES, AKv, BKv, V>(st, p, nbatch)
+  if (vec2) {
+    if (ak) { if (bk) AFESP_GEMM_CASE(true, true, 2); else AFESP_GEMM_CASE(true, false, 2); }
+    else    { if (bk) AFESP_GEMM_CASE(false, true, 2); else AFESP_GEMM_CASE(false, false, 2); }
+  } else {
+    if (ak) { if (bk) AFESP_GEMM_CASE(true, true, 1); else AFESP_GEMM_CASE(true, false, 1); }
+    else    { if (bk) AFESP_GEMM_CASE(false, true, 1); else AFESP_GEMM_CASE(false, false, 1); }
+  }
+#undef AFESP_GEMM_CASE
+}
+
+}  // namespace
+
+void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, double alpha, const double* A,
+           long long lda, const double* B, long long ldb, double beta, double* C, long long ldc,
+           const GemmBatch* batch) {
+  AFESP_REQUIRE(M >= 0 && N >= 0 && K >= 0, "dgemm: negative dimension");
+  if (M == 0 || N == 0) return;
+  const int nbatch = batch ? batch->count : 1;
+  if (nbatch == 0) return;
+  const bool ta = (transA == 'T' || transA == 't'), tb = (transB == 'T' || transB == 't');
+  AFESP_REQUIRE(ta || transA == 'N' || transA == 'n', "dgemm: transA must be N or T");
+  AFESP_REQUIRE(tb || transB == 'N' || transB == 'n', "dgemm: transB must be N or T");
+  if (K == 0 || alpha == 0.0) {
+    AFESP_REQUIRE(nbatch == 1, "dgemm: K==0 batched not supported");
+    scale_c<<<std::min<long long>(((long long)M * N + 255) / 256, 4096), 256, 0, st>>>(C, M, N, ldc, beta);
+    count_launch();
+    return;
+  }
+  Params p{};
+  p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K;
+  p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.alpha = alpha; p.beta = beta;
+  if (batch) {
+    p.sA = batch->strideA; p.sB = batch->strideB; p.sC = batch->strideC;
+    p.Ap = batch->Aptr; p.Bp = batch->Bptr; p.Cp = batch->Cptr;
+  }
+  p.splitk = 1;
+  const bool ak = ta;    // op(A)(m,k) contiguous in k  <=> transA == 'T'
+  const bool bk = !tb;   // op(B)(k,n) contiguous in k  <=> transB == 'N'
+  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  bool vec2 = (lda % 2 == 0) && (ldb % 2 == 0);
+  if (batch && (batch->Aptr || batch->Bptr)) vec2 = vec2 && batch->ptr_aligned16;  // alignment is the caller's promise
+  else vec2 = vec2 && aligned16(A) && aligned16(B) && (!batch || (batch->strideA % 2 == 0 && batch->strideB % 2 == 0));
+
+  g_gemm_flops += 2.0 * M * N * (double)K * nbatch;
+
+  // tile selection: big square tile when both extents are large, skinny variants otherwise
+  enum { L, S, TM, TN } cfg;
+  if (M <= 32 && N > 64) cfg = TM;
+  else if (N <= 32 && M > 64) cfg = TN;
+  else if (M >= 96 && N >= 96) cfg = L;
+  else cfg = S;
+  const int bm = (cfg == L) ? 128 : (cfg == S ? 64 : (cfg == TM ? 32 : 128));
+  const int bn = (cfg == L) ? 128 : (cfg == S ? 64 : (cfg == TM ? 128 : 32));
+  long long tiles = (long long)((M + bm - 1) / bm) * ((N + bn - 1) / bn) * nbatch;
+  if (cfg == L && tiles < num_sms() && (long long)((M + 63) / 64) * ((N + 63) / 64) * nbatch >= tiles * 2) {
+    // not enough 128x128 tiles to fill the chip: fall back to 64x64 tiles (more CTAs, 3 resident per SM)
+    cfg = S;
+    tiles = (long long)((M + 63) / 64) * ((N + 63) / 64) * nbatch;
+  }
+  // split-K for skinny outputs with a long reduction
+  if (nbatch == 1 && tiles * 2 <= num_sms() && K >= 512) {
+    int want = (int)std::min<long long>(num_sms() * 2 / tiles, (K + 127) / 128);
+    if (want > 1) {
+      int kchunk = ((K + want - 1) / want + 15) / 16 * 16;
+      int splits = (K + kchunk - 1) / kchunk;
+      if (splits > 1) {
+        p.splitk = splits; p.kchunk = kchunk;
+        size_t need = (size_t)splits * M * N;
+        if (g_ws.n < need) g_ws.alloc(need);
+        p.ws = g_ws.p;
+      }
+    }
+  }
+  switch (cfg) {
+    case L: launch_tile<128, 128, 64, 32, 3>(st, p, nbatch, ak, bk, vec2); break;
+    case S: launch_tile<64, 64, 32, 32, 3>(st, p, nbatch, ak, bk, vec2); break;
+    case TM: launch_tile<32, 128, 32, 32, 3>(st, p, nbatch, ak, bk, vec2); break;
+    case TN: launch_tile<128, 32, 32, 32, 3>(st, p, nbatch, ak, bk, vec2); break;
+  }
+  if (p.splitk > 1) {
+    long long MN = (long long)M * N;
+    splitk_reduce<<<(int)std::min<long long>((MN + 255) / 256, 2048), 256, 0, st>>>(p.ws, p.splitk, M, N, alpha,
+                                                                                   beta, C, ldc);
+    count_launch();
+    AFESP_CUDA_CHECK(cudaGetLastError());
+  }
+}
+
+}  // namespace afesp

@@ -1,0 +1,226 @@
+// Packed-ERI kernels: AO->MO transformation, MP2 energy, and the integral slices the CC drivers consume.
+//
+// Replaces src/mp2.f90:285-438 (four O(n^5) quarter transforms over dense n^4 temporaries, serial repack, MP2 sum)
+// and the gathers of src/ccsd.f90:111-143,182-194 (spin-orbital <pq||rs>) and :496-512 (spin-free slices).
+//
+// Packing (src/integrals.f90:196-210, 0-based here): pair(i,j) = max(max+1)/2 + min; eri[pair(pair(i,j),pair(k,l))].
+// 64-bit indices throughout (the reference's default-integer neri overflows at nbf = 400).
+//
+// AO->MO is done as two half transforms over *pair-packed* matrices instead of dense n^4 arrays:
+//   phase 1:  H(kl, pq) = sum_ij C(p,i) C(q,j) (ij|kl)        (kl = spectator pair, p>=q packed)
+//   phase 2:  (pq|rs)   = sum_kl C(r,k) C(s,l) H(kl, pq)      (pq = spectator pair, r>=s packed)
+// Each phase processes spectator blocks:  unpack -> DMMA GEMM -> batched DMMA GEMM -> pack.  Flops 8 n^3 npair
+// (half the dense 8 n^5), peak extra memory npair^2 doubles (51 GB at n=400 vs 2 x 205 GB dense).
+#include "integrals.cuh"
+
+#include <algorithm>
+
+#include "kernels.cuh"
+
+namespace afesp {
+namespace {
+
+__host__ __device__ __forceinline__ long long tri(long long i, long long j) {
+  return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i;
+}
+
+// X(xb, k, l) = src(x0+xb ; pair(k,l)),  xb fastest.
+// mode 0: src is the packed triangular ERI array: src[tri(x, kl)]
+// mode 1: src is a full matrix S[kl + ld * x]   (spectator is the *column*; used by phase 2 on H(kl,pq))
+__global__ void k_unpack_pairs(double* __restrict__ X, const double* __restrict__ src, int mode, long long ld,
+                               long long x0, int nb, int n) {
+  const long long total = (long long)nb * n * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int xb = (int)(idx % nb);
+    long long kl = idx / nb;
+    int k = (int)(kl % n), l = (int)(kl / n);
+    long long pr = tri(k, l);
+    X[idx] = mode == 0 ? src[tri(x0 + xb, pr)] : src[pr + ld * (x0 + xb)];
+  }
+}
+
+// Variant for mode 1 that reads S coalesced along kl and writes X coalesced along xb (32x32 smem transpose over
+// (pair index, spectator)).  Grid: (ceil(npair/32), ceil(nb/32)).  Writes both X(xb,k,l) and X(xb,l,k).
+__global__ void k_unpack_pairs_T(double* __restrict__ X, const double* __restrict__ S, long long ld, long long x0,
+                                 int nb, int n, long long npair) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const long long pr0 = (long long)blockIdx.x * 32;
+  const int xb0 = blockIdx.y * 32;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    long long pr = pr0 + tx;
+    int xb = xb0 + r;
+    if (pr < npair && xb < nb) tile[r][tx] = S[pr + ld * (x0 + xb)];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    long long pr = pr0 + r;
+    int xb = xb0 + tx;
+    if (pr < npair && xb < nb) {
+      // invert pr -> (k >= l)
+      long long k = (long long)((sqrt(8.0 * (double)pr + 1.0) - 1.0) * 0.5);
+      while (k * (k + 1) / 2 > pr) --k;
+      while ((k + 1) * (k + 2) / 2 <= pr) ++k;
+      long long l = pr - k * (k + 1) / 2;
+      double v = tile[tx][r];
+      X[xb + (long long)nb * (k + n * l)] = v;
+      X[xb + (long long)nb * (l + n * k)] = v;
+    }
+  }
+}
+
+// dest(x0+xb ; pair(r,s)) = Z(xb, r, s) for r >= s.
+// mode 0: dest is a full matrix D[x + ld * pair]   (phase 1: H(kl,pq), spectator = row, coalesced along xb)
+// mode 1: dest is the packed triangular array, only pair <= x is stored: D[tri(x, pair)]   (phase 2)
+__global__ void k_pack_pairs(double* __restrict__ D, const double* __restrict__ Z, int mode, long long ld, long long x0,
+                             int nb, int n) {
+  const long long total = (long long)nb * n * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int xb = (int)(idx % nb);
+    long long rs = idx / nb;
+    int r = (int)(rs % n), s = (int)(rs / n);
+    if (r < s) continue;
+    long long pr = tri(r, s), x = x0 + xb;
+    if (mode == 0) D[x + ld * pr] = Z[idx];
+    else if (pr <= x) D[x * (x + 1) / 2 + pr] = Z[idx];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_mp2(const double* __restrict__ g, const double* __restrict__ eps, int n, int o,
+                                              double* __restrict__ partials) {
+  const int v = n - o;
+  const long long total = (long long)o * o * v * v;
+  double acc = 0.0;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int b = (int)(idx % v) + o;
+    long long t = idx / v;
+    int a = (int)(t % v) + o;
+    t /= v;
+    int j = (int)(t % o), i = (int)(t / o);
+    long long ia = tri(i, a), jb = tri(j, b), ib = tri(i, b), ja = tri(j, a);
+    double iajb = g[tri(ia, jb)];
+    acc += iajb * (2.0 * iajb - g[tri(ib, ja)]) / (eps[i] + eps[j] - eps[a] - eps[b]);
+  }
+  __shared__ double sh[8];
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += sh[w];
+    partials[blockIdx.x] = s;
+  }
+}
+
+struct SliceSpec { int lo[4], n[4]; };
+
+// out(p,q,r,s) = <PQ|RS> = (PR|QS), P = lo0+p, ... (physicist order, src/ccsd.f90:500-501)
+__global__ void k_slice_phys(double* __restrict__ out, const double* __restrict__ g, SliceSpec sp) {
+  const long long total = (long long)sp.n[0] * sp.n[1] * sp.n[2] * sp.n[3];
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long t = idx;
+    int p = (int)(t % sp.n[0]) + sp.lo[0]; t /= sp.n[0];
+    int q = (int)(t % sp.n[1]) + sp.lo[1]; t /= sp.n[1];
+    int r = (int)(t % sp.n[2]) + sp.lo[2]; t /= sp.n[2];
+    int s = (int)t + sp.lo[3];
+    out[idx] = g[tri(tri(p, r), tri(q, s))];
+  }
+}
+
+// out(P,Q,R,S) = <PQ||RS> over spin-orbitals (even = alpha, odd = beta of spatial orbital P/2), src/ccsd.f90:111-143
+__global__ void k_slice_spinorb(double* __restrict__ out, const double* __restrict__ g, SliceSpec sp) {
+  const long long total = (long long)sp.n[0] * sp.n[1] * sp.n[2] * sp.n[3];
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long t = idx;
+    int P = (int)(t % sp.n[0]) + sp.lo[0]; t /= sp.n[0];
+    int Q = (int)(t % sp.n[1]) + sp.lo[1]; t /= sp.n[1];
+    int R = (int)(t % sp.n[2]) + sp.lo[2]; t /= sp.n[2];
+    int S = (int)t + sp.lo[3];
+    int p = P >> 1, q = Q >> 1, r = R >> 1, s = S >> 1;
+    double val = 0.0;
+    if ((P & 1) == (R & 1) && (Q & 1) == (S & 1)) val += g[tri(tri(p, r), tri(q, s))];
+    if ((P & 1) == (S & 1) && (Q & 1) == (R & 1)) val -= g[tri(tri(p, s), tri(q, r))];
+    out[idx] = val;
+  }
+}
+
+inline int grid_for(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 16)); }
+
+// One half transform over spectator blocks (see file header).
+void half_transform(Engine& e, int n, const double* C, const double* src, int src_mode, long long src_ld, double* dst,
+                    int dst_mode, long long dst_ld, long long nspect, long long max_block_bytes) {
+  const long long n2 = (long long)n * n;
+  const long long npair = (long long)n * (n + 1) / 2;
+  long long nb = std::max<long long>(1, std::min<long long>(nspect, max_block_bytes / (3 * n2 * 8)));
+  if (nb > 16) nb = nb / 16 * 16;
+  Scratch X(e.pool, (size_t)(nb * n2)), Y(e.pool, (size_t)(nb * n2)), Z(e.pool, (size_t)(nb * n2));
+  for (long long x0 = 0; x0 < nspect; x0 += nb) {
+    const int cb = (int)std::min<long long>(nb, nspect - x0);
+    if (src_mode == 0) {
+      k_unpack_pairs<<<grid_for((long long)cb * n2), 256, 0, e.stream>>>(X.p, src, 0, 0, x0, cb, n);
+    } else {
+      dim3 grid((unsigned)((npair + 31) / 32), (unsigned)((cb + 31) / 32));
+      k_unpack_pairs_T<<<grid, dim3(32, 8), 0, e.stream>>>(X.p, src, src_ld, x0, cb, n, npair);
+    }
+    count_launch();
+    // Y(xb,k,s) = sum_l X(xb,k,l) C(s,l):  (cb*n x n) = X (cb*n x n) * C^T
+    dgemm(e.stream, 'N', 'T', cb * n, n, n, 1.0, X.p, (long long)cb * n, C, n, 0.0, Y.p, (long long)cb * n);
+    // Z(xb,r,s) = sum_k Y(xb,k,s) C(r,k):  for each s, (cb x n) = Y_s (cb x n) * C^T
+    GemmBatch bt;
+    bt.count = n; bt.strideA = (long long)cb * n; bt.strideB = 0; bt.strideC = (long long)cb * n;
+    dgemm(e.stream, 'N', 'T', cb, n, n, 1.0, Y.p, cb, C, n, 0.0, Z.p, cb, &bt);
+    k_pack_pairs<<<grid_for((long long)cb * n2), 256, 0, e.stream>>>(dst, Z.p, dst_mode, dst_ld, x0, cb, n);
+    count_launch();
+    AFESP_CUDA_CHECK(cudaGetLastError());
+  }
+}
+
+}  // namespace
+
+long long npair_of(int n) { return (long long)n * (n + 1) / 2; }
+long long npacked_of(int n) { long long m = npair_of(n); return m * (m + 1) / 2; }
+
+void ao2mo_packed(Engine& e, int n, const double* eri_ao, const double* C, double* eri_mo, long long block_bytes) {
+  const long long npair = npair_of(n);
+  Scratch H(e.pool, (size_t)(npair * npair));
+  // phase 1: spectator = kl (AO pair), transform (ij) -> (pq): H(kl, pq), kl fastest
+  half_transform(e, n, C, eri_ao, 0, 0, H.p, 0, npair, npair, block_bytes);
+  // phase 2: spectator = pq (MO pair = column of H), transform (kl) -> (rs): eri_mo[tri(pq, rs)], rs <= pq
+  half_transform(e, n, C, H.p, 1, npair, eri_mo, 1, 0, npair, block_bytes);
+}
+
+void mp2_energy(Engine& e, int n, int nocc, const double* eri_mo, const double* eps, double* out_dev) {
+  const long long total = (long long)nocc * nocc * (n - nocc) * (n - nocc);
+  int nb = std::min(grid_for(total), 1024);
+  double* part = reduce_scratch(e, nb);
+  k_mp2<<<nb, 256, 0, e.stream>>>(eri_mo, eps, n, nocc, part);
+  count_launch();
+  finish_partials(e, part, nb, 1, out_dev);
+}
+
+void slice_phys(Engine& e, double* out, const double* eri_mo, const int lo[4], const int cnt[4]) {
+  SliceSpec sp;
+  long long total = 1;
+  for (int d = 0; d < 4; ++d) { sp.lo[d] = lo[d]; sp.n[d] = cnt[d]; total *= cnt[d]; }
+  if (total == 0) return;
+  k_slice_phys<<<grid_for(total), 256, 0, e.stream>>>(out, eri_mo, sp);
+  count_launch();
+}
+
+void slice_spinorb(Engine& e, double* out, const double* eri_mo, const int lo[4], const int cnt[4]) {
+  SliceSpec sp;
+  long long total = 1;
+  for (int d = 0; d < 4; ++d) { sp.lo[d] = lo[d]; sp.n[d] = cnt[d]; total *= cnt[d]; }
+  if (total == 0) return;
+  k_slice_spinorb<<<grid_for(total), 256, 0, e.stream>>>(out, eri_mo, sp);
+  count_launch();
+}
+
+}  // namespace afesp

@@ -1,0 +1,22 @@
+// Packed-ERI kernels (integrals.cu).
+#pragma once
+#include "tensor.cuh"
+
+namespace afesp {
+
+long long npair_of(int n);    // n(n+1)/2
+long long npacked_of(int n);  // npair(npair+1)/2
+
+// eri_mo[packed] = sum C C C C eri_ao[packed];  C is C(mo,ao) column-major n x n (src/hf.f90:102).  All device.
+void ao2mo_packed(Engine& e, int n, const double* eri_ao, const double* C, double* eri_mo,
+                  long long block_bytes = 3LL << 30);
+
+// MP2 correlation energy (src/mp2.f90:418-438) from packed MO integrals; result in out_dev[0].
+void mp2_energy(Engine& e, int n, int nocc, const double* eri_mo, const double* eps, double* out_dev);
+
+// out(p,q,r,s) = <PQ|RS> = (PR|QS) with P = lo[0]+p ...; spatial orbitals (src/ccsd.f90:496-512)
+void slice_phys(Engine& e, double* out, const double* eri_mo, const int lo[4], const int cnt[4]);
+// out(P,Q,R,S) = <PQ||RS> over spin-orbital index ranges (src/ccsd.f90:111-143, 182-194)
+void slice_spinorb(Engine& e, double* out, const double* eri_mo, const int lo[4], const int cnt[4]);
+
+}  // namespace afesp

@@ -1,0 +1,241 @@
+// Bandwidth-bound helper kernels of the CC path.  All are grid-stride, coalesced along the fastest (first) index;
+// reductions are two-stage and deterministic (warp shuffle -> block partials -> fixed-order final sum).
+#include "kernels.cuh"
+
+namespace afesp {
+namespace {
+
+constexpr int RB = 256;  // reduction block size
+
+inline int grid_for(long long n, int block = 256) {
+  long long b = (n + block - 1) / block;
+  return (int)std::max<long long>(1, std::min<long long>(b, 148LL * 16));
+}
+
+__global__ void k_divide_d2(double* __restrict__ out, const double* __restrict__ x, const double* __restrict__ eo,
+                            const double* __restrict__ ev, int o, int v) {
+  const long long oo = (long long)o * o, total = oo * v * v;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int ij = (int)(idx % oo);
+    long long ab = idx / oo;
+    int i = ij % o, j = ij / o, a = (int)(ab % v), b = (int)(ab / v);
+    out[idx] = x[idx] / (eo[i] + eo[j] - ev[a] - ev[b]);
+  }
+}
+
+__global__ void k_divide_d1(double* __restrict__ out, const double* __restrict__ x, const double* __restrict__ eo,
+                            const double* __restrict__ ev, int o, int v) {
+  int total = o * v;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+    out[idx] = x[idx] / (eo[idx % o] - ev[idx / o]);
+}
+
+__global__ void k_t2_plus_t1t1(double* __restrict__ out, const double* __restrict__ t2, const double* __restrict__ t1,
+                               int o, int v, double ca, double cb) {
+  const long long oo = (long long)o * o, total = oo * v * v;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int ij = (int)(idx % oo);
+    long long ab = idx / oo;
+    int i = ij % o, j = ij / o, a = (int)(ab % v), b = (int)(ab / v);
+    double r = t2[idx] + ca * t1[i + o * a] * t1[j + o * b];
+    if (cb != 0.0) r += cb * t1[i + o * b] * t1[j + o * a];
+    out[idx] = r;
+  }
+}
+
+__global__ void k_axpby(long long n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = (b == 0.0) ? a * x[i] : a * x[i] + b * y[i];
+}
+
+__global__ void k_fill(long long n, double val, double* __restrict__ y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = val;
+}
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* partials) {
+  __shared__ double sh[NV][RB / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double x = v[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+    if (lane == 0) sh[k][warp] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+    for (int w = 0; w < RB / 32; ++w) s += sh[threadIdx.x][w];
+    partials[(long long)blockIdx.x * NV + threadIdx.x] = s;
+  }
+}
+
+struct PtrPack { const double* p[8]; double c[8]; };
+
+template <int NX>
+__global__ void __launch_bounds__(RB) k_dotn(long long n, PtrPack xs, const double* __restrict__ y,
+                                              double* __restrict__ partials) {
+  double acc[NX];
+#pragma unroll
+  for (int k = 0; k < NX; ++k) acc[k] = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double yv = y[i];
+#pragma unroll
+    for (int k = 0; k < NX; ++k) acc[k] += xs.p[k][i] * yv;
+  }
+  block_reduce_store<NX>(acc, partials);
+}
+
+// out[v] = sum_b partials[b*nvals + v]; one block per value, fixed summation order (deterministic)
+__global__ void __launch_bounds__(RB) k_finish(const double* __restrict__ partials, int nblocks, int nvals,
+                                                double* __restrict__ out) {
+  __shared__ double sh[RB];
+  const int v = blockIdx.x;
+  double s = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += RB) s += partials[(long long)b * nvals + v];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = RB / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[v] = sh[0];
+}
+
+__global__ void __launch_bounds__(RB) k_energy_restricted(const double* __restrict__ vo, const double* __restrict__ t2,
+                                                           const double* __restrict__ t1,
+                                                           const double* __restrict__ t2_old, int o, int v,
+                                                           double* __restrict__ partials) {
+  const long long oo = (long long)o * o, total = oo * v * v;
+  double acc[2] = {0.0, 0.0};
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int ij = (int)(idx % oo);
+    long long ab = idx / oo;
+    int i = ij % o, j = ij / o, a = (int)(ab % v), b = (int)(ab / v);
+    double t = t2[idx];
+    double vx = vo[ij + oo * (b + (long long)v * a)];
+    acc[0] += (2.0 * vo[idx] - vx) * (t + t1[i + o * a] * t1[j + o * b]);
+    double d = t - t2_old[idx];
+    acc[1] += d * d;
+  }
+  block_reduce_store<2>(acc, partials);
+}
+
+__global__ void __launch_bounds__(RB) k_energy_spinorb(const double* __restrict__ vo, const double* __restrict__ t2,
+                                                        const double* __restrict__ t1,
+                                                        const double* __restrict__ t2_old, int o, int v,
+                                                        double* __restrict__ partials) {
+  const long long oo = (long long)o * o, total = oo * v * v;
+  double acc[2] = {0.0, 0.0};
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int ij = (int)(idx % oo);
+    long long ab = idx / oo;
+    int i = ij % o, j = ij / o, a = (int)(ab % v), b = (int)(ab / v);
+    double t = t2[idx];
+    acc[0] += 0.25 * vo[idx] * (t + 2.0 * t1[i + o * a] * t1[j + o * b]);
+    double d = t - t2_old[idx];
+    acc[1] += d * d;
+  }
+  block_reduce_store<2>(acc, partials);
+}
+
+template <int NX>
+__global__ void k_lincomb(long long n, PtrPack xs, double* __restrict__ y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < NX; ++k) s += xs.c[k] * xs.p[k][i];
+    y[i] = s;
+  }
+}
+
+}  // namespace
+
+void divide_d2(cudaStream_t st, double* out, const double* x, const double* eo, const double* ev, int o, int v) {
+  k_divide_d2<<<grid_for((long long)o * o * v * v), 256, 0, st>>>(out, x, eo, ev, o, v);
+  count_launch();
+}
+void divide_d1(cudaStream_t st, double* out, const double* x, const double* eo, const double* ev, int o, int v) {
+  k_divide_d1<<<grid_for((long long)o * v), 256, 0, st>>>(out, x, eo, ev, o, v);
+  count_launch();
+}
+void t2_plus_t1t1(cudaStream_t st, double* out, const double* t2, const double* t1, int o, int v, double ca,
+                  double cb) {
+  k_t2_plus_t1t1<<<grid_for((long long)o * o * v * v), 256, 0, st>>>(out, t2, t1, o, v, ca, cb);
+  count_launch();
+}
+void axpby(cudaStream_t st, long long n, double a, const double* x, double b, double* y) {
+  if (n <= 0) return;
+  k_axpby<<<grid_for(n), 256, 0, st>>>(n, a, x, b, y);
+  count_launch();
+}
+void fill(cudaStream_t st, long long n, double val, double* y) {
+  if (n <= 0) return;
+  k_fill<<<grid_for(n), 256, 0, st>>>(n, val, y);
+  count_launch();
+}
+
+double* reduce_scratch(Engine& e, size_t n) {
+  if (e.red.n < n) e.red.alloc(std::max<size_t>(n, 1 << 16));
+  return e.red.p;
+}
+
+void finish_partials(Engine& e, const double* partials, int nblocks, int nvals, double* out) {
+  k_finish<<<nvals, RB, 0, e.stream>>>(partials, nblocks, nvals, out);
+  count_launch();
+  AFESP_CUDA_CHECK(cudaGetLastError());
+}
+
+void dotn(Engine& e, long long n, int nx, const double* const* xp, const double* y, double* out) {
+  AFESP_REQUIRE(nx >= 1 && nx <= 8, "dotn: 1..8 vectors");
+  PtrPack pk{};
+  for (int k = 0; k < nx; ++k) pk.p[k] = xp[k];
+  int nb = std::min(grid_for(n, RB), 1024);
+  double* part = reduce_scratch(e, (size_t)nb * 8);
+  switch (nx) {
+#define C(NX) case NX: k_dotn<NX><<<nb, RB, 0, e.stream>>>(n, pk, y, part); break;
+    C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8)
+#undef C
+  }
+  count_launch();
+  finish_partials(e, part, nb, nx, out);
+}
+
+void cc_energy_restricted(Engine& e, const double* v_oovv, const double* t2, const double* t1, const double* t2_old,
+                          int o, int v, double* out) {
+  int nb = std::min(grid_for((long long)o * o * v * v, RB), 1024);
+  double* part = reduce_scratch(e, (size_t)nb * 2);
+  k_energy_restricted<<<nb, RB, 0, e.stream>>>(v_oovv, t2, t1, t2_old, o, v, part);
+  count_launch();
+  finish_partials(e, part, nb, 2, out);
+}
+
+void cc_energy_spinorb(Engine& e, const double* oovv, const double* t2, const double* t1, const double* t2_old, int o,
+                       int v, double* out) {
+  int nb = std::min(grid_for((long long)o * o * v * v, RB), 1024);
+  double* part = reduce_scratch(e, (size_t)nb * 2);
+  k_energy_spinorb<<<nb, RB, 0, e.stream>>>(oovv, t2, t1, t2_old, o, v, part);
+  count_launch();
+  finish_partials(e, part, nb, 2, out);
+}
+
+void lincomb(cudaStream_t st, long long n, int nx, const double* const* xp, const double* c, double* y) {
+  AFESP_REQUIRE(nx >= 1 && nx <= 8, "lincomb: 1..8 vectors");
+  PtrPack pk{};
+  for (int k = 0; k < nx; ++k) { pk.p[k] = xp[k]; pk.c[k] = c[k]; }
+  int nb = grid_for(n);
+  switch (nx) {
+#define C(NX) case NX: k_lincomb<NX><<<nb, 256, 0, st>>>(n, pk, y); break;
+    C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8)
+#undef C
+  }
+  count_launch();
+}
+
+}  // namespace afesp

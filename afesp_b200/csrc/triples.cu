@@ -1,0 +1,502 @@
+// Perturbative triples on the device: [T], (T), renormalised and completely renormalised variants (spin-free,
+// src/ccsd.f90:2018-2336) and the spin-orbital (T) (src/ccsd.f90:1812-1922).
+//
+// The reference evaluates, for every ordered (i,j,k) and every (a,b,c), 12 (24 for CR) strided dot products
+// (:2168-2173, :2188-2193).  Here each (i,j,k) block is built from FP64 DMMA GEMMs:
+//     X_pqr(a,(b,c)) = sum_d t2(p,q,a,d) v_vovv(d,r,b,c)            [v x v^2 x v]
+//                    - sum_l t2(l,p,b,a) v_ovoo(l,c,q,r)            [v^2 x v x o]   (accumulated into the same block)
+//     W_ijk(a,b,c)   = sum over the six simultaneous permutations of X               (tiled combine kernel)
+// batched over as many triples as fit the work buffer, followed by one fused epilogue kernel that forms the
+// energy denominators, z3, y, the x-bar combinations and all six reductions in a single pass over W (and M3).
+//
+// Occupied-triple symmetry: W, z3, y and M3 are covariant under simultaneous permutation of (i,a),(j,b),(k,c), so the
+// sum over the orbit of an ordered triple equals  mult * sum_abc x~(abc) u(abc)  with the symmetrised
+//     x~ = [8 x(abc) - 4 (x(acb) + x(cba) + x(bac)) + 2 (x(bca) + x(cab))] / 6
+// (the group average of make_x_bar, :2314-2318; the same combination the GAMESS comment at :2320-2331 lists).  Only
+// i <= j <= k is computed, weighted by mult = 6, 3 or 1.  Work is dealt round-robin over (rank, nranks): the unit of
+// multi-GPU sharding; the caller sums the six partial results across ranks.
+#include <algorithm>
+
+#include "ccsd.cuh"
+
+namespace afesp {
+namespace {
+
+constexpr int TS = 8;               // label tile edge
+constexpr int TP = TS + 1;          // padded edge (bank spread)
+constexpr int BOX = TS * TP * TP;   // doubles per staged box
+
+__constant__ int c_perm[6][3] = {{0, 1, 2}, {1, 0, 2}, {2, 1, 0}, {0, 2, 1}, {1, 2, 0}, {2, 0, 1}};
+__constant__ double c_coef[6] = {8.0 / 6.0, -4.0 / 6.0, -4.0 / 6.0, -4.0 / 6.0, 2.0 / 6.0, 2.0 / 6.0};
+
+struct TripleDesc { int i, j, k; double weight; };
+
+__device__ __forceinline__ int box_off(int x, int y, int z) { return (z * TP + y) * TP + x; }
+
+// W[tb](a,b,c) = sum_t X[tb][t](L[p0], L[p1], L[p2]),  L = (a,b,c), p = c_perm[t]
+__global__ void __launch_bounds__(TS* TS* TS) k_combine(const double* __restrict__ X, double* __restrict__ W, int v,
+                                                         int ntile) {
+  __shared__ double s[6 * BOX];
+  const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
+  int tile = blockIdx.x;
+  const int O[3] = {(tile % ntile) * TS, ((tile / ntile) % ntile) * TS, (tile / (ntile * ntile)) * TS};
+  const long long v3 = (long long)v * v * v;
+  const double* Xb = X + (long long)blockIdx.y * 6 * v3;
+#pragma unroll
+  for (int t = 0; t < 6; ++t) {
+    int x = O[c_perm[t][0]] + tx, y = O[c_perm[t][1]] + ty, z = O[c_perm[t][2]] + tz;
+    double val = 0.0;
+    if (x < v && y < v && z < v) val = Xb[t * v3 + x + (long long)v * (y + (long long)v * z)];
+    s[t * BOX + box_off(tx, ty, tz)] = val;
+  }
+  __syncthreads();
+  const int l[3] = {tx, ty, tz};
+  double w = 0.0;
+#pragma unroll
+  for (int t = 0; t < 6; ++t) w += s[t * BOX + box_off(l[c_perm[t][0]], l[c_perm[t][1]], l[c_perm[t][2]])];
+  int a = O[0] + tx, b = O[1] + ty, c = O[2] + tz;
+  if (a < v && b < v && c < v) W[(long long)blockIdx.y * v3 + a + (long long)v * (b + (long long)v * c)] = w;
+}
+
+struct EnergyArgs {
+  const double* W;   // [nb][v^3]
+  const double* M;   // [nb][v^3] or null
+  const double* t1;  // (o,v)
+  const double* t2;  // (o,o,v,v)
+  const double* vo;  // v_oovv (o,o,v,v)
+  const double* eo;
+  const double* ev;
+  const TripleDesc* tr;
+  int o, v, ntile;
+  int use_z, do_y, do_m, paren;
+  double* partials;  // [gridDim.y * gridDim.x][6]
+};
+
+__global__ void __launch_bounds__(TS* TS* TS) k_energy_spatial(const EnergyArgs g) {
+  extern __shared__ double sm[];
+  double* sW = sm;                      // 6 boxes of W at permuted origins
+  double* sV = sW + 6 * BOX;            // [3 pairs][3][3][TS*TS]  v_oovv(pair; R1, R2)
+  double* sT = sV + 27 * TS * TS;       // [3 occ][3 ranges][TS]    t1(occ; R)
+  double* sY = sT + 9 * TS;             // [3][TS*TS]               t2(jk;B,C), t2(ik;A,C), t2(ij;A,B)
+  __shared__ double red[6][TS * TS * TS / 32];
+  const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
+  const int tid = tx + TS * (ty + TS * tz);
+  const int o = g.o, v = g.v, ntile = g.ntile;
+  const TripleDesc td = g.tr[blockIdx.y];
+  const int occ[3] = {td.i, td.j, td.k};
+  int tile = blockIdx.x;
+  const int O[3] = {(tile % ntile) * TS, ((tile / ntile) % ntile) * TS, (tile / (ntile * ntile)) * TS};
+  const long long v3 = (long long)v * v * v, oo = (long long)o * o;
+  const double* Wb = g.W + (long long)blockIdx.y * v3;
+#pragma unroll
+  for (int t = 0; t < 6; ++t) {
+    int x = O[c_perm[t][0]] + tx, y = O[c_perm[t][1]] + ty, z = O[c_perm[t][2]] + tz;
+    double val = 0.0;
+    if (x < v && y < v && z < v) val = Wb[x + (long long)v * (y + (long long)v * z)];
+    sW[t * BOX + box_off(tx, ty, tz)] = val;
+  }
+  if (g.use_z) {
+    // v_oovv(p,q; x in R1, y in R2) for the occupied pairs (j,k), (i,k), (i,j) and all ordered range pairs
+    for (int e = tid; e < 27 * TS * TS; e += TS * TS * TS) {
+      int xy = e % (TS * TS), rr = (e / (TS * TS)) % 9, pr = e / (9 * TS * TS);
+      int r1 = rr / 3, r2 = rr % 3;
+      int x = O[r1] + xy % TS, y = O[r2] + xy / TS;
+      int p = pr == 0 ? occ[1] : occ[0], q = pr == 2 ? occ[1] : occ[2];
+      sV[e] = (x < v && y < v) ? g.vo[p + (long long)o * q + oo * (x + (long long)v * y)] : 0.0;
+    }
+  }
+  if (g.use_z || g.do_y) {
+    for (int e = tid; e < 9 * TS; e += TS * TS * TS) {
+      int x = O[(e / TS) % 3] + e % TS;
+      sT[e] = x < v ? g.t1[occ[e / (3 * TS)] + (long long)o * x] : 0.0;
+    }
+  }
+  if (g.do_y) {
+    for (int e = tid; e < 3 * TS * TS; e += TS * TS * TS) {
+      int xy = e % (TS * TS), pr = e / (TS * TS);
+      int r1 = pr == 0 ? 1 : 0, r2 = pr == 2 ? 1 : 2;
+      int x = O[r1] + xy % TS, y = O[r2] + xy / TS;
+      int p = pr == 0 ? occ[1] : occ[0], q = pr == 2 ? occ[1] : occ[2];
+      sY[e] = (x < v && y < v) ? g.t2[p + (long long)o * q + oo * (x + (long long)v * y)] : 0.0;
+    }
+  }
+  __syncthreads();
+
+  double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  const int l[3] = {tx, ty, tz};
+  const int a = O[0] + tx, b = O[1] + ty, c = O[2] + tz;
+  if (a < v && b < v && c < v) {
+    const double D3 = g.eo[td.i] + g.eo[td.j] + g.eo[td.k] - g.ev[a] - g.ev[b] - g.ev[c];
+    double tt = 0.0, zt = 0.0;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+      const int q0 = c_perm[t][0], q1 = c_perm[t][1], q2 = c_perm[t][2];
+      tt += c_coef[t] * sW[t * BOX + box_off(l[q0], l[q1], l[q2])];
+      if (g.use_z) {
+        // z3 at labels (a',b',c') = (L[q0], L[q1], L[q2])                                  (src/ccsd.f90:2178-2179)
+        double z = sT[(0 * 3 + q0) * TS + l[q0]] * sV[((0 * 3 + q1) * 3 + q2) * TS * TS + l[q1] + TS * l[q2]] +
+                   sT[(1 * 3 + q1) * TS + l[q1]] * sV[((1 * 3 + q0) * 3 + q2) * TS * TS + l[q0] + TS * l[q2]] +
+                   sT[(2 * 3 + q2) * TS + l[q2]] * sV[((2 * 3 + q0) * 3 + q1) * TS * TS + l[q0] + TS * l[q1]];
+        zt += c_coef[t] * z;
+      }
+    }
+    tt /= D3;
+    zt /= D3;
+    const double w = sW[box_off(tx, ty, tz)];
+    acc[0] = tt * w;
+    if (g.paren) acc[1] = (tt + zt) * w;
+    if (g.do_y) {
+      const double ta = sT[(0 * 3 + 0) * TS + tx], tb = sT[(1 * 3 + 1) * TS + ty], tc = sT[(2 * 3 + 2) * TS + tz];
+      const double y = ta * tb * tc + ta * sY[0 * TS * TS + ty + TS * tz] + tb * sY[1 * TS * TS + tx + TS * tz] +
+                       tc * sY[2 * TS * TS + tx + TS * ty];                                 // (:2183-2184)
+      acc[2] = tt * y;
+      if (g.paren) acc[3] = (tt + zt) * y;
+    }
+    if (g.do_m) {
+      const double m = g.M[(long long)blockIdx.y * v3 + a + (long long)v * (b + (long long)v * c)];
+      acc[4] = tt * m;
+      if (g.paren) acc[5] = (tt + zt) * m;
+    }
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double x = acc[k] * td.weight;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+    if (lane == 0) red[k][warp] = x;
+  }
+  __syncthreads();
+  if (tid < 6) {
+    double sacc = 0.0;
+    for (int w2 = 0; w2 < TS * TS * TS / 32; ++w2) sacc += red[tid][w2];
+    g.partials[((long long)blockIdx.y * gridDim.x + blockIdx.x) * 6 + tid] = sacc;
+  }
+}
+
+// Spin-orbital epilogue (src/ccsd.f90:1873-1910): t3c = X - X(bac) - X(cba), same for the disconnected part,
+// e_T += t3c (t3c / D + t3d) / 36, times the orbit weight.
+struct EnergySoArgs {
+  const double* X;   // [nb][v^3] connected block before P(a/bc)
+  const double* t1;
+  const double* vo;  // oovv (o,o,v,v)
+  const double* eo;
+  const double* ev;
+  const TripleDesc* tr;
+  int o, v, ntile;
+  double* partials;  // [blocks][1]
+};
+
+__global__ void __launch_bounds__(TS* TS* TS) k_energy_spinorb_t(const EnergySoArgs g) {
+  __shared__ double sX[3 * BOX];
+  __shared__ double sV[27 * TS * TS];
+  __shared__ double sT[9 * TS];
+  __shared__ double red[TS * TS * TS / 32];
+  const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
+  const int tid = tx + TS * (ty + TS * tz);
+  const int o = g.o, v = g.v, ntile = g.ntile;
+  const TripleDesc td = g.tr[blockIdx.y];
+  const int occ[3] = {td.i, td.j, td.k};
+  int tile = blockIdx.x;
+  const int O[3] = {(tile % ntile) * TS, ((tile / ntile) % ntile) * TS, (tile / (ntile * ntile)) * TS};
+  const long long v3 = (long long)v * v * v, oo = (long long)o * o;
+  const double* Xb = g.X + (long long)blockIdx.y * v3;
+  const int P3[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 1, 0}};  // abc, bac, cba
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    int x = O[P3[t][0]] + tx, y = O[P3[t][1]] + ty, z = O[P3[t][2]] + tz;
+    double val = 0.0;
+    if (x < v && y < v && z < v) val = Xb[x + (long long)v * (y + (long long)v * z)];
+    sX[t * BOX + box_off(tx, ty, tz)] = val;
+  }
+  // oovv(p,q; x in R1, y in R2) for occupied pairs (j,k), (i,k), (j,i)                      (:1877-1878)
+  for (int e = tid; e < 27 * TS * TS; e += TS * TS * TS) {
+    int xy = e % (TS * TS), rr = (e / (TS * TS)) % 9, pr = e / (9 * TS * TS);
+    int r1 = rr / 3, r2 = rr % 3;
+    int x = O[r1] + xy % TS, y = O[r2] + xy / TS;
+    int p = pr == 1 ? occ[0] : occ[1], q = pr == 2 ? occ[0] : occ[2];
+    sV[e] = (x < v && y < v) ? g.vo[p + (long long)o * q + oo * (x + (long long)v * y)] : 0.0;
+  }
+  for (int e = tid; e < 9 * TS; e += TS * TS * TS) {
+    int x = O[(e / TS) % 3] + e % TS;
+    sT[e] = x < v ? g.t1[occ[e / (3 * TS)] + (long long)o * x] : 0.0;
+  }
+  __syncthreads();
+  double acc = 0.0;
+  const int l[3] = {tx, ty, tz};
+  const int a = O[0] + tx, b = O[1] + ty, c = O[2] + tz;
+  if (a < v && b < v && c < v) {
+    const double D3 = g.eo[td.i] + g.eo[td.j] + g.eo[td.k] - g.ev[a] - g.ev[b] - g.ev[c];
+    double t3c = 0.0, t3d = 0.0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const int q0 = P3[t][0], q1 = P3[t][1], q2 = P3[t][2];
+      const double sgn = t == 0 ? 1.0 : -1.0;
+      t3c += sgn * sX[t * BOX + box_off(l[q0], l[q1], l[q2])];
+      // disconnected part at labels (a',b',c'): t1(i,a') oovv(j,k,b',c') - t1(j,a') oovv(i,k,b',c') - t1(k,a') oovv(j,i,b',c')
+      const int bc = l[q1] + TS * l[q2];
+      double d = sT[(0 * 3 + q0) * TS + l[q0]] * sV[((0 * 3 + q1) * 3 + q2) * TS * TS + bc] -
+                 sT[(1 * 3 + q0) * TS + l[q0]] * sV[((1 * 3 + q1) * 3 + q2) * TS * TS + bc] -
+                 sT[(2 * 3 + q0) * TS + l[q0]] * sV[((2 * 3 + q1) * 3 + q2) * TS * TS + bc];
+      t3d += sgn * d;
+    }
+    acc = t3c * (t3c / D3 + t3d / D3) / 36.0 * td.weight;
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double sacc = 0.0;
+    for (int w2 = 0; w2 < TS * TS * TS / 32; ++w2) sacc += red[w2];
+    g.partials[(long long)blockIdx.y * gridDim.x + blockIdx.x] = sacc;
+  }
+}
+
+struct DevPtrs {  // device pointer arrays for the batched GEMMs of one batch
+  DBuf raw;       // reinterpret as const double*[]
+  size_t cap = 0;
+  void ensure(size_t nptr) {
+    if (cap < nptr) { raw.alloc(nptr); cap = nptr; }  // sizeof(double) == sizeof(pointer)
+  }
+};
+
+std::vector<TripleDesc> my_triples(int o, bool symmetric, bool strict, int rank, int nranks) {
+  // symmetric: unique i<=j<=k with orbit multiplicity; strict: i<j<k only (spin-orbital, others vanish)
+  std::vector<TripleDesc> all;
+  if (symmetric) {
+    for (int i = 0; i < o; ++i)
+      for (int j = i; j < o; ++j)
+        for (int k = j; k < o; ++k) {
+          if (strict && (i == j || j == k)) continue;
+          double w = (i == j && j == k) ? 1.0 : ((i == j || j == k) ? 3.0 : 6.0);
+          all.push_back({i, j, k, w});
+        }
+  } else {
+    for (int i = 0; i < o; ++i)
+      for (int j = 0; j < o; ++j)
+        for (int k = 0; k < o; ++k) all.push_back({i, j, k, 1.0});
+  }
+  std::vector<TripleDesc> mine;
+  for (size_t t = 0; t < all.size(); ++t)
+    if ((int)(t % (size_t)nranks) == rank) mine.push_back(all[t]);
+  return mine;
+}
+
+static_assert(sizeof(double) == sizeof(void*), "pointer arrays are carried in double buffers");
+
+}  // namespace
+
+void triples_partition_counts(int o, bool symmetric, bool strict, int nranks, long long* counts) {
+  for (int r = 0; r < nranks; ++r) counts[r] = (long long)my_triples(o, symmetric, strict, r, nranks).size();
+}
+
+double triples_denominator_constant(CCState& s) {
+  // 1 + 2 sum t1^2 + sum asym_t2 * c  (src/ccsd.f90:2243), from the converged amplitudes (:2073-2105)
+  Engine& e = s.eng;
+  const int o = s.o, v = s.v;
+  Scratch a(e.pool, (size_t)s.t2.size()), c(e.pool, (size_t)s.t2.size());
+  TView A(a.p, s.t2.dims);
+  transpose(e, "ijab->jiab", -1.0, s.t2.view(), 0.0, A);
+  axpby(e.stream, s.t2.size(), 2.0, s.t2.p(), 1.0, a.p);
+  t2_plus_t1t1(e.stream, c.p, s.t2.p(), s.t1.p(), o, v, 1.0, 0.0);
+  if (s.red_out.n < 16) s.red_out.alloc(16);
+  const double* pa[1] = {a.p};
+  dotn(e, s.t2.size(), 1, pa, c.p, s.red_out.p);
+  double h = 0.0;
+  AFESP_CUDA_CHECK(cudaMemcpyAsync(&h, s.red_out.p, 8, cudaMemcpyDeviceToHost, e.stream));
+  AFESP_CUDA_CHECK(cudaStreamSynchronize(e.stream));
+  return 1.0 + 2.0 * cc_t1_norm2(s) + h;
+}
+
+void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int rank, int nranks, double sums[6]) {
+  AFESP_REQUIRE(s.restricted, "triples_spatial needs a spin-free CCSD state");
+  AFESP_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "triples: bad (rank, nranks)");
+  Engine& e = s.eng;
+  cudaStream_t st = e.stream;
+  const int o = s.o, v = s.v;
+  const long long v2 = (long long)v * v, v3 = v2 * v;
+  const bool do_y = renorm || comp_renorm, do_m = comp_renorm;
+  const bool use_z = paren && do_y;  // Q2: z3_bar is only formed for (T) *and* (R or CR)  (src/ccsd.f90:2211-2215)
+  if (do_m) AFESP_REQUIRE(s.has("I_vovv_pp") && s.has("I_ooov_pp"), "CR triples need the CR intermediates");
+  for (int k = 0; k < 6; ++k) sums[k] = 0.0;
+
+  // GEMM-ready operand layouts (the reference's reshapes at :2056-2066, re-aimed at contiguous GEMM blocks)
+  Tensor T2v({v, v, o, o}), T2o({o, v, v, o}), Vv({v, v, v, o}), Vo({o, v, o, o});
+  transpose(e, "ijad->adij", 1.0, s.t2.view(), 0.0, T2v.view());            // T2v(a,d;p,q) = t2(p,q,a,d)
+  transpose(e, "lpba->labp", 1.0, s.t2.view(), 0.0, T2o.view());            // T2o(l,a,b;p) = t2(l,p,b,a)
+  transpose(e, "cbkd->dbck", 1.0, s.get("v_vvov").view(), 0.0, Vv.view());  // Vv(d,b,c;k) = v_vvov(c,b,k,d)
+  transpose(e, "kjcl->lcjk", 1.0, s.get("v_oovo").view(), 0.0, Vo.view());  // Vo(l,c;j,k) = v_oovo(k,j,c,l)
+  Tensor Mv, Mo;
+  if (do_m) {
+    Mv.init({v, v, v, o}); Mo.init({o, v, o, o});
+    transpose(e, "dkbc->dbck", 1.0, s.get("I_vovv_pp").view(), 0.0, Mv.view());  // I_vovv_pp(d,k,b,c)
+    transpose(e, "jklc->lcjk", 1.0, s.get("I_ooov_pp").view(), 0.0, Mo.view());  // I_ooov_pp(j,k,l,c)
+  }
+
+  std::vector<TripleDesc> tri = my_triples(o, s.opt.triples_ijk_symmetry, false, rank, nranks);
+  if (tri.empty()) return;
+  const long long per_triple = (6 + 1 + (do_m ? 1 : 0)) * v3 * 8;
+  int nb = (int)std::max<long long>(1, std::min<long long>((long long)tri.size(), s.opt.triples_batch_bytes / per_triple));
+  nb = std::min(nb, 65535 / 6);
+  Scratch X(e.pool, (size_t)nb * 6 * v3), W(e.pool, (size_t)nb * v3);
+  std::unique_ptr<Scratch> Mw;
+  if (do_m) Mw.reset(new Scratch(e.pool, (size_t)nb * v3));
+  const int ntile = (v + TS - 1) / TS;
+  const long long blocks_per_triple = (long long)ntile * ntile * ntile;
+  AFESP_REQUIRE(blocks_per_triple < (1LL << 31), "triples: too many label tiles");
+  DBuf descs((size_t)nb * 3);  // TripleDesc is 24 bytes = 3 doubles
+  static_assert(sizeof(TripleDesc) == 24, "TripleDesc layout");
+  DevPtrs ptrs;
+  ptrs.ensure((size_t)nb * 6 * 5);
+  const size_t nbatches = (tri.size() + nb - 1) / nb;
+  DBuf batch_sums(nbatches * 6);
+  const bool al16 = (v % 2 == 0) && (o % 2 == 0);
+  const int perm6[6][3] = {{0, 1, 2}, {1, 0, 2}, {2, 1, 0}, {0, 2, 1}, {1, 2, 0}, {2, 0, 1}};
+  const size_t esmem = (size_t)(6 * BOX + 27 * TS * TS + 9 * TS + 3 * TS * TS) * sizeof(double);
+  AFESP_CUDA_CHECK(cudaFuncSetAttribute(k_energy_spatial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+
+  for (size_t bi = 0; bi < nbatches; ++bi) {
+    const size_t t0 = bi * nb;
+    const int cb = (int)std::min<size_t>(nb, tri.size() - t0);
+    AFESP_CUDA_CHECK(cudaMemcpyAsync(descs.p, &tri[t0], (size_t)cb * sizeof(TripleDesc), cudaMemcpyHostToDevice, st));
+    const int ng = cb * 6;
+    auto run_gemms = [&](const Tensor& Bv, const Tensor& Bo) {
+      std::vector<const double*> hp((size_t)ng * 5);
+      for (int tb = 0; tb < cb; ++tb) {
+        const TripleDesc& td = tri[t0 + tb];
+        const int idx[3] = {td.i, td.j, td.k};
+        for (int t = 0; t < 6; ++t) {
+          const int p = idx[perm6[t][0]], q = idx[perm6[t][1]], r = idx[perm6[t][2]];
+          const int g = tb * 6 + t;
+          hp[0 * ng + g] = T2v.p() + ((long long)p + (long long)o * q) * v2;          // A1 (a x d)
+          hp[1 * ng + g] = Bv.p() + (long long)r * v3;                                // B1 (d x bc)
+          hp[2 * ng + g] = X.p + (long long)g * v3;                                   // C
+          hp[3 * ng + g] = T2o.p() + (long long)p * o * v2;                           // A2 (l x ab), used transposed
+          hp[4 * ng + g] = Bo.p() + ((long long)q + (long long)o * r) * o * v;        // B2 (l x c)
+        }
+      }
+      AFESP_CUDA_CHECK(cudaMemcpyAsync(ptrs.raw.p, hp.data(), hp.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
+      AFESP_CUDA_CHECK(cudaStreamSynchronize(st));  // hp is a stack-scoped staging vector
+      const double* const* dp = reinterpret_cast<const double* const*>(ptrs.raw.p);
+      GemmBatch b1;
+      b1.count = ng; b1.Aptr = dp + 0 * ng; b1.Bptr = dp + 1 * ng;
+      b1.Cptr = (double* const*)(dp + 2 * ng); b1.ptr_aligned16 = al16;
+      dgemm(st, 'N', 'N', v, (int)v2, v, 1.0, nullptr, v, nullptr, v, 0.0, nullptr, v, &b1);
+      GemmBatch b2;
+      b2.count = ng; b2.Aptr = dp + 3 * ng; b2.Bptr = dp + 4 * ng;
+      b2.Cptr = (double* const*)(dp + 2 * ng); b2.ptr_aligned16 = al16;
+      dgemm(st, 'T', 'N', (int)v2, v, o, -1.0, nullptr, o, nullptr, o, 1.0, nullptr, v2, &b2);
+    };
+    dim3 grid((unsigned)blocks_per_triple, (unsigned)cb), block(TS, TS, TS);
+    run_gemms(Vv, Vo);
+    k_combine<<<grid, block, 0, st>>>(X.p, W.p, v, ntile);
+    count_launch();
+    if (do_m) {
+      run_gemms(Mv, Mo);
+      k_combine<<<grid, block, 0, st>>>(X.p, Mw->p, v, ntile);
+      count_launch();
+    }
+    EnergyArgs ea{};
+    ea.W = W.p; ea.M = do_m ? Mw->p : nullptr; ea.t1 = s.t1.p(); ea.t2 = s.t2.p(); ea.vo = s.get("v_oovv").p();
+    ea.eo = s.eo.p(); ea.ev = s.ev.p(); ea.tr = reinterpret_cast<const TripleDesc*>(descs.p);
+    ea.o = o; ea.v = v; ea.ntile = ntile; ea.use_z = use_z; ea.do_y = do_y; ea.do_m = do_m; ea.paren = paren;
+    const long long nblocks = blocks_per_triple * cb;
+    ea.partials = reduce_scratch(e, (size_t)nblocks * 6);
+    k_energy_spatial<<<grid, block, esmem, st>>>(ea);
+    count_launch();
+    AFESP_CUDA_CHECK(cudaGetLastError());
+    finish_partials(e, ea.partials, (int)nblocks, 6, batch_sums.p + bi * 6);
+  }
+  std::vector<double> h(nbatches * 6);
+  AFESP_CUDA_CHECK(cudaMemcpyAsync(h.data(), batch_sums.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
+  AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (size_t bi = 0; bi < nbatches; ++bi)
+    for (int k = 0; k < 6; ++k) sums[k] += h[bi * 6 + k];
+  if (!paren) { sums[1] = 0.0; sums[3] = 0.0; sums[5] = 0.0; }
+}
+
+void triples_spinorb(CCState& s, int rank, int nranks, double* e_T) {
+  AFESP_REQUIRE(!s.restricted, "triples_spinorb needs a spin-orbital CCSD state");
+  AFESP_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "triples: bad (rank, nranks)");
+  Engine& e = s.eng;
+  cudaStream_t st = e.stream;
+  const int o = s.o, v = s.v;
+  const long long v2 = (long long)v * v, v3 = v2 * v;
+  *e_T = 0.0;
+  // X(a,b,c) = sum_f [ t2(j,k,a,f) vovv(f,i,b,c) - t2(i,k,a,f) vovv(f,j,b,c) - t2(j,i,a,f) vovv(f,k,b,c) ]
+  //          + sum_m [ ovoo(m,a,j,k) t2(m,i,b,c) - ovoo(m,a,i,k) t2(m,j,b,c) - ovoo(m,a,j,i) t2(m,k,b,c) ]
+  // (src/ccsd.f90:1881-1889 with t2(m,i,c,b) = -t2(m,i,b,c)); six DMMA GEMMs accumulate into one block.
+  Tensor T2v({v, v, o, o}), Vv({v, v, v, o});
+  transpose(e, "ijaf->afij", 1.0, s.t2.view(), 0.0, T2v.view());             // T2v(a,f;p,q) = t2(p,q,a,f)
+  transpose(e, "fibc->fbci", 1.0, s.get("vovv").view(), 0.0, Vv.view());     // Vv(f,b,c;i) = vovv(f,i,b,c)
+  Tensor& ovoo = s.get("ovoo");
+  // i<j<k only: the summand is symmetric in (i,j,k) and vanishes when two occupied indices coincide.
+  std::vector<TripleDesc> tri = my_triples(o, s.opt.triples_ijk_symmetry, s.opt.triples_ijk_symmetry, rank, nranks);
+  if (tri.empty()) return;
+  const long long per_triple = v3 * 8;
+  int nb = (int)std::max<long long>(1, std::min<long long>((long long)tri.size(), s.opt.triples_batch_bytes / per_triple));
+  nb = std::min(nb, 65535);
+  Scratch X(e.pool, (size_t)nb * v3);
+  const int ntile = (v + TS - 1) / TS;
+  const long long blocks_per_triple = (long long)ntile * ntile * ntile;
+  DBuf descs((size_t)nb * 3);
+  DevPtrs ptrs;
+  ptrs.ensure((size_t)nb * 13);
+  const size_t nbatches = (tri.size() + nb - 1) / nb;
+  DBuf batch_sums(nbatches);
+  const bool al16 = (v % 2 == 0) && (o % 2 == 0);
+  for (size_t bi = 0; bi < nbatches; ++bi) {
+    const size_t t0 = bi * nb;
+    const int cb = (int)std::min<size_t>(nb, tri.size() - t0);
+    AFESP_CUDA_CHECK(cudaMemcpyAsync(descs.p, &tri[t0], (size_t)cb * sizeof(TripleDesc), cudaMemcpyHostToDevice, st));
+    std::vector<const double*> hp((size_t)cb * 13);
+    for (int tb = 0; tb < cb; ++tb) {
+      const TripleDesc& td = tri[t0 + tb];
+      const int i = td.i, j = td.j, k = td.k;
+      // term s: (p,q | r) for the f-sum, (q',r' | p') for the m-sum
+      const int pq[3][2] = {{j, k}, {i, k}, {j, i}};
+      const int r[3] = {i, j, k};
+      for (int t = 0; t < 3; ++t) {
+        hp[(size_t)(0 + t) * cb + tb] = T2v.p() + ((long long)pq[t][0] + (long long)o * pq[t][1]) * v2;  // (a x f)
+        hp[(size_t)(3 + t) * cb + tb] = Vv.p() + (long long)r[t] * v3;                                   // (f x bc)
+        hp[(size_t)(6 + t) * cb + tb] = ovoo.p() + ((long long)pq[t][0] + (long long)o * pq[t][1]) * o * v;  // (m x a)
+        hp[(size_t)(9 + t) * cb + tb] = s.t2.p() + (long long)o * r[t];                                  // (m x bc), ld o^2
+      }
+      hp[(size_t)12 * cb + tb] = X.p + (long long)tb * v3;
+    }
+    AFESP_CUDA_CHECK(cudaMemcpyAsync(ptrs.raw.p, hp.data(), hp.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
+    AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
+    const double* const* dp = reinterpret_cast<const double* const*>(ptrs.raw.p);
+    double* const* cp = (double* const*)(dp + (size_t)12 * cb);
+    for (int t = 0; t < 3; ++t) {
+      GemmBatch b1;
+      b1.count = cb; b1.Aptr = dp + (size_t)(0 + t) * cb; b1.Bptr = dp + (size_t)(3 + t) * cb; b1.Cptr = cp;
+      b1.ptr_aligned16 = al16;
+      dgemm(st, 'N', 'N', v, (int)v2, v, t == 0 ? 1.0 : -1.0, nullptr, v, nullptr, v, t == 0 ? 0.0 : 1.0, nullptr, v, &b1);
+    }
+    for (int t = 0; t < 3; ++t) {
+      GemmBatch b2;
+      b2.count = cb; b2.Aptr = dp + (size_t)(6 + t) * cb; b2.Bptr = dp + (size_t)(9 + t) * cb; b2.Cptr = cp;
+      b2.ptr_aligned16 = al16;
+      dgemm(st, 'T', 'N', v, (int)v2, o, t == 0 ? 1.0 : -1.0, nullptr, o, nullptr, (long long)o * o, 1.0, nullptr, v, &b2);
+    }
+    EnergySoArgs ea{};
+    ea.X = X.p; ea.t1 = s.t1.p(); ea.vo = s.get("oovv").p(); ea.eo = s.eo.p(); ea.ev = s.ev.p();
+    ea.tr = reinterpret_cast<const TripleDesc*>(descs.p); ea.o = o; ea.v = v; ea.ntile = ntile;
+    const long long nblocks = blocks_per_triple * cb;
+    ea.partials = reduce_scratch(e, (size_t)nblocks);
+    dim3 grid((unsigned)blocks_per_triple, (unsigned)cb), block(TS, TS, TS);
+    k_energy_spinorb_t<<<grid, block, 0, st>>>(ea);
+    count_launch();
+    AFESP_CUDA_CHECK(cudaGetLastError());
+    finish_partials(e, ea.partials, (int)nblocks, 1, batch_sums.p + bi);
+  }
+  std::vector<double> h(nbatches);
+  AFESP_CUDA_CHECK(cudaMemcpyAsync(h.data(), batch_sums.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
+  AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (double x : h) *e_T += x;
+}
+
+}  // namespace afesp

@@ -1,0 +1,376 @@
+"""Host side of the drop-in: a Python mirror of the reference's program flow (src/main.F90:36-175).
+
+The reference's Fortran main program reads `els.in` and the `*.dat` files, runs RHF on the host, and then enters
+the hot path.  This module plays that role above the C ABI so the path can be exercised without a Fortran compiler
+(none exists in this image): same inputs, same calc_type strings, same convergence logic, same printed lines.
+Everything from the AO->MO transform onwards runs on the GPU through include/afesp_gpu.h; the SCF (outside the
+north-star path) is a small NumPy routine that follows src/hf.f90 step by step because CC energies
+are first order in the residual SCF error.  Nothing here imports the test oracle.
+"""
+from __future__ import annotations
+
+import io
+import os
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .capi import AfespGpu
+
+# calc_type -> (level, restricted, paren, renorm, comp_renorm)  (src/system.f90:116-165)
+CALC_TYPES = {
+    "RHF": (0, True, False, False, False),
+    "UHF": (0, False, False, False, False),
+    "MP2_spinorb": (1, False, False, False, False),
+    "MP2_spatial": (1, True, False, False, False),
+    "CCSD_spinorb": (2, False, False, False, False),
+    "CCSD_spatial": (2, True, False, False, False),
+    "CCSD(T)_spinorb": (3, False, False, False, False),
+    "CCSD(T)_spatial": (3, True, True, False, False),
+    "CCSD[T]_spatial": (3, True, False, False, False),
+    "RCCSD(T)_spatial": (3, True, True, True, False),
+    "RCCSD[T]_spatial": (3, True, False, True, False),
+    "CRCCSD(T)_spatial": (3, True, True, False, True),
+    "CRCCSD[T]_spatial": (3, True, False, False, True),
+}
+
+
+@dataclass
+class ElsInput:
+    """The &elsinput namelist (src/system.f90:96-97) plus the integral files."""
+
+    calc_type: str = "CCSD(T)_spatial"
+    scf_e_tol: float = 1e-6
+    scf_d_tol: float = 1e-6
+    scf_diis_n_errmat: int = 6
+    ccsd_e_tol: float = 1e-6
+    ccsd_t_tol: float = 1e-6
+    ccsd_diis_n_errmat: int = 8
+    scf_maxiter: int = 50
+    ccsd_maxiter: int = 50
+    write_fcidump: bool = False
+    scf_read_guess: bool = False
+    scf_write_guess: bool = False
+    nbasis: int = 0
+    nel: int = 0
+    e_nuc: float = 0.0
+    ovlp: np.ndarray | None = None
+    core_hamil: np.ndarray | None = None
+    eri: np.ndarray | None = None      # packed AO ERIs, canonical order (src/integrals.f90:196-210)
+    guess: np.ndarray | None = None    # guess_in.dat Fock matrix
+
+
+@dataclass
+class ElsResult:
+    e_hf: float = 0.0
+    e_nuc: float = 0.0
+    e_mp2: float = 0.0
+    e_ccsd: float = 0.0
+    energies: dict = field(default_factory=dict)
+    scf_table: list = field(default_factory=list)
+    ccsd_table: list = field(default_factory=list)
+    ccsd_converged: bool = False
+    t1_diagnostic: float = 0.0
+    coeff: np.ndarray | None = None
+    eps: np.ndarray | None = None
+    timings: dict = field(default_factory=dict)
+    stdout: str = ""
+
+
+def pair_index(i, j):
+    i = np.asarray(i, dtype=np.int64)
+    j = np.asarray(j, dtype=np.int64)
+    hi, lo = np.maximum(i, j), np.minimum(i, j)
+    return hi * (hi + 1) // 2 + lo
+
+
+def parse_namelist(text):
+    out = {}
+    for raw in text.splitlines():
+        line = raw.strip()
+        if not line or line[0] in "&/" or "=" not in line:
+            continue
+        k, v = [s.strip() for s in line.split("=", 1)]
+        v = v.rstrip(",").strip()
+        if v[:1] in "\"'":
+            out[k] = v.strip("\"'")
+        elif v.lower() in (".true.", ".t.", "t"):
+            out[k] = True
+        elif v.lower() in (".false.", ".f.", "f"):
+            out[k] = False
+        else:
+            try:
+                out[k] = int(v)
+            except ValueError:
+                out[k] = float(v.lower().replace("d", "e"))
+    return out
+
+
+def _sym_from_triples(d, n):
+    m = np.zeros((n, n))
+    i, j = d[:, 0].astype(int) - 1, d[:, 1].astype(int) - 1
+    m[i, j] = d[:, 2]
+    m[j, i] = d[:, 2]
+    return m
+
+
+def read_inputs(dirpath) -> ElsInput:
+    """read_system_in, read_integrals_in, read_geometry_in (src/system.f90:81, integrals.f90:48, geometry.f90:8)."""
+    inp = ElsInput()
+    with open(os.path.join(dirpath, "els.in")) as f:
+        for k, v in parse_namelist(f.read()).items():
+            if hasattr(inp, k):
+                setattr(inp, k, v)
+    if inp.calc_type not in CALC_TYPES:
+        raise ValueError("system::read_system_in: Unrecognised calculation type!")
+    s = np.loadtxt(os.path.join(dirpath, "s.dat"), ndmin=2)
+    n = int(max(s[:, 0].max(), s[:, 1].max()))
+    inp.nbasis = n
+    inp.ovlp = _sym_from_triples(s, n)
+    inp.core_hamil = _sym_from_triples(np.loadtxt(os.path.join(dirpath, "t.dat"), ndmin=2), n) + \
+        _sym_from_triples(np.loadtxt(os.path.join(dirpath, "v.dat"), ndmin=2), n)
+    d = np.loadtxt(os.path.join(dirpath, "eri.dat"), ndmin=2)
+    idx = d[:, :4].astype(np.int64) - 1
+    npair = n * (n + 1) // 2
+    eri = np.zeros(npair * (npair + 1) // 2)
+    eri[pair_index(pair_index(idx[:, 0], idx[:, 1]), pair_index(idx[:, 2], idx[:, 3]))] = d[:, 4]
+    inp.eri = eri
+    with open(os.path.join(dirpath, "geom.dat")) as f:
+        toks = f.read().split()
+    nat = int(toks[0])
+    g = np.array(toks[1:1 + 4 * nat], dtype=float).reshape(nat, 4)
+    set_geometry(inp, g[:, 0], g[:, 1:])
+    if inp.scf_read_guess:
+        gd = np.loadtxt(os.path.join(dirpath, "guess_in.dat"), ndmin=2)
+        inp.guess = np.zeros((n, n))
+        inp.guess[gd[:, 0].astype(int) - 1, gd[:, 1].astype(int) - 1] = gd[:, 2]
+    return inp
+
+
+def set_geometry(inp: ElsInput, charges, xyz):
+    z = np.asarray(charges).astype(int)  # charges(i) = int(charge)  (src/geometry.f90:33)
+    xyz = np.asarray(xyz, dtype=float)
+    inp.nel = int(z.sum())
+    e = 0.0
+    for j in range(1, len(z)):
+        for i in range(j):
+            e += z[i] * z[j] / np.linalg.norm(xyz[i] - xyz[j])
+    inp.e_nuc = e
+
+
+def _unpack(packed, n):
+    r = np.arange(n)
+    ij = pair_index(r[:, None], r[None, :])
+    return packed[pair_index(ij[:, :, None, None], ij[None, None, :, :])]
+
+
+def rhf(inp: ElsInput, out=None):
+    """do_rhf (src/hf.f90:21-151) with Pulay DIIS (:197-242); returns (e_elec, C[mo,ao], eps, table, converged)."""
+    n, nocc = inp.nbasis, inp.nel // 2
+    S, h = inp.ovlp, inp.core_hamil
+    g = _unpack(inp.eri, n)
+    J_src = g                      # (ij|kl)
+    K_src = g.transpose(0, 2, 1, 3)  # (ik|jl) viewed as [i,j,k,l]
+    w, U = np.linalg.eigh(S)
+    X = U @ np.diag(1.0 / np.sqrt(w)) @ U.T
+    F = inp.guess.copy() if (inp.scf_read_guess and inp.guess is not None) else h.copy()
+    nerr = inp.scf_diis_n_errmat
+    use_diis = nerr >= 2
+    Fs = np.zeros((max(nerr, 1), n, n))
+    Es = np.zeros((max(nerr, 1), n, n))
+    slot = n_active = 0
+    energy, D_old = 0.0, np.zeros((n, n))
+    table, conv = [], False
+    C_mo = eps = None
+    t0 = time.perf_counter()
+    for it in range(1, inp.scf_maxiter + 1):
+        eps, Cp = np.linalg.eigh(X.T @ F @ X)
+        C_mo = (X @ Cp).T
+        D = C_mo[:nocc].T @ C_mo[:nocc]
+        e_old, energy = energy, float(np.sum(D * (h + F)))
+        rms = float(np.sqrt(np.sum((D - D_old) ** 2)))
+        conv = rms < inp.scf_d_tol and abs(energy - e_old) < inp.scf_e_tol
+        D_old = D
+        t1 = time.perf_counter()
+        table.append((it, energy, energy - e_old, rms))
+        if out is not None:
+            out.write(" %9d   %15.10f   %15.10f   %15.10f   %8.6f\n" % (it, energy, energy - e_old, rms, t1 - t0))
+        t0 = t1
+        if conv:
+            break
+        F = h + 2.0 * np.einsum("ijkl,kl->ij", J_src, D) - np.einsum("ijkl,kl->ij", K_src, D)
+        if use_diis:
+            slot = slot + 1 if slot < nerr else 1
+            n_active = min(n_active + 1, nerr)
+            Fs[slot - 1] = F
+            Es[slot - 1] = F @ D @ S - S @ D @ F
+            na = n_active
+            if na > 1:
+                B = np.zeros((na + 1, na + 1))
+                for i in range(na):
+                    for j in range(i + 1):
+                        B[i, j] = B[j, i] = np.sum(Es[i] * Es[j])
+                B[na, :na] = B[:na, na] = -1.0
+                rhs = np.zeros(na + 1)
+                rhs[na] = -1.0
+                c = np.linalg.solve(B, rhs)
+                F = np.tensordot(c[:na], Fs[:na], axes=(0, 0))
+    return energy, C_mo, eps, table, conv
+
+
+def assemble_triples(e_ccsd, sums, const, paren, renorm, comp_renorm):
+    """Energy assembly of do_ccsd_t_spatial (src/ccsd.f90:2239-2276)."""
+    e_T, e_TT, D_T, D_TT, e_CR, e_CRT = [float(x) for x in sums]
+    en = {}
+    if renorm or comp_renorm:
+        D_T += const
+        if paren:
+            D_TT += const
+    en["e_ccsd_t"] = e_ccsd + e_T
+    if paren:
+        en["e_ccsd_tt"] = e_ccsd + e_TT
+    if renorm or comp_renorm:
+        en["e_rccsd_t"] = e_ccsd + e_T / D_T
+        en["D_T"] = D_T
+        if paren:
+            en["e_rccsd_tt"] = e_ccsd + e_TT / D_TT
+        if comp_renorm:
+            en["e_crccsd_t"] = e_ccsd + e_CR / D_T
+            en["D_TT"] = D_TT
+            if paren:
+                en["e_crccsd_tt"] = e_ccsd + e_CRT / D_TT
+    return en
+
+
+def ccsd_loop(gpu: AfespGpu, nocc, restricted, eps, e_tol, t_tol, diis_n, maxiter, out=None):
+    """The iteration loop of do_ccsd_spatial / do_ccsd_spinorb (src/ccsd.f90:339-396 / 229-271) on the host side:
+    the GPU does one iteration per call, the host keeps the table, the convergence test (:1805) and the DIIS call."""
+    e, rms = gpu.ccsd_init(nocc, restricted, eps, diis_n)
+    table = [("MP1", e, e - 0.0, rms)]
+    if out is not None:
+        out.write("-" * 75 + "\n Iteration        Energy           deltaE          delta RMS T2      Time  \n" + "-" * 75 + "\n")
+        out.write(" %9s   %15.12f   %15.12f   %15.12f\n" % ("MP1", e, e, rms))
+    conv = False
+    e_old = e
+    ms = []
+    for it in range(1, maxiter + 1):
+        t0 = time.perf_counter()
+        e, rms = gpu.ccsd_iterate()
+        ms.append(gpu.last_stage_ms())
+        table.append((it, e, e - e_old, rms))
+        if out is not None:
+            out.write(" %9d   %15.12f   %15.12f   %15.12f   %8.6f\n" % (it, e, e - e_old, rms, time.perf_counter() - t0))
+        if np.sqrt(rms) < t_tol and abs(e - e_old) < e_tol:
+            conv = True
+            break
+        e_old = e
+        gpu.ccsd_diis()
+    return table, conv, e, ms
+
+
+def run(inp: ElsInput, gpu: AfespGpu | None = None, device: int = 0, verbose: bool = False) -> ElsResult:
+    """Whole program (src/main.F90): RHF on the host, everything from do_mp2_spatial onwards on the GPU."""
+    level, restricted, paren, renorm, comp_renorm = CALC_TYPES[inp.calc_type]
+    out = io.StringIO()
+    res = ElsResult(e_nuc=inp.e_nuc)
+    t0 = time.perf_counter()
+    out.write(" " + "-" * 23 + "\n Restricted Hartree-Fock\n " + "-" * 23 + "\n")
+    res.e_hf, C_mo, eps, res.scf_table, conv = rhf(inp, out)
+    res.coeff, res.eps = C_mo, eps
+    res.timings["rhf_s"] = time.perf_counter() - t0
+    if not conv:
+        out.write(" Convergence not reached, please increase maxiter.\n")
+    if level >= 1:
+        own = gpu is None
+        gpu = gpu or AfespGpu(device)
+        try:
+            nocc = inp.nel // 2
+            t0 = time.perf_counter()
+            out.write(" ----------\n MP2\n ----------\n Performing AO to MO ERI transformation...\n")
+            gpu.ao2mo(inp.nbasis, inp.eri, C_mo, want_result=False)
+            res.timings["ao2mo_device_ms"] = gpu.last_stage_ms()
+            out.write(" Calculating MP2 energy...\n")
+            res.e_mp2 = gpu.mp2_energy(nocc, eps)
+            out.write(" MP2 correlation energy (Hartree): %15.8f\n" % res.e_mp2)
+            res.timings["mp2_s"] = time.perf_counter() - t0
+            if level >= 2:
+                t0 = time.perf_counter()
+                out.write(" ----------\n CCSD\n ----------\n")
+                res.ccsd_table, res.ccsd_converged, res.e_ccsd, ms = ccsd_loop(
+                    gpu, nocc, restricted, eps, inp.ccsd_e_tol, inp.ccsd_t_tol, inp.ccsd_diis_n_errmat,
+                    inp.ccsd_maxiter, out)
+                res.timings["ccsd_iter_device_ms"] = ms
+                if res.ccsd_converged:
+                    out.write("-" * 75 + "\n Convergence reached within tolerance.\n")
+                    out.write(" Final CCSD Energy (Hartree): %15.12f\n" % res.e_ccsd)
+                res.t1_diagnostic, _, _ = gpu.ccsd_finalize(want_cr=comp_renorm)
+                res.timings["ccsd_s"] = time.perf_counter() - t0
+                if restricted and res.ccsd_converged:
+                    out.write(" T1 diagnostic: %8.5f\n" % res.t1_diagnostic)
+                if level >= 3 and res.ccsd_converged:
+                    t0 = time.perf_counter()
+                    out.write(" ----------\n CCSD(T)\n ----------\n")
+                    if restricted:
+                        sums, const = gpu.ccsd_t_spatial(paren, renorm, comp_renorm)
+                        res.energies = assemble_triples(res.e_ccsd, sums, const, paren, renorm, comp_renorm)
+                        res.energies["triples_sums"] = sums
+                    else:
+                        res.energies = {"e_ccsd_t": res.e_ccsd + gpu.ccsd_t_spinorb()}
+                    res.timings["triples_device_ms"] = gpu.last_stage_ms()
+                    res.timings["triples_s"] = time.perf_counter() - t0
+        finally:
+            if own:
+                gpu.close()
+    out.write(final_table(inp, res))
+    res.stdout = out.getvalue()
+    if verbose:
+        print(res.stdout)
+    return res
+
+
+def final_table(inp: ElsInput, r: ElsResult) -> str:
+    """The 'Final energy breakdown' block, labels byte-identical to src/main.F90:123-175 (parsed by els_wrapper.py)."""
+    level, restricted, paren, renorm, comp_renorm = CALC_TYPES[inp.calc_type]
+    base = r.e_hf + r.e_nuc
+    L = [" " + "=" * 64, " Final energy breakdown", " %-31s %15.10f" % ("RHF energy:", base)]
+
+    def two(label, corr):
+        L.append(" %-31s %15.10f" % (label + " correlation energy:", corr))
+        L.append(" %-31s %15.10f" % (label + " energy:", corr + base))
+
+    highest = 0.0
+    if level >= 1:
+        two("MP2", r.e_mp2)
+        highest = r.e_mp2
+    if level >= 2:
+        two("CCSD", r.e_ccsd)
+        highest = r.e_ccsd
+    en = r.energies
+    if level >= 3 and en:
+        if restricted:
+            two("CCSD[T]", en["e_ccsd_t"]); highest = en["e_ccsd_t"]
+            if paren:
+                two("CCSD(T)", en["e_ccsd_tt"]); highest = en["e_ccsd_tt"]
+            if renorm or comp_renorm:
+                two("R-CCSD[T]", en["e_rccsd_t"]); highest = en["e_rccsd_t"]
+                if paren:
+                    two("R-CCSD(T)", en["e_rccsd_tt"]); highest = en["e_rccsd_tt"]
+                if comp_renorm:
+                    two("CR-CCSD[T]", en["e_crccsd_t"]); highest = en["e_crccsd_t"]
+                    if paren:
+                        two("CR-CCSD(T)", en["e_crccsd_tt"]); highest = en["e_crccsd_tt"]
+        else:
+            two("CCSD(T)", en["e_ccsd_t"]); highest = en["e_ccsd_t"]
+    if level >= 2 and restricted:
+        L.append(" " + "-" * 47)
+        L.append(" %-31s %15.10f" % ("T1 diagnostic:", r.t1_diagnostic))
+    if (renorm or comp_renorm) and en:
+        L.append(" %-31s %15.10f" % ("D[T]:", en["D_T"]))
+        if paren:  # sys%D_TT is only set for the CR methods and prints as zero otherwise (src/ccsd.f90:2262-2266)
+            L.append(" %-31s %15.10f" % ("D(T):", en.get("D_TT", 0.0)))
+    L.append(" " + "-" * 47)
+    L.append(" %-31s %15.10f" % ("Total electronic energy:", r.e_hf + highest))
+    L.append(" %-31s %15.10f" % ("Nuclear repulsion:", r.e_nuc))
+    L.append(" %-31s %15.10f" % ("Total energy:", r.e_hf + highest + r.e_nuc))
+    return "\n".join(L) + "\n"

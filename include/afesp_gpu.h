@@ -1,0 +1,110 @@
+/* afesp_gpu.h -- C ABI of the B200-native coupled-cluster engine (libafesp_gpu.so).
+ *
+ * Drop-in boundary for the coupled-cluster hot path of AFESP (brianz98/A-Fortran-Electronic-Structure-Programme).
+ * The reference has no FFI today; the boundary sits at the call sites of src/main.F90 that enter the hot path
+ * (do_mp2_spatial :60/:98, do_ccsd_spinorb :67, do_ccsd_spatial :105, do_ccsd_t_spinorb[_acc] :75-79,
+ * do_ccsd_t_spatial :112) and follows the only precedent in the reference for handing plain arrays to an
+ * accelerator routine, do_ccsd_t_spinorb_acc (src/ccsd.f90:1924-1938; selected by `#ifdef OPENACC`, main.F90:74).
+ * shim/afesp_gpu.f90 holds the ISO_C_BINDING interfaces and INTEGRATION.md the edited call sites.
+ *
+ * Conventions (what a Fortran caller needs):
+ *   - every function returns an int status: 0 = ok, non-zero = failure (1 bad argument/state, 2 CUDA error,
+ *     3 linear solve failed, 4 NCCL error); afesp_gpu_last_error() gives the text.  The shim maps a non-zero
+ *     status to `call error('afesp_gpu::<fn>', msg)` -> stderr + stop 999 (src/error_handling.f90:7-20).
+ *   - scalars by value; arrays are caller-owned, contiguous, column-major real(c_double), never retained after the
+ *     call returns; a NULL output pointer means "do not copy back".
+ *   - the library prints nothing: the host program keeps every line of els.out.
+ *   - one handle = one CUDA device; all state between calls (integrals, amplitudes, intermediates, DIIS history)
+ *     stays on that device.  Calls on one handle must not overlap (the caller is single-threaded, main.F90).
+ *   - there is no CPU fallback: without a usable CUDA device afesp_gpu_open fails.
+ *
+ * Packed two-electron integrals use the reference's 8-fold canonical order (src/integrals.f90:196-210):
+ *   pair(i,j) = i(i-1)/2 + j (1-based, i >= j);  eri[pair(pair(i,j), pair(k,l))] = (ij|kl); length npair(npair+1)/2.
+ */
+#ifndef AFESP_GPU_H
+#define AFESP_GPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* afesp_handle;
+
+/* Context ------------------------------------------------------------------------------------------------------ */
+int afesp_gpu_open(int device, afesp_handle* h);
+int afesp_gpu_close(afesp_handle h);
+const char* afesp_gpu_last_error(afesp_handle h); /* h may be NULL: error of the last failed afesp_gpu_open */
+/* Parity switches, all default to the reference's as-coded behaviour (value 1):
+ *   "q1_transposed_foo"        spin-orbital F_mi dgemm term lands transposed (src/ccsd.f90:793-795)
+ *   "q3a_truncated_e"          `do e = 1, nocc` over a virtual index in I_ooov_pp (src/ccsd.f90:2535)
+ *   "q3b_stale_intermediates"  CR intermediates use I_vo/asym_t2 of the last iteration's input (src/ccsd.f90:2377)
+ *   "triples_ijk_symmetry"     (T) over unique i<=j<=k with multiplicities (1) or all o^3 ordered triples (0)
+ *   "triples_batch_bytes"      work-buffer budget of the (T) batches, bytes */
+int afesp_gpu_set_option(afesp_handle h, const char* key, double value);
+/* Kernel launches and executed DMMA flop (2*M*N*K per GEMM) since the handle was opened. */
+int afesp_gpu_counters(afesp_handle h, long long* launches, double* gemm_flops);
+
+/* AO->MO transform + MP2: replaces the body of do_mp2_spatial (src/mp2.f90:261-449) ---------------------------- */
+/* eri_ao[npacked], coeff(n,n) = C(mo,ao) (sys%canon_coeff, src/hf.f90:102,127) -> eri_mo[npacked] (host, optional).
+ * Passing eri_ao == NULL and coeff == NULL repeats the transform on the copies already resident on the device. */
+int afesp_gpu_ao2mo(afesp_handle h, int nbasis, const double* eri_ao, const double* coeff, double* eri_mo);
+/* Load packed MO integrals directly (a host that already holds int_store%eri_mo). */
+int afesp_gpu_set_eri_mo(afesp_handle h, int nbasis, const double* eri_mo);
+/* MP2 correlation energy from the device-resident MO integrals (src/mp2.f90:418-438); eps = sys%canon_levels(n). */
+int afesp_gpu_mp2_energy(afesp_handle h, int nocc, const double* eps, double* e_mp2);
+
+/* CCSD: replaces do_ccsd_spatial (src/ccsd.f90:279-402) / do_ccsd_spinorb (src/ccsd.f90:71-277) ----------------- */
+/* init_cc + init_diis_cc_t + the first update_cc_energy: returns the "MP1" line (energy, sum dT2^2).
+ * nocc = number of doubly occupied spatial orbitals (sys%nel/2) in both formulations. */
+int afesp_gpu_ccsd_init(afesp_handle h, int nocc, int restricted, const double* eps, int diis_n_errmat,
+                        double* e_mp1, double* rmst2);
+/* One pass of the iteration body up to and including update_cc_energy (src/ccsd.f90:340-359 / 230-246):
+ * stash amplitudes for DIIS, intermediates, amplitude equations, energy.  rmst2 is the squared norm the reference
+ * prints (src/ccsd.f90:1806); the host applies the convergence test of :1805. */
+int afesp_gpu_ccsd_iterate(afesp_handle h, double* e_cc, double* rmst2);
+/* update_diis_cc (src/ccsd.f90:617-676): extrapolate the amplitudes in place. */
+int afesp_gpu_ccsd_diis(afesp_handle h);
+/* After convergence (src/ccsd.f90:366-393 / 252-269): T1 diagnostic (spin-free: sqrt(sum t1^2)/sqrt(nel)), the CR
+ * intermediates when want_cr != 0, optional copies of t1(o,v) and t2(o,o,v,v).  Amplitudes and the integral
+ * slices (T) needs stay on the device (the int_store_cc hand-over of the reference). */
+int afesp_gpu_ccsd_finalize(afesp_handle h, int want_cr, double* t1_diagnostic, double* t1, double* t2);
+
+/* Triples: replaces do_ccsd_t_spatial (src/ccsd.f90:2018-2293) / do_ccsd_t_spinorb (src/ccsd.f90:1812-1922) ------ */
+/* sums[6] = e_T, e_TT, D_T, D_TT, e_CR, e_CRT as accumulated by the (i,j,k) loop (src/ccsd.f90:2218-2233), summed
+ * over all ranks of the communicator when one is attached; denominator_constant = 1 + 2 sum t1^2 + sum asym_t2*c
+ * (src/ccsd.f90:2243).  The host assembles the printed energies exactly as src/ccsd.f90:2239-2276. */
+int afesp_gpu_ccsd_t_spatial(afesp_handle h, int paren, int renorm, int comp_renorm, double sums[6],
+                             double* denominator_constant);
+/* e_T of src/ccsd.f90:1910 (host adds sys%e_ccsd). */
+int afesp_gpu_ccsd_t_spinorb(afesp_handle h, double* e_T);
+
+/* Multi-GPU: one process (or handle) per device; (T) triples are dealt round-robin over ranks and the six sums are
+ * combined with one ncclAllReduce.  The 128-byte id comes from rank 0 and is broadcast by the host (MPI, torchrun...). */
+int afesp_gpu_comm_unique_id(char id[128]);
+int afesp_gpu_comm_init(afesp_handle h, int rank, int nranks, const char id[128]);
+/* Without NCCL: give the handle a (rank, nranks) share only; the caller sums the partial results itself. */
+int afesp_gpu_set_partition(afesp_handle h, int rank, int nranks);
+/* Host-only: number of (i,j,k) work units per rank (no device needed). */
+int afesp_gpu_triples_partition(int nocc_active, int symmetric, int strict, int nranks, long long* counts);
+
+/* Operators of src/linalg.fpp on host arrays (used by the parity tests; the CC drivers call the same kernels) ---- */
+/* dgemm_wrapper (src/linalg.fpp:58-89): C(MxN) = alpha*op(A)(MxK)*op(B)(KxN) + beta*C, leading dimensions inferred
+ * exactly as the reference does (LDA = K if transA=='T' else M; LDB = N if transB=='T' else K; LDC = M). */
+int afesp_gpu_dgemm_wrapper(afesp_handle h, char transA, char transB, int outer_row, int outer_col, int inner_dim,
+                            const double* A, const double* B, double* C, double alpha, double beta);
+/* omp_reshape (src/linalg.fpp:99-156): out(perm(i,j,k,l)) = beta*out + in(i,j,k,l); arr_order e.g. "2341" means
+ * out(j,k,l,i) = in(i,j,k,l).  has_beta == 0 reproduces the absent optional argument (out is overwritten). */
+int afesp_gpu_omp_reshape(afesp_handle h, double* out_arr, const double* in_arr, const int in_dims[4],
+                          const char arr_order[4], int has_beta, double beta);
+/* Synthetic-workload helper (bench): time `reps` back-to-back device-resident dgemms, returns milliseconds/gemm. */
+int afesp_gpu_bench_dgemm(afesp_handle h, char transA, char transB, int M, int N, int K, int reps, double* ms);
+/* Raw DMMA issue-rate probe: register-resident mma.sync loop on all SMs; returns TFLOP/s (the FP64 tensor peak the
+ * roofline fractions are quoted against; MEASURED_PEAKS.json has no FP64 entry). */
+int afesp_gpu_dmma_peak(afesp_handle h, double* tflops);
+/* Time the (i,j,k)-sharded triples of the current state without recomputing CCSD: ms of device time. */
+int afesp_gpu_last_stage_ms(afesp_handle h, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFESP_GPU_H */

@@ -39,3 +39,24 @@ def load_system(name, calc_type=None):
     if sysm.scf_read_guess and z["guess"].size:
         sysm.guess = z["guess"]
     return sysm
+
+
+def load_els_input(name, calc_type=None):
+    """The same fixture as an afesp_b200.host.ElsInput (the product host type; no oracle involved)."""
+    from afesp_b200 import host
+
+    z = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
+    inp = host.ElsInput()
+    for k, v in host.parse_namelist(str(z["els_in"])).items():
+        if hasattr(inp, k):
+            setattr(inp, k, v)
+    if calc_type is not None:
+        inp.calc_type = calc_type
+    inp.ovlp = z["ovlp"]
+    inp.core_hamil = z["ke"] + z["en"]
+    inp.eri = z["eri"]
+    inp.nbasis = inp.ovlp.shape[0]
+    host.set_geometry(inp, z["geom"][:, 0], z["geom"][:, 1:])
+    if inp.scf_read_guess and z["guess"].size:
+        inp.guess = z["guess"]
+    return inp

@@ -1,0 +1,218 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle and the reference's golden outputs.
+
+Tolerances (BASELINE.json north_star): energies within 1e-9 Eh, converged amplitudes within 1e-8, identical
+iteration counts.  Index permutations are bit-exact; GEMMs are compared at 1e-12 relative to the operand scale.
+"""
+import numpy as np
+import pytest
+
+from oracle import afesp_oracle as orc
+from tests._fixtures import golden, load_els_input, load_system
+
+pytestmark = pytest.mark.gpu
+
+E_TOL = 1e-9
+G = golden()
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from afesp_b200 import AfespGpu
+
+    g = AfespGpu(0)
+    yield g
+    g.close()
+
+
+# ---------------------------------------------------------------- operators of linalg.fpp
+@pytest.mark.parametrize("ta", ["N", "T"])
+@pytest.mark.parametrize("tb", ["N", "T"])
+@pytest.mark.parametrize("shape", [(1, 1, 1), (7, 5, 3), (33, 65, 17), (130, 129, 70), (20, 400, 64), (257, 31, 300),
+                                   (441, 49, 441), (64, 64, 4096), (21, 21, 3087), (128, 256, 64)])
+def test_dgemm_wrapper_matches_blas_semantics(gpu, ta, tb, shape):
+    M, N, K = shape
+    rng = np.random.default_rng(M * 1000 + N * 10 + K)
+    A = rng.standard_normal((K, M) if ta == "T" else (M, K))
+    B = rng.standard_normal((N, K) if tb == "T" else (K, N))
+    C0 = rng.standard_normal((M, N))
+    opA = A.T if ta == "T" else A
+    opB = B.T if tb == "T" else B
+    for alpha, beta in [(1.0, 0.0), (0.5, 1.0), (-1.0, 0.25)]:
+        want = alpha * (opA @ opB) + beta * C0
+        got = gpu.dgemm_wrapper(ta, tb, M, N, K, A.ravel(order="F"), B.ravel(order="F"), C0.ravel(order="F"),
+                                alpha, beta).reshape((M, N), order="F")
+        scale = np.abs(opA) @ np.abs(opB) + np.abs(C0)
+        assert np.max(np.abs(got - want) / scale) < 1e-13
+
+
+def test_dgemm_beta_zero_ignores_nan_in_c(gpu):
+    A = np.ones((4, 3)); B = np.ones((3, 5)); Cn = np.full((4, 5), np.nan)
+    got = gpu.dgemm_wrapper("N", "N", 4, 5, 3, A.ravel(order="F"), B.ravel(order="F"), Cn.ravel(order="F"), 1.0, 0.0)
+    assert np.array_equal(got, np.full(20, 3.0))
+
+
+def test_omp_reshape_all_24_orders_bit_exact(gpu):
+    import itertools
+
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((5, 7, 19, 3))
+    for perm in itertools.permutations("1234"):
+        order = "".join(perm)
+        axes = [int(c) - 1 for c in order]
+        want = np.transpose(x, axes)  # out(perm(i,j,k,l)) = in(i,j,k,l)   (src/linalg.fpp:133-147)
+        got = gpu.omp_reshape(x, order)
+        assert np.array_equal(got, want), order
+        y = rng.standard_normal(want.shape)
+        got2 = gpu.omp_reshape(x, order, out_arr=y, beta=-0.5)
+        assert np.array_equal(got2, -0.5 * y + want), order
+
+
+def test_omp_reshape_large_transpose_bit_exact(gpu):
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((20, 20, 45, 45))
+    for order in ["3412", "2143", "4321", "1342", "3124"]:
+        axes = [int(c) - 1 for c in order]
+        assert np.array_equal(gpu.omp_reshape(x, order), np.transpose(x, axes))
+
+
+# ---------------------------------------------------------------- AO->MO + MP2
+@pytest.mark.parametrize("name", ["n2", "f2", "h2o"])
+def test_ao2mo_and_mp2_match_oracle_and_golden(gpu, name, oracle_runs):
+    s, r = oracle_runs(name, "MP2_spatial")
+    eri_mo = gpu.ao2mo(s.nbasis, s.eri, s.coeff)
+    assert np.max(np.abs(eri_mo - s.eri_mo)) < 1e-11
+    e = gpu.mp2_energy(s.nel // 2, s.eps)
+    assert abs(e - r["e_mp2"]) < E_TOL
+    key = "MP2 correlation energy" if name != "h2o" else "E_MP2_corr"
+    assert abs(e - G[name]["final"][key]) < E_TOL + 0.5e-10
+
+
+# ---------------------------------------------------------------- full program through the product host driver
+def _check_table(table, gold_rows, tol=E_TOL):
+    assert len(table) == len(gold_rows), "iteration count differs from the reference"
+    for (it, e, de, rms), row in zip(table, gold_rows):
+        assert str(it) == str(row[0])
+        assert abs(e - row[1]) < tol, (it, e, row[1])
+        if len(row) > 3:
+            assert abs(rms - row[3]) < 1e-9
+
+
+FINAL_MAP = {
+    "CCSD[T] correlation energy": "e_ccsd_t", "CCSD(T) correlation energy": "e_ccsd_tt",
+    "R-CCSD[T] correlation energy": "e_rccsd_t", "R-CCSD(T) correlation energy": "e_rccsd_tt",
+    "CR-CCSD[T] correlation energy": "e_crccsd_t", "CR-CCSD(T) correlation energy": "e_crccsd_tt",
+    "D[T]": "D_T", "D(T)": "D_TT",
+}
+
+
+@pytest.mark.parametrize("name", ["n2", "f2"])
+def test_crccsd_t_spatial_matches_shipped_els_out(gpu, name):
+    from afesp_b200 import host
+
+    inp = load_els_input(name)  # CRCCSD(T)_spatial as shipped
+    res = host.run(inp, gpu=gpu)
+    g = G[name]
+    assert len(res.scf_table) == len(g["scf"])
+    assert abs(res.e_hf + res.e_nuc - g["final"]["RHF energy"]) < E_TOL
+    assert abs(res.e_mp2 - g["final"]["MP2 correlation energy"]) < E_TOL
+    assert res.ccsd_converged
+    _check_table(res.ccsd_table, g["ccsd"])
+    assert abs(res.e_ccsd - g["e_ccsd_12"]) < E_TOL
+    assert abs(res.t1_diagnostic - g["final"]["T1 diagnostic"]) < E_TOL
+    for label, key in FINAL_MAP.items():
+        assert abs(res.energies[key] - g["final"][label]) < E_TOL + 0.5e-10, (label, res.energies[key], g["final"][label])
+    # the printed block keeps the reference's labels
+    for label in ["CR-CCSD(T) correlation energy:", "T1 diagnostic:", "D[T]:", "Total energy:"]:
+        assert label in res.stdout
+
+
+@pytest.mark.parametrize("calc", ["CCSD(T)_spatial", "CCSD[T]_spatial", "RCCSD(T)_spatial", "RCCSD[T]_spatial",
+                                  "CRCCSD[T]_spatial"])
+def test_spatial_calc_types_match_oracle(gpu, calc, oracle_runs):
+    from afesp_b200 import host
+
+    s, r = oracle_runs("h2o", calc)
+    res = host.run(load_els_input("h2o", calc), gpu=gpu)
+    assert len(res.ccsd_table) == len(r["ccsd"])
+    assert abs(res.e_ccsd - r["e_ccsd"]) < E_TOL
+    for key in ["e_ccsd_t", "e_ccsd_tt", "e_rccsd_t", "e_rccsd_tt", "e_crccsd_t", "e_crccsd_tt", "D_T", "D_TT"]:
+        assert (key in r) == (key in res.energies), key
+        if key in r:
+            assert abs(res.energies[key] - r[key]) < E_TOL, (key, res.energies[key], r[key])
+    if calc == "CCSD(T)_spatial":  # Q2: E(T) == E[T] as coded
+        assert abs(res.energies["e_ccsd_tt"] - res.energies["e_ccsd_t"]) < 1e-13
+
+
+def test_converged_amplitudes_match_oracle(gpu, oracle_runs):
+    s, r = oracle_runs("h2o", "CCSD_spatial")
+    gpu.ao2mo(s.nbasis, s.eri, s.coeff, want_result=False)
+    from afesp_b200 import host
+
+    table, conv, e, _ = host.ccsd_loop(gpu, s.nel // 2, True, s.eps, s.ccsd_e_tol, s.ccsd_t_tol,
+                                       s.ccsd_diis_n_errmat, s.ccsd_maxiter)
+    _, t1, t2 = gpu.ccsd_finalize(want_amplitudes=True)
+    cc = r["cc"]
+    assert conv and len(table) == len(r["ccsd"])
+    assert np.sqrt(np.mean((t1 - cc["t1"]) ** 2)) < 1e-8 and np.max(np.abs(t1 - cc["t1"])) < 1e-8
+    assert np.sqrt(np.mean((t2 - cc["t2"]) ** 2)) < 1e-8 and np.max(np.abs(t2 - cc["t2"])) < 1e-8
+
+
+# ---------------------------------------------------------------- spin-orbital path
+def test_spinorbital_ccsd_matches_old_ref_out_with_q1_off(gpu):
+    from afesp_b200 import host
+
+    gpu.set_option("q1_transposed_foo", 0)
+    try:
+        res = host.run(load_els_input("h2o", "CCSD_spinorb"), gpu=gpu)
+    finally:
+        gpu.set_option("q1_transposed_foo", 1)
+    rows = res.ccsd_table[1:]
+    assert len(rows) == len(G["h2o"]["ccsd"]) == 19
+    for (it, e, _, _), (git, ge) in zip(rows, G["h2o"]["ccsd"]):
+        assert it == git and abs(e - ge) < E_TOL
+
+
+def test_spinorbital_ccsd_t_as_coded_matches_oracle(gpu, oracle_runs):
+    from afesp_b200 import host
+
+    s, r = oracle_runs("h2o", "CCSD(T)_spinorb", q1=True)
+    res = host.run(load_els_input("h2o", "CCSD(T)_spinorb"), gpu=gpu)
+    assert len(res.ccsd_table) == len(r["ccsd"])
+    for (it, e, _, rms), (oit, oe, _, orms) in zip(res.ccsd_table, r["ccsd"]):
+        assert abs(e - oe) < E_TOL and abs(rms - orms) < 1e-9
+    assert abs(res.e_ccsd - (-0.311554581875)) < E_TOL
+    assert abs(res.energies["e_ccsd_t"] - r["e_ccsd_t"]) < E_TOL
+
+
+# ---------------------------------------------------------------- (T) sharding and symmetry properties
+def test_triples_partition_sums_and_symmetry_switch(gpu, oracle_runs):
+    from afesp_b200 import host
+
+    s, r = oracle_runs("f2")  # CRCCSD(T)_spatial
+    gpu.ao2mo(s.nbasis, s.eri, s.coeff, want_result=False)
+    host.ccsd_loop(gpu, s.nel // 2, True, s.eps, s.ccsd_e_tol, s.ccsd_t_tol, s.ccsd_diis_n_errmat, s.ccsd_maxiter)
+    gpu.ccsd_finalize(want_cr=True)
+    full, const = gpu.ccsd_t_spatial(True, False, True)
+    want = np.array(r["triples_sums"])
+    assert np.max(np.abs(full - want)) < E_TOL
+    # the work dealt to 3 "ranks" adds up to the whole (what the NCCL allreduce does across GPUs)
+    parts = []
+    for rank in range(3):
+        gpu.set_partition(rank, 3)
+        parts.append(gpu.ccsd_t_spatial(True, False, True)[0])
+    gpu.set_partition(0, 1)
+    assert np.max(np.abs(np.sum(parts, axis=0) - full)) < 1e-11
+    # all o^3 ordered triples (the reference's loop) give the same sums as the i<=j<=k orbit form
+    gpu.set_option("triples_ijk_symmetry", 0)
+    try:
+        allo3, _ = gpu.ccsd_t_spatial(True, False, True)
+    finally:
+        gpu.set_option("triples_ijk_symmetry", 1)
+    assert np.max(np.abs(allo3 - full)) < 1e-10
+    # tiny work buffer -> many batches, same answer
+    gpu.set_option("triples_batch_bytes", 1 << 20)
+    try:
+        small, _ = gpu.ccsd_t_spatial(True, False, True)
+    finally:
+        gpu.set_option("triples_batch_bytes", 6 << 30)
+    assert np.max(np.abs(small - full)) < 1e-11
