@@ -36,6 +36,7 @@ SIGNATURES = {
     "afesp_gpu_bench_dgemm": [_H, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_int, _dp],
     "afesp_gpu_dmma_peak": [_H, _dp],
     "afesp_gpu_last_stage_ms": [_H, _dp],
+    "afesp_gpu_gemm_time": [_H, _dp, _dp],
 }
 
 _lib = None
@@ -261,6 +262,12 @@ class AfespGpu:
         self._check("bench_dgemm", self.lib.afesp_gpu_bench_dgemm(self.h, transA.encode(), transB.encode(), int(M),
                                                                   int(N), int(K), int(reps), C.byref(ms)))
         return ms.value
+
+    def gemm_time(self):
+        """(milliseconds, executed flop) of all DMMA GEMM launches since option gemm_timing was set / last call."""
+        ms, fl = C.c_double(0), C.c_double(0)
+        self._check("gemm_time", self.lib.afesp_gpu_gemm_time(self.h, C.byref(ms), C.byref(fl)))
+        return ms.value, fl.value
 
     def dmma_peak(self):
         t = C.c_double(0)

@@ -176,6 +176,8 @@ int afesp_gpu_set_option(afesp_handle hv, const char* key, double value) {
     else if (k == "q3b_stale_intermediates") o.q3b_stale_intermediates = value != 0.0;
     else if (k == "triples_ijk_symmetry") o.triples_ijk_symmetry = value != 0.0;
     else if (k == "triples_batch_bytes") o.triples_batch_bytes = (long long)value;
+    else if (k == "finalize_keep_ccsd") o.finalize_keep_ccsd = value != 0.0;
+    else if (k == "gemm_timing") gemm_timing_enable(value != 0.0);
     else throw Error(1, "set_option: unknown key " + k);
   });
 }
@@ -303,6 +305,12 @@ int afesp_gpu_ccsd_finalize(afesp_handle hv, int want_cr, double* t1_diag, doubl
       ccsd_spatial_cr_intermediates(s);
     }
     // release what the (T) stage does not need (the reference's cc_int goes out of scope, src/ccsd.f90:386-392)
+    if (s.opt.finalize_keep_ccsd) {
+      tm.stop();
+      if (t1) AFESP_CUDA_CHECK(cudaMemcpy(t1, s.t1.p(), s.t1.size() * 8, cudaMemcpyDeviceToHost));
+      if (t2) AFESP_CUDA_CHECK(cudaMemcpy(t2, s.t2.p(), s.t2.size() * 8, cudaMemcpyDeviceToHost));
+      return;
+    }
     s.diis = CCDiis();
     for (const char* nm : {"v_vvvv", "W_efab", "vvvv", "ovvv", "W_vvov", "I_oooo", "I_ovov", "I_voov", "I_ooov_p",
                            "x_voov", "c_oovv", "A_oovv", "W_ijmn", "W_ovvo", "tau", "tau_tilde"})
@@ -474,6 +482,14 @@ int afesp_gpu_dmma_peak(afesp_handle hv, double* tflops) {
     AFESP_CUDA_CHECK(cudaGetLastError());
     const double flops = 2.0 * 256.0 * 8.0 * iters * (threads / 32.0) * blocks;
     *tflops = flops / (h.last_ms * 1e-3) / 1e12;
+  });
+}
+
+int afesp_gpu_gemm_time(afesp_handle hv, double* ms, double* flops) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(ms && flops, "gemm_time: null output");
+    AFESP_CUDA_CHECK(cudaStreamSynchronize(h.s.eng.stream));
+    *ms = gemm_timing_collect(flops);
   });
 }
 

@@ -28,6 +28,7 @@ struct Options {
   bool q3b_stale_intermediates = true;  // CR intermediates read I_vo/asym_t2 of the last iteration's input (:2377)
   bool triples_ijk_symmetry = true;     // (T): loop unique i<=j<=k with multiplicities instead of all o^3
   long long triples_batch_bytes = 6LL << 30;
+  bool finalize_keep_ccsd = false;      // keep DIIS history and intermediates after finalize (benchmark loops)
 };
 
 struct CCState {

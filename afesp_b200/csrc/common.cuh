@@ -73,6 +73,10 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
            const GemmBatch* batch = nullptr);
 // Executed DMMA flop counter (2*M*N*K per gemm), for "% of FP64 tensor peak" from executed flops.
 extern double g_gemm_flops;
+// Optional per-launch device timing of the GEMM kernel (CUDA events on the launching stream), used by bench.py for
+// the live roofline figure.  gemm_timing_collect() synchronises and returns the accumulated milliseconds.
+void gemm_timing_enable(bool on);
+double gemm_timing_collect(double* flops_out);
 
 // ---- permute (permute.cu): out = alpha * permute(in) + beta * out for rank <= 6 ----
 // perm[d] = which input axis becomes output axis d (numpy transpose convention), dims = input extents,

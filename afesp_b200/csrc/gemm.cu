@@ -233,6 +233,32 @@ __global__ void scale_c(double* C, int M, int N, long long ldc, double beta) {
 int g_num_sms = 0;
 DBuf g_ws;  // split-K workspace, grown on demand
 
+// per-launch event timing (off by default)
+bool g_timing = false;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_ev_pool;
+size_t g_ev_used = 0;
+double g_timed_ms = 0.0, g_timed_flops = 0.0;
+double drain_events() {
+  double ms = 0.0;
+  for (size_t i = 0; i < g_ev_used; ++i) {
+    cudaEventSynchronize(g_ev_pool[i].second);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, g_ev_pool[i].first, g_ev_pool[i].second);
+    ms += t;
+  }
+  g_ev_used = 0;
+  return ms;
+}
+std::pair<cudaEvent_t, cudaEvent_t>* next_events() {
+  if (g_ev_used == 2048) g_timed_ms += drain_events();
+  if (g_ev_used == g_ev_pool.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    g_ev_pool.emplace_back(a, b);
+  }
+  return &g_ev_pool[g_ev_used++];
+}
+
 int num_sms() {
   if (!g_num_sms) {
     int dev = 0;
@@ -336,6 +362,8 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
       }
     }
   }
+  std::pair<cudaEvent_t, cudaEvent_t>* evs = g_timing ? next_events() : nullptr;
+  if (evs) { cudaEventRecord(evs->first, st); g_timed_flops += 2.0 * M * N * (double)K * nbatch; }
   switch (cfg) {
     case L: launch_tile<128, 128, 64, 32, 3>(st, p, nbatch, ak, bk, vec2); break;
     case S: launch_tile<64, 64, 32, 32, 3>(st, p, nbatch, ak, bk, vec2); break;
@@ -349,6 +377,20 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
     count_launch();
     AFESP_CUDA_CHECK(cudaGetLastError());
   }
+  if (evs) cudaEventRecord(evs->second, st);
+}
+
+void gemm_timing_enable(bool on) {
+  if (on && !g_timing) { g_timed_ms = 0.0; g_timed_flops = 0.0; g_ev_used = 0; }
+  g_timing = on;
+}
+
+double gemm_timing_collect(double* flops_out) {
+  g_timed_ms += drain_events();
+  double ms = g_timed_ms;
+  if (flops_out) *flops_out = g_timed_flops;
+  g_timed_ms = 0.0; g_timed_flops = 0.0;
+  return ms;
 }
 
 }  // namespace afesp

@@ -39,7 +39,10 @@ const char* afesp_gpu_last_error(afesp_handle h); /* h may be NULL: error of the
  *   "q3a_truncated_e"          `do e = 1, nocc` over a virtual index in I_ooov_pp (src/ccsd.f90:2535)
  *   "q3b_stale_intermediates"  CR intermediates use I_vo/asym_t2 of the last iteration's input (src/ccsd.f90:2377)
  *   "triples_ijk_symmetry"     (T) over unique i<=j<=k with multiplicities (1) or all o^3 ordered triples (0)
- *   "triples_batch_bytes"      work-buffer budget of the (T) batches, bytes */
+ *   "triples_batch_bytes"      work-buffer budget of the (T) batches, bytes
+ * Measurement switches (default 0):
+ *   "finalize_keep_ccsd"       afesp_gpu_ccsd_finalize keeps the DIIS history and intermediates (benchmark loops)
+ *   "gemm_timing"              bracket every DMMA GEMM launch with CUDA events (see afesp_gpu_gemm_time) */
 int afesp_gpu_set_option(afesp_handle h, const char* key, double value);
 /* Kernel launches and executed DMMA flop (2*M*N*K per GEMM) since the handle was opened. */
 int afesp_gpu_counters(afesp_handle h, long long* launches, double* gemm_flops);
@@ -101,8 +104,11 @@ int afesp_gpu_bench_dgemm(afesp_handle h, char transA, char transB, int M, int N
 /* Raw DMMA issue-rate probe: register-resident mma.sync loop on all SMs; returns TFLOP/s (the FP64 tensor peak the
  * roofline fractions are quoted against; MEASURED_PEAKS.json has no FP64 entry). */
 int afesp_gpu_dmma_peak(afesp_handle h, double* tflops);
-/* Time the (i,j,k)-sharded triples of the current state without recomputing CCSD: ms of device time. */
+/* Device time (CUDA events on the engine's stream) of the last stage call on this handle, milliseconds. */
 int afesp_gpu_last_stage_ms(afesp_handle h, double* ms);
+/* With option "gemm_timing" on: accumulated device milliseconds and executed flop of all DMMA GEMM launches since the
+ * option was switched on or since the previous call (synchronises the stream). */
+int afesp_gpu_gemm_time(afesp_handle h, double* ms, double* flops);
 
 #ifdef __cplusplus
 }
