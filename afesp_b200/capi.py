@@ -33,7 +33,7 @@ SIGNATURES = {
     "afesp_gpu_triples_partition": [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)],
     "afesp_gpu_dgemm_wrapper": [_H, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double],
     "afesp_gpu_omp_reshape": [_H, _dp, _dp, _ip, C.c_char_p, C.c_int, C.c_double],
-    "afesp_gpu_bench_dgemm": [_H, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_int, _dp],
+    "afesp_gpu_bench_dgemm": [_H, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, _dp],
     "afesp_gpu_dmma_peak": [_H, _dp],
     "afesp_gpu_last_stage_ms": [_H, _dp],
     "afesp_gpu_gemm_time": [_H, _dp, _dp],
@@ -257,10 +257,10 @@ class AfespGpu:
             float(beta if beta is not None else 0.0)))
         return out.reshape(oshape, order="F")
 
-    def bench_dgemm(self, transA, transB, M, N, K, reps=5):
+    def bench_dgemm(self, transA, transB, M, N, K, reps=5, beta=0.0):
         ms = C.c_double(0)
         self._check("bench_dgemm", self.lib.afesp_gpu_bench_dgemm(self.h, transA.encode(), transB.encode(), int(M),
-                                                                  int(N), int(K), int(reps), C.byref(ms)))
+                                                                  int(N), int(K), float(beta), int(reps), C.byref(ms)))
         return ms.value
 
     def gemm_time(self):

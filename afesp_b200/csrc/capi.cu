@@ -178,6 +178,7 @@ int afesp_gpu_set_option(afesp_handle hv, const char* key, double value) {
     else if (k == "triples_batch_bytes") o.triples_batch_bytes = (long long)value;
     else if (k == "finalize_keep_ccsd") o.finalize_keep_ccsd = value != 0.0;
     else if (k == "gemm_timing") gemm_timing_enable(value != 0.0);
+    else if (k == "gemm_force_config") gemm_force_config((int)value);
     else throw Error(1, "set_option: unknown key " + k);
   });
 }
@@ -446,7 +447,7 @@ int afesp_gpu_omp_reshape(afesp_handle hv, double* out_arr, const double* in_arr
   });
 }
 
-int afesp_gpu_bench_dgemm(afesp_handle hv, char ta, char tb, int M, int N, int K, int reps, double* ms) {
+int afesp_gpu_bench_dgemm(afesp_handle hv, char ta, char tb, int M, int N, int K, double beta, int reps, double* ms) {
   return guarded(hv, [&](Handle& h) {
     AFESP_REQUIRE(M > 0 && N > 0 && K > 0 && reps > 0 && ms, "bench_dgemm: bad arguments");
     const bool tA = (ta == 'T' || ta == 't'), tB = (tb == 'T' || tb == 't');
@@ -458,7 +459,7 @@ int afesp_gpu_bench_dgemm(afesp_handle hv, char ta, char tb, int M, int N, int K
     dgemm(st, ta, tb, M, N, K, 1.0, dA.p, lda, dB.p, ldb, 0.0, dC.p, M);  // warm-up
     AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
     StageTimer tm(&h);
-    for (int r = 0; r < reps; ++r) dgemm(st, ta, tb, M, N, K, 1.0, dA.p, lda, dB.p, ldb, 0.0, dC.p, M);
+    for (int r = 0; r < reps; ++r) dgemm(st, ta, tb, M, N, K, 1.0, dA.p, lda, dB.p, ldb, beta, dC.p, M);
     tm.stop();
     AFESP_CUDA_CHECK(cudaGetLastError());
     *ms = h.last_ms / reps;

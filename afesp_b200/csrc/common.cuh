@@ -76,6 +76,7 @@ extern double g_gemm_flops;
 // Optional per-launch device timing of the GEMM kernel (CUDA events on the launching stream), used by bench.py for
 // the live roofline figure.  gemm_timing_collect() synchronises and returns the accumulated milliseconds.
 void gemm_timing_enable(bool on);
+void gemm_force_config(int cfg);  // tuning aid: -1 = automatic tile selection
 double gemm_timing_collect(double* flops_out);
 
 // ---- permute (permute.cu): out = alpha * permute(in) + beta * out for rank <= 6 ----

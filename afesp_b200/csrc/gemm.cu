@@ -16,6 +16,8 @@
 //
 // Skinny problems (M*N tile count below the SM count with a long K) are split along K into a workspace and
 // reduced by a second kernel, deterministically (no atomics).
+#include <cmath>
+
 #include "common.cuh"
 
 namespace afesp {
@@ -66,10 +68,11 @@ __device__ __forceinline__ void load_tile(double* smem, const double* __restrict
   constexpr int NROWS = KMAJOR ? BMN : BK;
   constexpr int CPR = ROWLEN / VEC;               // chunks per row
   constexpr int TOTAL = CPR * NROWS;
-  static_assert(TOTAL % NT == 0, "tile copy must divide evenly over the CTA");
+  constexpr int ITERS = (TOTAL + NT - 1) / NT;
 #pragma unroll
-  for (int i = 0; i < TOTAL / NT; ++i) {
+  for (int i = 0; i < ITERS; ++i) {
     int c = tid + i * NT;
+    if (TOTAL % NT != 0 && c >= TOTAL) break;
     int r = c / CPR;
     int cc = (c % CPR) * VEC;
     int mn = KMAJOR ? (mn0 + r) : (mn0 + cc);
@@ -98,10 +101,11 @@ struct Params {
   int splitk;            // >1: write raw partials to ws[split][M*N]
   int kchunk;            // K extent per split (multiple of BK)
   double* ws;
+  int cvec;              // 1: C base 16-byte aligned and ldc even -> 16-byte epilogue accesses
 };
 
-template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool AK, bool BKM, int VEC>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) gemm_f64_dmma(const Params p) {
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, int MINB, bool AK, bool BKM, int VEC>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) gemm_f64_dmma(const Params p) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   using TA = Tile<BM, BK, AK>;
   using TB = Tile<BN, BK, BKM>;
@@ -183,6 +187,44 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) gemm_f64_dmma(c
     return;
   }
   const double alpha = p.alpha, beta = p.beta;
+  if (p.cvec) {
+    // 16-byte epilogue: lanes (gid, gid^1) swap one accumulator so that each thread owns two consecutive rows of one
+    // column: even gid keeps column 2*tig for rows (gid, gid+1), odd gid keeps column 2*tig+1 for rows (gid-1, gid).
+    const bool odd = gid & 1;
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      const int m = m0 + wm0 + 8 * i + (gid & ~1);
+      double2 oldv[NTL];
+      if (beta != 0.0) {  // issue every read of this row block before the first dependent store (memory-level parallelism)
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) {
+          const int n = n0 + wn0 + 8 * j + 2 * tig + (odd ? 1 : 0);
+          oldv[j] = make_double2(0.0, 0.0);
+          if (n < p.N && m < p.M) {
+            const double* c = C + m + (long long)n * p.ldc;
+            if (m + 1 < p.M) oldv[j] = *reinterpret_cast<const double2*>(c);
+            else oldv[j].x = *c;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NTL; ++j) {
+        const double send = odd ? acc[i][j][0] : acc[i][j][1];
+        const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
+        const double lo = odd ? recv : acc[i][j][0];
+        const double hi = odd ? acc[i][j][1] : recv;
+        const int n = n0 + wn0 + 8 * j + 2 * tig + (odd ? 1 : 0);
+        if (n < p.N && m < p.M) {
+          double* c = C + m + (long long)n * p.ldc;
+          double2 v = make_double2(alpha * lo, alpha * hi);
+          if (beta != 0.0) { v.x += beta * oldv[j].x; v.y += beta * oldv[j].y; }
+          if (m + 1 < p.M) *reinterpret_cast<double2*>(c) = v;
+          else *c = v.x;
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < MT; ++i) {
     int m = m0 + wm0 + 8 * i + gid;
@@ -268,11 +310,11 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool AK, bool BKM, int VEC>
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, int MINB, bool AK, bool BKM, int VEC>
 void launch_cfg(cudaStream_t st, const Params& p, int nbatch) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   constexpr size_t SMEM = (size_t)STAGES * (Tile<BM, BK, AK>::SIZE + Tile<BN, BK, BKM>::SIZE) * sizeof(double);
-  auto kern = gemm_f64_dmma<BM, BN, BK, WM, WN, STAGES, AK, BKM, VEC>;
+  auto kern = gemm_f64_dmma<BM, BN, BK, WM, WN, STAGES, MINB, AK, BKM, VEC>;
   static bool attr_set = false;
   if (!attr_set) {
     AFESP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
@@ -285,10 +327,10 @@ void launch_cfg(cudaStream_t st, const Params& p, int nbatch) {
   AFESP_CUDA_CHECK(cudaGetLastError());
 }
 
-template <int BM, int BN, int WM, int WN, int STAGES>
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB>
 void launch_tile(cudaStream_t st, const Params& p, int nbatch, bool ak, bool bk, bool vec2) {
   constexpr int BK = 16;
-#define AFESP_GEMM_CASE(AKv, BKv, V) launch_cfg<BM, BN, BK, WM, WN, STAGES, AKv, BKv, V>(st, p, nbatch)
+#define AFESP_GEMM_CASE(AKv, BKv, V) launch_cfg<BM, BN, BK, WM, WN, STAGES, MINB, AKv, BKv, V>(st, p, nbatch)
   if (vec2) {
     if (ak) { if (bk) AFESP_GEMM_CASE(true, true, 2); else AFESP_GEMM_CASE(true, false, 2); }
     else    { if (bk) AFESP_GEMM_CASE(false, true, 2); else AFESP_GEMM_CASE(false, false, 2); }
@@ -297,6 +339,53 @@ void launch_tile(cudaStream_t st, const Params& p, int nbatch, bool ak, bool bk,
     else    { if (bk) AFESP_GEMM_CASE(false, true, 1); else AFESP_GEMM_CASE(false, false, 1); }
   }
 #undef AFESP_GEMM_CASE
+}
+
+// Tile menu.  `eff` is the measured fraction of the DMMA issue peak the config reaches on a large square problem
+// (B200, profiles/); `occ` its resident CTAs per SM.  The dispatcher maximises eff * (useful / padded work) *
+// (wave fill) over the menu.
+struct TileCfg { int bm, bn, occ; double eff; };
+constexpr int NCFG = 7;
+const TileCfg kCfg[NCFG] = {
+    {128, 128, 1, 0.83},  // 0: 8 warps of 64x32
+    {64, 128, 2, 0.85},   // 1: 8 warps of 32x32
+    {128, 64, 2, 0.86},   // 2: 8 warps of 32x32
+    {64, 64, 3, 0.87},    // 3: 4 warps of 32x32  (three resident CTAs hide the cp.async prologue and the epilogue)
+    {32, 128, 3, 0.84},   // 4: 4 warps of 32x32 (skinny M)
+    {128, 32, 3, 0.82},   // 5: 4 warps of 32x32 (skinny N)
+    {96, 128, 1, 0.74},   // 6: 8 warps of 48x32
+};
+int g_force_cfg = -1;
+
+void launch_by_cfg(int cfg, cudaStream_t st, const Params& p, int nbatch, bool ak, bool bk, bool vec2) {
+  switch (cfg) {
+    case 0: launch_tile<128, 128, 64, 32, 3, 1>(st, p, nbatch, ak, bk, vec2); break;
+    case 1: launch_tile<64, 128, 32, 32, 3, 2>(st, p, nbatch, ak, bk, vec2); break;
+    case 2: launch_tile<128, 64, 32, 32, 3, 2>(st, p, nbatch, ak, bk, vec2); break;
+    case 3: launch_tile<64, 64, 32, 32, 3, 3>(st, p, nbatch, ak, bk, vec2); break;
+    case 4: launch_tile<32, 128, 32, 32, 3, 3>(st, p, nbatch, ak, bk, vec2); break;
+    case 5: launch_tile<128, 32, 32, 32, 3, 3>(st, p, nbatch, ak, bk, vec2); break;
+    case 6: launch_tile<96, 128, 48, 32, 3, 1>(st, p, nbatch, ak, bk, vec2); break;
+    default: throw Error(1, "gemm: bad tile config");
+  }
+}
+
+int choose_cfg(int M, int N, int nbatch, long long* tiles_out) {
+  int best = 0;
+  double best_score = -1.0;
+  const double sms = num_sms();
+  for (int c = 0; c < NCFG; ++c) {
+    const TileCfg& t = kCfg[c];
+    const long long tm = (M + t.bm - 1) / t.bm, tn = (N + t.bn - 1) / t.bn;
+    const long long tiles = tm * tn * nbatch;
+    const double useful = ((double)M * N) / ((double)tm * t.bm * tn * t.bn);
+    const double slots = sms * t.occ;
+    const double waves = std::ceil(tiles / slots);
+    const double fill = tiles / (waves * slots);
+    const double score = t.eff * useful * fill;
+    if (score > best_score) { best_score = score; best = c; if (tiles_out) *tiles_out = tiles; }
+  }
+  return best;
 }
 
 }  // namespace
@@ -334,19 +423,16 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
 
   g_gemm_flops += 2.0 * M * N * (double)K * nbatch;
 
-  // tile selection: big square tile when both extents are large, skinny variants otherwise
-  enum { L, S, TM, TN } cfg;
-  if (M <= 32 && N > 64) cfg = TM;
-  else if (N <= 32 && M > 64) cfg = TN;
-  else if (M >= 96 && N >= 96) cfg = L;
-  else cfg = S;
-  const int bm = (cfg == L) ? 128 : (cfg == S ? 64 : (cfg == TM ? 32 : 128));
-  const int bn = (cfg == L) ? 128 : (cfg == S ? 64 : (cfg == TM ? 128 : 32));
-  long long tiles = (long long)((M + bm - 1) / bm) * ((N + bn - 1) / bn) * nbatch;
-  if (cfg == L && tiles < num_sms() && (long long)((M + 63) / 64) * ((N + 63) / 64) * nbatch >= tiles * 2) {
-    // not enough 128x128 tiles to fill the chip: fall back to 64x64 tiles (more CTAs, 3 resident per SM)
-    cfg = S;
-    tiles = (long long)((M + 63) / 64) * ((N + 63) / 64) * nbatch;
+  // tile selection (see kCfg)
+  long long tiles = 0;
+  int cfg = choose_cfg(M, N, nbatch, &tiles);
+  if (g_force_cfg >= 0 && g_force_cfg < NCFG) {
+    cfg = g_force_cfg;
+    tiles = (long long)((M + kCfg[cfg].bm - 1) / kCfg[cfg].bm) * ((N + kCfg[cfg].bn - 1) / kCfg[cfg].bn) * nbatch;
+  }
+  {
+    const bool c_al = batch && batch->Cptr ? batch->ptr_aligned16 : (aligned16(C) && (!batch || batch->strideC % 2 == 0));
+    p.cvec = (ldc % 2 == 0) && c_al ? 1 : 0;
   }
   // split-K for skinny outputs with a long reduction
   if (nbatch == 1 && tiles * 2 <= num_sms() && K >= 512) {
@@ -364,12 +450,7 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
   }
   std::pair<cudaEvent_t, cudaEvent_t>* evs = g_timing ? next_events() : nullptr;
   if (evs) { cudaEventRecord(evs->first, st); g_timed_flops += 2.0 * M * N * (double)K * nbatch; }
-  switch (cfg) {
-    case L: launch_tile<128, 128, 64, 32, 3>(st, p, nbatch, ak, bk, vec2); break;
-    case S: launch_tile<64, 64, 32, 32, 3>(st, p, nbatch, ak, bk, vec2); break;
-    case TM: launch_tile<32, 128, 32, 32, 3>(st, p, nbatch, ak, bk, vec2); break;
-    case TN: launch_tile<128, 32, 32, 32, 3>(st, p, nbatch, ak, bk, vec2); break;
-  }
+  launch_by_cfg(cfg, st, p, nbatch, ak, bk, vec2);
   if (p.splitk > 1) {
     long long MN = (long long)M * N;
     splitk_reduce<<<(int)std::min<long long>((MN + 255) / 256, 2048), 256, 0, st>>>(p.ws, p.splitk, M, N, alpha,
@@ -379,6 +460,8 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
   }
   if (evs) cudaEventRecord(evs->second, st);
 }
+
+void gemm_force_config(int cfg) { g_force_cfg = cfg; }
 
 void gemm_timing_enable(bool on) {
   if (on && !g_timing) { g_timed_ms = 0.0; g_timed_flops = 0.0; g_ev_used = 0; }

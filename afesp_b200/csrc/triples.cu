@@ -16,6 +16,8 @@
 // i <= j <= k is computed, weighted by mult = 6, 3 or 1.  Work is dealt round-robin over (rank, nranks): the unit of
 // multi-GPU sharding; the caller sums the six partial results across ranks.
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 
 #include "ccsd.cuh"
 
@@ -33,144 +35,202 @@ struct TripleDesc { int i, j, k; double weight; };
 
 __device__ __forceinline__ int box_off(int x, int y, int z) { return (z * TP + y) * TP + x; }
 
-// W[tb](a,b,c) = sum_t X[tb][t](L[p0], L[p1], L[p2]),  L = (a,b,c), p = c_perm[t]
-__global__ void __launch_bounds__(TS* TS* TS) k_combine(const double* __restrict__ X, double* __restrict__ W, int v,
-                                                         int ntile) {
-  __shared__ double s[6 * BOX];
-  const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
-  int tile = blockIdx.x;
-  const int O[3] = {(tile % ntile) * TS, ((tile / ntile) % ntile) * TS, (tile / (ntile * ntile)) * TS};
-  const long long v3 = (long long)v * v * v;
-  const double* Xb = X + (long long)blockIdx.y * 6 * v3;
-#pragma unroll
-  for (int t = 0; t < 6; ++t) {
-    int x = O[c_perm[t][0]] + tx, y = O[c_perm[t][1]] + ty, z = O[c_perm[t][2]] + tz;
-    double val = 0.0;
-    if (x < v && y < v && z < v) val = Xb[t * v3 + x + (long long)v * (y + (long long)v * z)];
-    s[t * BOX + box_off(tx, ty, tz)] = val;
-  }
-  __syncthreads();
-  const int l[3] = {tx, ty, tz};
-  double w = 0.0;
-#pragma unroll
-  for (int t = 0; t < 6; ++t) w += s[t * BOX + box_off(l[c_perm[t][0]], l[c_perm[t][1]], l[c_perm[t][2]])];
-  int a = O[0] + tx, b = O[1] + ty, c = O[2] + tz;
-  if (a < v && b < v && c < v) W[(long long)blockIdx.y * v3 + a + (long long)v * (b + (long long)v * c)] = w;
+// Compile-time permutation algebra (everything below constant-folds once the q/t/s loops are unrolled).
+// perm t -> (p0,p1,p2) in the order of c_perm: abc, bac, cba, acb, bca, cab
+__host__ __device__ constexpr int PM(int t, int m) {
+  return t == 0 ? (m == 0 ? 0 : (m == 1 ? 1 : 2))
+       : t == 1 ? (m == 0 ? 1 : (m == 1 ? 0 : 2))
+       : t == 2 ? (m == 0 ? 2 : (m == 1 ? 1 : 0))
+       : t == 3 ? (m == 0 ? 0 : (m == 1 ? 2 : 1))
+       : t == 4 ? (m == 0 ? 1 : (m == 1 ? 2 : 0))
+                : (m == 0 ? 2 : (m == 1 ? 0 : 1));
 }
+__host__ __device__ constexpr int perm_index(int r0, int r1, int r2) {
+  return (r0 == 0 && r1 == 1) ? 0 : (r0 == 1 && r1 == 0) ? 1 : (r0 == 2 && r1 == 1) ? 2
+       : (r0 == 0 && r1 == 2) ? 3 : (r0 == 1 && r1 == 2) ? 4 : 5;
+}
+// index of q o s, (q o s)[m] = q[s[m]]
+__host__ __device__ constexpr int COMP(int q, int s) {
+  return perm_index(PM(q, PM(s, 0)), PM(q, PM(s, 1)), PM(q, PM(s, 2)));
+}
+__host__ __device__ constexpr double COEF(int s) { return s == 0 ? 8.0 / 6.0 : (s <= 3 ? -4.0 / 6.0 : 2.0 / 6.0); }
 
-struct EnergyArgs {
-  const double* W;   // [nb][v^3]
-  const double* M;   // [nb][v^3] or null
-  const double* t1;  // (o,v)
-  const double* t2;  // (o,o,v,v)
-  const double* vo;  // v_oovv (o,o,v,v)
+struct FusedArgs {
+  const double* X;    // [nb][6][v^3]  per-permutation GEMM blocks X_t for the W term
+  const double* XM;   // [nb][6][v^3]  same for the M3 term (CR) or null
+  const double* t1;   // (o,v)
+  const double* t2;   // (o,o,v,v)
+  const double* vo;   // v_oovv (o,o,v,v)
   const double* eo;
   const double* ev;
   const TripleDesc* tr;
-  int o, v, ntile;
-  int use_z, do_y, do_m, paren;
-  double* partials;  // [gridDim.y * gridDim.x][6]
+  const int* tiles;   // [ntt][3] unordered label-tile triples A <= B <= C
+  int o, v;
+  double* partials;   // [gridDim.y * gridDim.x][6]
 };
 
-__global__ void __launch_bounds__(TS* TS* TS) k_energy_spatial(const EnergyArgs g) {
+template <int T>
+__device__ __forceinline__ int sel3(const int (&l)[3]) { return l[T]; }
+
+// One CTA = one unordered triple of label tiles {A,B,C} of one occupied triple (i,j,k).
+//   step 1: W_q(l) = sum_t X_t[(O o q) o p_t + l o p_t] for the six permuted tile origins q (the reference's 6-term sum,
+//           src/ccsd.f90:2168-2173), staged through shared memory so every global read is a coalesced 64-byte row;
+//   step 2: for each of the six tiles, D3, t~ = x~(W)/D3, z~, y, M3 and the six partial sums (:2175-2233).
+// W and M3 never touch global memory; each X element is read exactly once.  All permutation bookkeeping is resolved at
+// compile time (fully unrolled q/t/s loops) -- the kernel is otherwise instruction-bound.
+template <bool USE_Z, bool DO_Y, bool DO_M>
+constexpr size_t fused_smem_doubles() {
+  return (size_t)12 * BOX + ((USE_Z || DO_Y) ? (54 * TS * TS + 9 * TS) : 0) + (DO_M ? 6 * BOX : 0);
+}
+
+template <bool USE_Z, bool DO_Y, bool DO_M, bool PAREN>
+__global__ void __launch_bounds__(TS* TS* TS, 2) k_triples_fused(const FusedArgs g) {
   extern __shared__ double sm[];
-  double* sW = sm;                      // 6 boxes of W at permuted origins
-  double* sV = sW + 6 * BOX;            // [3 pairs][3][3][TS*TS]  v_oovv(pair; R1, R2)
-  double* sT = sV + 27 * TS * TS;       // [3 occ][3 ranges][TS]    t1(occ; R)
-  double* sY = sT + 9 * TS;             // [3][TS*TS]               t2(jk;B,C), t2(ik;A,C), t2(ij;A,B)
+  constexpr bool AUX = USE_Z || DO_Y;
+  double* sW = sm;                                  // [6][BOX]  W at origin O o q
+  double* sS = sW + 6 * BOX;                        // [6][BOX]  staging for the X_t boxes of one q
+  double* sV = sS + 6 * BOX;                        // [3 pairs][3][3][TS*TS]  v_oovv(pair; R1, R2)
+  double* sT = sV + (AUX ? 27 * TS * TS : 0);       // [3 occ][3 ranges][TS]    t1(occ; R)
+  double* sY = sT + (AUX ? 9 * TS : 0);             // [3 pairs][3][3][TS*TS]  t2(pair; R1, R2)
+  double* sM = sY + (AUX ? 27 * TS * TS : 0);       // [6][BOX]  M3 at origin O o q (CR only)
   __shared__ double red[6][TS * TS * TS / 32];
   const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
   const int tid = tx + TS * (ty + TS * tz);
-  const int o = g.o, v = g.v, ntile = g.ntile;
+  const int o = g.o, v = g.v;
   const TripleDesc td = g.tr[blockIdx.y];
   const int occ[3] = {td.i, td.j, td.k};
-  int tile = blockIdx.x;
-  const int O[3] = {(tile % ntile) * TS, ((tile / ntile) % ntile) * TS, (tile / (ntile * ntile)) * TS};
+  const int T3[3] = {g.tiles[3 * blockIdx.x], g.tiles[3 * blockIdx.x + 1], g.tiles[3 * blockIdx.x + 2]};
+  const int O[3] = {T3[0] * TS, T3[1] * TS, T3[2] * TS};
   const long long v3 = (long long)v * v * v, oo = (long long)o * o;
-  const double* Wb = g.W + (long long)blockIdx.y * v3;
+  const int l[3] = {tx, ty, tz};
+  const bool full = (O[0] + TS <= v) && (O[1] + TS <= v) && (O[2] + TS <= v);  // no edge tile involved
+  const long long thr_off = tx + (long long)v * (ty + (long long)v * tz);
+  // global offset of each tile origin O o u (u = 0..5) and the thread's permuted position inside a staged box
+  long long gorg[6];
+  int soff[6];
 #pragma unroll
-  for (int t = 0; t < 6; ++t) {
-    int x = O[c_perm[t][0]] + tx, y = O[c_perm[t][1]] + ty, z = O[c_perm[t][2]] + tz;
-    double val = 0.0;
-    if (x < v && y < v && z < v) val = Wb[x + (long long)v * (y + (long long)v * z)];
-    sW[t * BOX + box_off(tx, ty, tz)] = val;
+  for (int u = 0; u < 6; ++u) {
+    gorg[u] = O[PM(u, 0)] + (long long)v * (O[PM(u, 1)] + (long long)v * O[PM(u, 2)]) + thr_off;
+    soff[u] = box_off(l[PM(u, 0)], l[PM(u, 1)], l[PM(u, 2)]);
   }
-  if (g.use_z) {
-    // v_oovv(p,q; x in R1, y in R2) for the occupied pairs (j,k), (i,k), (i,j) and all ordered range pairs
+  const int my = box_off(tx, ty, tz);
+
+  if (USE_Z || DO_Y) {
     for (int e = tid; e < 27 * TS * TS; e += TS * TS * TS) {
       int xy = e % (TS * TS), rr = (e / (TS * TS)) % 9, pr = e / (9 * TS * TS);
-      int r1 = rr / 3, r2 = rr % 3;
-      int x = O[r1] + xy % TS, y = O[r2] + xy / TS;
-      int p = pr == 0 ? occ[1] : occ[0], q = pr == 2 ? occ[1] : occ[2];
-      sV[e] = (x < v && y < v) ? g.vo[p + (long long)o * q + oo * (x + (long long)v * y)] : 0.0;
+      int x = O[rr / 3] + xy % TS, y = O[rr % 3] + xy / TS;
+      int p = pr == 0 ? occ[1] : occ[0], q = pr == 2 ? occ[1] : occ[2];  // pairs (j,k), (i,k), (i,j)
+      bool ok = x < v && y < v;
+      long long off = p + (long long)o * q + oo * (x + (long long)v * y);
+      if (USE_Z) sV[e] = ok ? g.vo[off] : 0.0;
+      if (DO_Y) sY[e] = ok ? g.t2[off] : 0.0;
     }
-  }
-  if (g.use_z || g.do_y) {
     for (int e = tid; e < 9 * TS; e += TS * TS * TS) {
       int x = O[(e / TS) % 3] + e % TS;
       sT[e] = x < v ? g.t1[occ[e / (3 * TS)] + (long long)o * x] : 0.0;
     }
   }
-  if (g.do_y) {
-    for (int e = tid; e < 3 * TS * TS; e += TS * TS * TS) {
-      int xy = e % (TS * TS), pr = e / (TS * TS);
-      int r1 = pr == 0 ? 1 : 0, r2 = pr == 2 ? 1 : 2;
-      int x = O[r1] + xy % TS, y = O[r2] + xy / TS;
-      int p = pr == 0 ? occ[1] : occ[0], q = pr == 2 ? occ[1] : occ[2];
-      sY[e] = (x < v && y < v) ? g.t2[p + (long long)o * q + oo * (x + (long long)v * y)] : 0.0;
-    }
-  }
-  __syncthreads();
-
-  double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  const int l[3] = {tx, ty, tz};
-  const int a = O[0] + tx, b = O[1] + ty, c = O[2] + tz;
-  if (a < v && b < v && c < v) {
-    const double D3 = g.eo[td.i] + g.eo[td.j] + g.eo[td.k] - g.ev[a] - g.ev[b] - g.ev[c];
-    double tt = 0.0, zt = 0.0;
+  // step 1: the six W (and M3) tiles.  Software-pipelined: the six global loads of tile q+1 are in flight while tile q
+  // goes through shared memory.
+  constexpr int NQ = DO_M ? 12 : 6;
+  double val[6];
+  auto fetch = [&](int qq, double (&out)[6]) {
+    const double* Xb = (qq < 6 ? g.X : g.XM) + (long long)blockIdx.y * 6 * v3;
+    const int q = qq % 6;
 #pragma unroll
     for (int t = 0; t < 6; ++t) {
-      const int q0 = c_perm[t][0], q1 = c_perm[t][1], q2 = c_perm[t][2];
-      tt += c_coef[t] * sW[t * BOX + box_off(l[q0], l[q1], l[q2])];
-      if (g.use_z) {
-        // z3 at labels (a',b',c') = (L[q0], L[q1], L[q2])                                  (src/ccsd.f90:2178-2179)
-        double z = sT[(0 * 3 + q0) * TS + l[q0]] * sV[((0 * 3 + q1) * 3 + q2) * TS * TS + l[q1] + TS * l[q2]] +
-                   sT[(1 * 3 + q1) * TS + l[q1]] * sV[((1 * 3 + q0) * 3 + q2) * TS * TS + l[q0] + TS * l[q2]] +
-                   sT[(2 * 3 + q2) * TS + l[q2]] * sV[((2 * 3 + q0) * 3 + q1) * TS * TS + l[q0] + TS * l[q1]];
-        zt += c_coef[t] * z;
+      const int u = COMP(q, t);  // origin of the X_t box: O o (q o p_t)
+      bool ok = full || ((O[PM(u, 0)] + tx < v) && (O[PM(u, 1)] + ty < v) && (O[PM(u, 2)] + tz < v));
+      out[t] = ok ? __ldg(Xb + t * v3 + gorg[u]) : 0.0;
+    }
+  };
+  fetch(0, val);
+#pragma unroll
+  for (int qq = 0; qq < NQ; ++qq) {
+#pragma unroll
+    for (int t = 0; t < 6; ++t) sS[t * BOX + my] = val[t];
+    __syncthreads();
+    if (qq + 1 < NQ) fetch(qq + 1, val);
+    double w = 0.0;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) w += sS[t * BOX + soff[t]];
+    (qq < 6 ? sW : sM)[(qq % 6) * BOX + my] = w;
+    __syncthreads();
+  }
+  // step 2: energies of the six tiles
+  double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  const double eijk = g.eo[td.i] + g.eo[td.j] + g.eo[td.k];
+  double evl[3][3];  // ev of the thread's label in range r at local index l[m]: evl[r][m]
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int m = 0; m < 3; ++m) evl[r][m] = (O[r] + l[m] < v) ? g.ev[O[r] + l[m]] : 0.0;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    constexpr int dummy = 0; (void)dummy;
+    const int q0 = PM(q, 0), q1 = PM(q, 1), q2 = PM(q, 2);
+    const bool inside = full || ((O[q0] + tx < v) && (O[q1] + ty < v) && (O[q2] + tz < v));
+    if (inside) {
+      const double D3 = eijk - evl[q0][0] - evl[q1][1] - evl[q2][2];
+      double tt = 0.0, zt = 0.0;
+#pragma unroll
+      for (int s = 0; s < 6; ++s) {
+        const int s0 = PM(s, 0), s1 = PM(s, 1), s2 = PM(s, 2);
+        const int u = COMP(q, s);
+        tt += COEF(s) * sW[u * BOX + soff[s]];
+        if (USE_Z) {
+          // z3 at labels (a',b',c') = L o s: component m lies in range u[m] with local index l[s[m]]   (:2178-2179)
+          const int u0 = PM(u, 0), u1 = PM(u, 1), u2 = PM(u, 2);
+          double z = sT[(0 * 3 + u0) * TS + l[s0]] * sV[((0 * 3 + u1) * 3 + u2) * TS * TS + l[s1] + TS * l[s2]] +
+                     sT[(1 * 3 + u1) * TS + l[s1]] * sV[((1 * 3 + u0) * 3 + u2) * TS * TS + l[s0] + TS * l[s2]] +
+                     sT[(2 * 3 + u2) * TS + l[s2]] * sV[((2 * 3 + u0) * 3 + u1) * TS * TS + l[s0] + TS * l[s1]];
+          zt += COEF(s) * z;
+        }
+      }
+      const double rD = 1.0 / D3;
+      tt *= rD;
+      zt *= rD;
+      const double w = sW[q * BOX + my];
+      acc[0] += tt * w;
+      if (PAREN) acc[1] += (tt + zt) * w;
+      if (DO_Y) {
+        const double ta = sT[(0 * 3 + q0) * TS + tx], tb = sT[(1 * 3 + q1) * TS + ty], tc = sT[(2 * 3 + q2) * TS + tz];
+        const double y = ta * tb * tc + ta * sY[((0 * 3 + q1) * 3 + q2) * TS * TS + ty + TS * tz] +
+                         tb * sY[((1 * 3 + q0) * 3 + q2) * TS * TS + tx + TS * tz] +
+                         tc * sY[((2 * 3 + q0) * 3 + q1) * TS * TS + tx + TS * ty];             // (:2183-2184)
+        acc[2] += tt * y;
+        if (PAREN) acc[3] += (tt + zt) * y;
+      }
+      if (DO_M) {
+        const double m = sM[q * BOX + my];
+        acc[4] += tt * m;
+        if (PAREN) acc[5] += (tt + zt) * m;
       }
     }
-    tt /= D3;
-    zt /= D3;
-    const double w = sW[box_off(tx, ty, tz)];
-    acc[0] = tt * w;
-    if (g.paren) acc[1] = (tt + zt) * w;
-    if (g.do_y) {
-      const double ta = sT[(0 * 3 + 0) * TS + tx], tb = sT[(1 * 3 + 1) * TS + ty], tc = sT[(2 * 3 + 2) * TS + tz];
-      const double y = ta * tb * tc + ta * sY[0 * TS * TS + ty + TS * tz] + tb * sY[1 * TS * TS + tx + TS * tz] +
-                       tc * sY[2 * TS * TS + tx + TS * ty];                                 // (:2183-2184)
-      acc[2] = tt * y;
-      if (g.paren) acc[3] = (tt + zt) * y;
-    }
-    if (g.do_m) {
-      const double m = g.M[(long long)blockIdx.y * v3 + a + (long long)v * (b + (long long)v * c)];
-      acc[4] = tt * m;
-      if (g.paren) acc[5] = (tt + zt) * m;
-    }
   }
+  // ordered tiles that coincide (A == B etc.) are visited more than once: weight each visit accordingly
+  const double dup = (T3[0] == T3[1] && T3[1] == T3[2]) ? 1.0 / 6.0 : ((T3[0] == T3[1] || T3[1] == T3[2]) ? 0.5 : 1.0);
   const int lane = tid & 31, warp = tid >> 5;
+  const double wgt = td.weight * dup;
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
-    double x = acc[k] * td.weight;
+    const bool live = (k == 0) || (k == 1 && PAREN) || (k == 2 && DO_Y) || (k == 3 && DO_Y && PAREN) ||
+                      (k == 4 && DO_M) || (k == 5 && DO_M && PAREN);
+    if (!live) continue;
+    double x = acc[k] * wgt;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
     if (lane == 0) red[k][warp] = x;
   }
   __syncthreads();
   if (tid < 6) {
+    const int k = tid;
+    const bool live = (k == 0) || (k == 1 && PAREN) || (k == 2 && DO_Y) || (k == 3 && DO_Y && PAREN) ||
+                      (k == 4 && DO_M) || (k == 5 && DO_M && PAREN);
     double sacc = 0.0;
-    for (int w2 = 0; w2 < TS * TS * TS / 32; ++w2) sacc += red[tid][w2];
-    g.partials[((long long)blockIdx.y * gridDim.x + blockIdx.x) * 6 + tid] = sacc;
+    if (live)
+      for (int w2 = 0; w2 < TS * TS * TS / 32; ++w2) sacc += red[k][w2];
+    g.partials[((long long)blockIdx.y * gridDim.x + blockIdx.x) * 6 + k] = sacc;
   }
 }
 
@@ -286,6 +346,27 @@ std::vector<TripleDesc> my_triples(int o, bool symmetric, bool strict, int rank,
 
 static_assert(sizeof(double) == sizeof(void*), "pointer arrays are carried in double buffers");
 
+// Developer trace (AFESP_TRACE=1): host wall-clock of the phases of one (T) call, stream-synchronised. Off by default
+// (the library prints nothing in normal operation).
+struct Trace {
+  bool on;
+  cudaStream_t st;
+  std::chrono::steady_clock::time_point t0;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  explicit Trace(cudaStream_t s) : on(std::getenv("AFESP_TRACE") != nullptr), st(s) { t0 = std::chrono::steady_clock::now(); }
+  void lap(int k) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    auto t1 = std::chrono::steady_clock::now();
+    acc[k] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    t0 = t1;
+  }
+  void report(const char* names[], int n) {
+    if (!on) return;
+    for (int k = 0; k < n; ++k) std::fprintf(stderr, "[afesp trace] %-14s %10.3f ms\n", names[k], acc[k]);
+  }
+};
+
 }  // namespace
 
 void triples_partition_counts(int o, bool symmetric, bool strict, int nranks, long long* counts) {
@@ -322,47 +403,59 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
   if (do_m) AFESP_REQUIRE(s.has("I_vovv_pp") && s.has("I_ooov_pp"), "CR triples need the CR intermediates");
   for (int k = 0; k < 6; ++k) sums[k] = 0.0;
 
+  Trace tr(st);
   // GEMM-ready operand layouts (the reference's reshapes at :2056-2066, re-aimed at contiguous GEMM blocks)
-  Tensor T2v({v, v, o, o}), T2o({o, v, v, o}), Vv({v, v, v, o}), Vo({o, v, o, o});
-  transpose(e, "ijad->adij", 1.0, s.t2.view(), 0.0, T2v.view());            // T2v(a,d;p,q) = t2(p,q,a,d)
-  transpose(e, "lpba->labp", 1.0, s.t2.view(), 0.0, T2o.view());            // T2o(l,a,b;p) = t2(l,p,b,a)
-  transpose(e, "cbkd->dbck", 1.0, s.get("v_vvov").view(), 0.0, Vv.view());  // Vv(d,b,c;k) = v_vvov(c,b,k,d)
-  transpose(e, "kjcl->lcjk", 1.0, s.get("v_oovo").view(), 0.0, Vo.view());  // Vo(l,c;j,k) = v_oovo(k,j,c,l)
-  Tensor Mv, Mo;
+  // (work arrays come from the engine's pool: cudaFree of GB-sized blocks costs up to 100s of ms)
+  const size_t n_t2 = (size_t)s.t2.size(), n_ov3 = (size_t)o * v3, n_o3v = (size_t)o * o * o * v;
+  Scratch sT2v(e.pool, n_t2), sT2o(e.pool, n_t2), sVv(e.pool, n_ov3), sVo(e.pool, n_o3v);
+  TView T2v(sT2v.p, {v, v, o, o}), T2o(sT2o.p, {o, v, v, o}), Vv(sVv.p, {v, v, v, o}), Vo(sVo.p, {o, v, o, o});
+  transpose(e, "ijad->adij", 1.0, s.t2.view(), 0.0, T2v);            // T2v(a,d;p,q) = t2(p,q,a,d)
+  transpose(e, "lpba->labp", 1.0, s.t2.view(), 0.0, T2o);            // T2o(l,a,b;p) = t2(l,p,b,a)
+  transpose(e, "cbkd->dbck", 1.0, s.get("v_vvov").view(), 0.0, Vv);  // Vv(d,b,c;k) = v_vvov(c,b,k,d)
+  transpose(e, "kjcl->lcjk", 1.0, s.get("v_oovo").view(), 0.0, Vo);  // Vo(l,c;j,k) = v_oovo(k,j,c,l)
+  std::unique_ptr<Scratch> sMv, sMo;
+  TView Mv, Mo;
   if (do_m) {
-    Mv.init({v, v, v, o}); Mo.init({o, v, o, o});
-    transpose(e, "dkbc->dbck", 1.0, s.get("I_vovv_pp").view(), 0.0, Mv.view());  // I_vovv_pp(d,k,b,c)
-    transpose(e, "jklc->lcjk", 1.0, s.get("I_ooov_pp").view(), 0.0, Mo.view());  // I_ooov_pp(j,k,l,c)
+    sMv.reset(new Scratch(e.pool, n_ov3)); sMo.reset(new Scratch(e.pool, n_o3v));
+    Mv = TView(sMv->p, {v, v, v, o}); Mo = TView(sMo->p, {o, v, o, o});
+    transpose(e, "dkbc->dbck", 1.0, s.get("I_vovv_pp").view(), 0.0, Mv);  // I_vovv_pp(d,k,b,c)
+    transpose(e, "jklc->lcjk", 1.0, s.get("I_ooov_pp").view(), 0.0, Mo);  // I_ooov_pp(j,k,l,c)
   }
 
   std::vector<TripleDesc> tri = my_triples(o, s.opt.triples_ijk_symmetry, false, rank, nranks);
   if (tri.empty()) return;
-  const long long per_triple = (6 + 1 + (do_m ? 1 : 0)) * v3 * 8;
+  tr.lap(0);
+  const long long per_triple = (do_m ? 12 : 6) * v3 * 8;
   int nb = (int)std::max<long long>(1, std::min<long long>((long long)tri.size(), s.opt.triples_batch_bytes / per_triple));
   nb = std::min(nb, 65535 / 6);
-  Scratch X(e.pool, (size_t)nb * 6 * v3), W(e.pool, (size_t)nb * v3);
-  std::unique_ptr<Scratch> Mw;
-  if (do_m) Mw.reset(new Scratch(e.pool, (size_t)nb * v3));
+  Scratch X(e.pool, (size_t)nb * 6 * v3);
+  std::unique_ptr<Scratch> XM;
+  if (do_m) XM.reset(new Scratch(e.pool, (size_t)nb * 6 * v3));
+  // unordered label-tile triples A <= B <= C
   const int ntile = (v + TS - 1) / TS;
-  const long long blocks_per_triple = (long long)ntile * ntile * ntile;
-  AFESP_REQUIRE(blocks_per_triple < (1LL << 31), "triples: too many label tiles");
-  DBuf descs((size_t)nb * 3);  // TripleDesc is 24 bytes = 3 doubles
+  std::vector<int> tiles_h;
+  for (int A = 0; A < ntile; ++A)
+    for (int B = A; B < ntile; ++B)
+      for (int C = B; C < ntile; ++C) { tiles_h.push_back(A); tiles_h.push_back(B); tiles_h.push_back(C); }
+  const long long ntt = (long long)tiles_h.size() / 3;
+  Scratch tiles_d(e.pool, (tiles_h.size() + 1) / 2 + 1);
+  AFESP_CUDA_CHECK(cudaMemcpyAsync(tiles_d.p, tiles_h.data(), tiles_h.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  Scratch descs(e.pool, (size_t)nb * 3);  // TripleDesc is 24 bytes = 3 doubles
   static_assert(sizeof(TripleDesc) == 24, "TripleDesc layout");
-  DevPtrs ptrs;
-  ptrs.ensure((size_t)nb * 6 * 5);
+  Scratch ptrs_raw(e.pool, (size_t)nb * 6 * 5);
+  struct { double* p; } ptrs_shim{ptrs_raw.p};
   const size_t nbatches = (tri.size() + nb - 1) / nb;
-  DBuf batch_sums(nbatches * 6);
+  Scratch batch_sums(e.pool, nbatches * 6);
   const bool al16 = (v % 2 == 0) && (o % 2 == 0);
   const int perm6[6][3] = {{0, 1, 2}, {1, 0, 2}, {2, 1, 0}, {0, 2, 1}, {1, 2, 0}, {2, 0, 1}};
-  const size_t esmem = (size_t)(6 * BOX + 27 * TS * TS + 9 * TS + 3 * TS * TS) * sizeof(double);
-  AFESP_CUDA_CHECK(cudaFuncSetAttribute(k_energy_spatial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
 
+  tr.lap(1);
   for (size_t bi = 0; bi < nbatches; ++bi) {
     const size_t t0 = bi * nb;
     const int cb = (int)std::min<size_t>(nb, tri.size() - t0);
     AFESP_CUDA_CHECK(cudaMemcpyAsync(descs.p, &tri[t0], (size_t)cb * sizeof(TripleDesc), cudaMemcpyHostToDevice, st));
     const int ng = cb * 6;
-    auto run_gemms = [&](const Tensor& Bv, const Tensor& Bo) {
+    auto run_gemms = [&](const TView& Bv, const TView& Bo, double* out) {
       std::vector<const double*> hp((size_t)ng * 5);
       for (int tb = 0; tb < cb; ++tb) {
         const TripleDesc& td = tri[t0 + tb];
@@ -370,44 +463,67 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
         for (int t = 0; t < 6; ++t) {
           const int p = idx[perm6[t][0]], q = idx[perm6[t][1]], r = idx[perm6[t][2]];
           const int g = tb * 6 + t;
-          hp[0 * ng + g] = T2v.p() + ((long long)p + (long long)o * q) * v2;          // A1 (a x d)
-          hp[1 * ng + g] = Bv.p() + (long long)r * v3;                                // B1 (d x bc)
-          hp[2 * ng + g] = X.p + (long long)g * v3;                                   // C
-          hp[3 * ng + g] = T2o.p() + (long long)p * o * v2;                           // A2 (l x ab), used transposed
-          hp[4 * ng + g] = Bo.p() + ((long long)q + (long long)o * r) * o * v;        // B2 (l x c)
+          hp[0 * ng + g] = T2v.p + ((long long)p + (long long)o * q) * v2;            // A1 (a x d)
+          hp[1 * ng + g] = Bv.p + (long long)r * v3;                                  // B1 (d x bc)
+          hp[2 * ng + g] = out + (long long)g * v3;                                   // C
+          hp[3 * ng + g] = T2o.p + (long long)p * o * v2;                             // A2 (l x ab), used transposed
+          hp[4 * ng + g] = Bo.p + ((long long)q + (long long)o * r) * o * v;          // B2 (l x c)
         }
       }
-      AFESP_CUDA_CHECK(cudaMemcpyAsync(ptrs.raw.p, hp.data(), hp.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
+      AFESP_CUDA_CHECK(cudaMemcpyAsync(ptrs_shim.p, hp.data(), hp.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
       AFESP_CUDA_CHECK(cudaStreamSynchronize(st));  // hp is a stack-scoped staging vector
-      const double* const* dp = reinterpret_cast<const double* const*>(ptrs.raw.p);
-      GemmBatch b1;
-      b1.count = ng; b1.Aptr = dp + 0 * ng; b1.Bptr = dp + 1 * ng;
-      b1.Cptr = (double* const*)(dp + 2 * ng); b1.ptr_aligned16 = al16;
-      dgemm(st, 'N', 'N', v, (int)v2, v, 1.0, nullptr, v, nullptr, v, 0.0, nullptr, v, &b1);
+      tr.lap(2);
+      const double* const* dp = reinterpret_cast<const double* const*>(ptrs_shim.p);
+      // hole term first, write-only (bandwidth-bound, K = o); the particle GEMM then accumulates on top of it so the
+      // read-modify-write of X hides inside a compute-bound kernel.
       GemmBatch b2;
       b2.count = ng; b2.Aptr = dp + 3 * ng; b2.Bptr = dp + 4 * ng;
       b2.Cptr = (double* const*)(dp + 2 * ng); b2.ptr_aligned16 = al16;
-      dgemm(st, 'T', 'N', (int)v2, v, o, -1.0, nullptr, o, nullptr, o, 1.0, nullptr, v2, &b2);
+      dgemm(st, 'T', 'N', (int)v2, v, o, -1.0, nullptr, o, nullptr, o, 0.0, nullptr, v2, &b2);
+      tr.lap(3);
+      GemmBatch b1;
+      b1.count = ng; b1.Aptr = dp + 0 * ng; b1.Bptr = dp + 1 * ng;
+      b1.Cptr = (double* const*)(dp + 2 * ng); b1.ptr_aligned16 = al16;
+      dgemm(st, 'N', 'N', v, (int)v2, v, 1.0, nullptr, v, nullptr, v, 1.0, nullptr, v, &b1);
+      tr.lap(4);
     };
-    dim3 grid((unsigned)blocks_per_triple, (unsigned)cb), block(TS, TS, TS);
-    run_gemms(Vv, Vo);
-    k_combine<<<grid, block, 0, st>>>(X.p, W.p, v, ntile);
-    count_launch();
-    if (do_m) {
-      run_gemms(Mv, Mo);
-      k_combine<<<grid, block, 0, st>>>(X.p, Mw->p, v, ntile);
-      count_launch();
+    run_gemms(Vv, Vo, X.p);
+    if (do_m) run_gemms(Mv, Mo, XM->p);
+    FusedArgs fa{};
+    fa.X = X.p; fa.XM = do_m ? XM->p : nullptr; fa.t1 = s.t1.p(); fa.t2 = s.t2.p(); fa.vo = s.get("v_oovv").p();
+    fa.eo = s.eo.p(); fa.ev = s.ev.p(); fa.tr = reinterpret_cast<const TripleDesc*>(descs.p);
+    fa.tiles = reinterpret_cast<const int*>(tiles_d.p);
+    fa.o = o; fa.v = v;
+    const long long nblocks = ntt * cb;
+    AFESP_REQUIRE(ntt < (1LL << 31), "triples: too many label tiles");
+    fa.partials = reduce_scratch(e, (size_t)nblocks * 6);
+    dim3 grid((unsigned)ntt, (unsigned)cb), block(TS, TS, TS);
+    {
+      auto go = [&](auto kern, size_t smem_doubles) {
+        const size_t fsmem = smem_doubles * sizeof(double);
+        AFESP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        kern<<<grid, block, fsmem, st>>>(fa);
+      };
+      const int mode = (use_z ? 8 : 0) | (do_y ? 4 : 0) | (do_m ? 2 : 0) | (paren ? 1 : 0);
+      switch (mode) {
+        case 0: go(k_triples_fused<false, false, false, false>, fused_smem_doubles<false, false, false>()); break;   // CCSD[T]
+        case 1: go(k_triples_fused<false, false, false, true>, fused_smem_doubles<false, false, false>()); break;    // CCSD(T) as coded (Q2: no z3_bar)
+        case 4: go(k_triples_fused<false, true, false, false>, fused_smem_doubles<false, true, false>()); break;    // R-CCSD[T]
+        case 13: go(k_triples_fused<true, true, false, true>, fused_smem_doubles<true, true, false>()); break;     // R-CCSD(T)
+        case 6: go(k_triples_fused<false, true, true, false>, fused_smem_doubles<false, true, true>()); break;     // CR-CCSD[T]
+        case 15: go(k_triples_fused<true, true, true, true>, fused_smem_doubles<true, true, true>()); break;      // CR-CCSD(T)
+        default: throw Error(1, "triples: unsupported combination of calc_type flags");
+      }
     }
-    EnergyArgs ea{};
-    ea.W = W.p; ea.M = do_m ? Mw->p : nullptr; ea.t1 = s.t1.p(); ea.t2 = s.t2.p(); ea.vo = s.get("v_oovv").p();
-    ea.eo = s.eo.p(); ea.ev = s.ev.p(); ea.tr = reinterpret_cast<const TripleDesc*>(descs.p);
-    ea.o = o; ea.v = v; ea.ntile = ntile; ea.use_z = use_z; ea.do_y = do_y; ea.do_m = do_m; ea.paren = paren;
-    const long long nblocks = blocks_per_triple * cb;
-    ea.partials = reduce_scratch(e, (size_t)nblocks * 6);
-    k_energy_spatial<<<grid, block, esmem, st>>>(ea);
     count_launch();
     AFESP_CUDA_CHECK(cudaGetLastError());
-    finish_partials(e, ea.partials, (int)nblocks, 6, batch_sums.p + bi * 6);
+    tr.lap(5);
+    finish_partials(e, fa.partials, (int)nblocks, 6, batch_sums.p + bi * 6);
+    tr.lap(6);
+  }
+  {
+    const char* names[] = {"layouts", "setup", "ptr upload", "gemm hole", "gemm particle", "fused epilogue", "finish"};
+    tr.report(names, 7);
   }
   std::vector<double> h(nbatches * 6);
   AFESP_CUDA_CHECK(cudaMemcpyAsync(h.data(), batch_sums.p, h.size() * 8, cudaMemcpyDeviceToHost, st));

@@ -100,7 +100,8 @@ int afesp_gpu_dgemm_wrapper(afesp_handle h, char transA, char transB, int outer_
 int afesp_gpu_omp_reshape(afesp_handle h, double* out_arr, const double* in_arr, const int in_dims[4],
                           const char arr_order[4], int has_beta, double beta);
 /* Synthetic-workload helper (bench): time `reps` back-to-back device-resident dgemms, returns milliseconds/gemm. */
-int afesp_gpu_bench_dgemm(afesp_handle h, char transA, char transB, int M, int N, int K, int reps, double* ms);
+int afesp_gpu_bench_dgemm(afesp_handle h, char transA, char transB, int M, int N, int K, double beta, int reps,
+                          double* ms);
 /* Raw DMMA issue-rate probe: register-resident mma.sync loop on all SMs; returns TFLOP/s (the FP64 tensor peak the
  * roofline fractions are quoted against; MEASURED_PEAKS.json has no FP64 entry). */
 int afesp_gpu_dmma_peak(afesp_handle h, double* tflops);
