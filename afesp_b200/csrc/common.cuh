@@ -84,5 +84,7 @@ double gemm_timing_collect(double* flops_out);
 // column-major (axis 0 fastest) on both sides.
 void permute(cudaStream_t st, int rank, const int* dims, const int* perm, double alpha, const double* in,
              double beta, double* out);
+void permute_strided(cudaStream_t st, int rank, const int* dims, const int* perm, double alpha, const double* in,
+                     double beta, double* out, const long long* ostride);
 
 }  // namespace afesp

@@ -18,6 +18,7 @@ struct PermParams {
   int rank;
   int odims[MAXR];          // output extents
   long long istr[MAXR];     // input stride of the input axis feeding output axis d
+  long long ostr[MAXR];     // output stride of output axis d (ostr[0] == 1)
   long long total;
   double alpha, beta;
 };
@@ -25,18 +26,20 @@ struct PermParams {
 __global__ void permute_gather(const PermParams p, const double* __restrict__ in, double* __restrict__ out) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < p.total;
        idx += (long long)gridDim.x * blockDim.x) {
-    long long rem = idx, off = 0;
+    long long rem = idx, off = 0, oo = 0;
 #pragma unroll
     for (int d = 0; d < MAXR; ++d) {
       if (d < p.rank) {
         long long q = rem / p.odims[d];
-        off += (rem - q * p.odims[d]) * p.istr[d];
+        long long c = rem - q * p.odims[d];
+        off += c * p.istr[d];
+        oo += c * p.ostr[d];
         rem = q;
       }
     }
     double v = p.alpha * in[off];
-    if (p.beta != 0.0) v += p.beta * out[idx];
-    out[idx] = v;
+    if (p.beta != 0.0) v += p.beta * out[oo];
+    out[oo] = v;
   }
 }
 
@@ -88,6 +91,13 @@ __global__ void permute_transpose(const TransParams p, const double* __restrict_
 
 void permute(cudaStream_t st, int rank, const int* dims, const int* perm, double alpha, const double* in, double beta,
              double* out) {
+  permute_strided(st, rank, dims, perm, alpha, in, beta, out, nullptr);
+}
+
+// Same, with explicit output strides (ostride[d] = stride of output axis d, ostride[0] must be 1): writes a permuted
+// tensor into a sub-block of a larger array (used to assemble the K-concatenated (T) operands).
+void permute_strided(cudaStream_t st, int rank, const int* dims, const int* perm, double alpha, const double* in,
+                     double beta, double* out, const long long* ostride) {
   AFESP_REQUIRE(rank >= 1 && rank <= MAXR, "permute: rank must be 1..6");
   // validate + input strides
   long long istr_full[MAXR];
@@ -99,27 +109,38 @@ void permute(cudaStream_t st, int rank, const int* dims, const int* perm, double
     istr_full[d] = total;
     total *= dims[d];
   }
+  long long ostr_full[MAXR];
+  {
+    long long acc = 1;
+    for (int d = 0; d < rank; ++d) {
+      ostr_full[d] = ostride ? ostride[d] : acc;
+      acc *= dims[perm[d]];
+    }
+    AFESP_REQUIRE(ostr_full[0] == 1, "permute: output axis 0 must have unit stride");
+  }
   if (total == 0) return;
   // Canonical form in output order: drop extent-1 axes, merge output-adjacent axes that are input-adjacent.
   int r = 0;
   int odims[MAXR];
-  long long istr[MAXR];
+  long long istr[MAXR], ostr_d[MAXR];
   for (int d = 0; d < rank; ++d) {
     int a = perm[d];
     if (dims[a] == 1) continue;
-    if (r > 0 && istr[r - 1] * odims[r - 1] == istr_full[a]) {
+    if (r > 0 && istr[r - 1] * odims[r - 1] == istr_full[a] && ostr_d[r - 1] * odims[r - 1] == ostr_full[d]) {
       odims[r - 1] *= dims[a];
     } else {
       odims[r] = dims[a];
       istr[r] = istr_full[a];
+      ostr_d[r] = ostr_full[d];
       ++r;
     }
   }
-  if (r == 0) { odims[0] = 1; istr[0] = 1; r = 1; }
+  if (r == 0) { odims[0] = 1; istr[0] = 1; ostr_d[0] = 1; r = 1; }
+  AFESP_REQUIRE(ostr_d[0] == 1, "permute: leading output axis must have unit stride");
   if (istr[0] == 1) {
     PermParams p{};
     p.rank = r;
-    for (int d = 0; d < r; ++d) { p.odims[d] = odims[d]; p.istr[d] = istr[d]; }
+    for (int d = 0; d < r; ++d) { p.odims[d] = odims[d]; p.istr[d] = istr[d]; p.ostr[d] = ostr_d[d]; }
     p.total = total; p.alpha = alpha; p.beta = beta;
     int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
     permute_gather<<<blocks, 256, 0, st>>>(p, in, out);
@@ -132,8 +153,6 @@ void permute(cudaStream_t st, int rank, const int* dims, const int* perm, double
     p.n0 = odims[d0];
     p.nb = odims[0];
     p.istr_b = istr[0];
-    long long ostr = 1, ostr_d[MAXR];
-    for (int d = 0; d < r; ++d) { ostr_d[d] = ostr; ostr *= odims[d]; }
     p.ostr_0 = ostr_d[d0];
     p.nrest = 0; p.rest_total = 1;
     for (int d = 1; d < r; ++d) {

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <cstring>
 
 #include "ccsd.cuh"
 
@@ -405,21 +406,37 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
 
   Trace tr(st);
   // GEMM-ready operand layouts (the reference's reshapes at :2056-2066, re-aimed at contiguous GEMM blocks)
-  // (work arrays come from the engine's pool: cudaFree of GB-sized blocks costs up to 100s of ms)
-  const size_t n_t2 = (size_t)s.t2.size(), n_ov3 = (size_t)o * v3, n_o3v = (size_t)o * o * o * v;
-  Scratch sT2v(e.pool, n_t2), sT2o(e.pool, n_t2), sVv(e.pool, n_ov3), sVo(e.pool, n_o3v);
-  TView T2v(sT2v.p, {v, v, o, o}), T2o(sT2o.p, {o, v, v, o}), Vv(sVv.p, {v, v, v, o}), Vo(sVo.p, {o, v, o, o});
-  transpose(e, "ijad->adij", 1.0, s.t2.view(), 0.0, T2v);            // T2v(a,d;p,q) = t2(p,q,a,d)
-  transpose(e, "lpba->labp", 1.0, s.t2.view(), 0.0, T2o);            // T2o(l,a,b;p) = t2(l,p,b,a)
-  transpose(e, "cbkd->dbck", 1.0, s.get("v_vvov").view(), 0.0, Vv);  // Vv(d,b,c;k) = v_vvov(c,b,k,d)
-  transpose(e, "kjcl->lcjk", 1.0, s.get("v_oovo").view(), 0.0, Vo);  // Vo(l,c;j,k) = v_oovo(k,j,c,l)
-  std::unique_ptr<Scratch> sMv, sMo;
-  TView Mv, Mo;
+  // K-concatenated GEMM operands (work arrays come from the engine's pool: cudaFree of GB-sized blocks is slow).
+  // With the hole term written in the layout (c,b,a) it lands in the buffer of the permutation (r,q,p) as
+  //     C_pqr(x,(y,z)) = sum_d t2(p,q,x,d) v_vovv(d,r,y,z) - sum_l v_ovoo(l,x,q,p) t2(l,r,y,z)
+  // i.e. ONE GEMM of depth K = v + o = nbf per permutation:
+  //     Acat(x, [d | l]; p,q) = [ t2(p,q,x,d) | -v_oovo(p,q,x,l) ]            (v x n) for each occupied pair
+  //     Bcat([d | l], (y,z); r) = [ v_vvov(z,y,r,d) ; t2(l,r,y,z) ]           (n x v^2) for each occupied index
+  // (the reference's reshapes at :2056-2066, re-aimed at GEMM blocks).  M3 uses I_ooov_pp / I_vovv_pp instead (:2188-2193).
+  const int n = v + o;
+  const size_t n_acat = (size_t)v * n * o * o, n_bcat = (size_t)n * v2 * o;
+  Scratch sAcat(e.pool, n_acat), sBcat(e.pool, n_bcat);
+  std::unique_ptr<Scratch> sAcatM, sBcatM;
+  auto put = [&](const TView& in, const char* from, const char* to, double alpha, double* out, const long long* ostr) {
+    int rank = (int)std::strlen(from), perm[4], dims[4];
+    for (int d = 0; d < rank; ++d) {
+      perm[d] = (int)(std::strchr(from, to[d]) - from);
+      dims[d] = in.dims[d];
+    }
+    permute_strided(st, rank, dims, perm, alpha, in.p, 0.0, out, ostr);
+  };
+  const long long a_str[4] = {1, v, (long long)v * n, (long long)v * n * o};          // (x, k, p, q)
+  const long long b_str[4] = {1, n, (long long)n * v, (long long)n * v2};             // (k, y, z, r)
+  put(s.t2.view(), "pqxd", "xdpq", 1.0, sAcat.p, a_str);
+  put(s.get("v_oovo").view(), "pqxl", "xlpq", -1.0, sAcat.p + (size_t)v * v, a_str);
+  put(s.get("v_vvov").view(), "zyrd", "dyzr", 1.0, sBcat.p, b_str);
+  put(s.t2.view(), "lryz", "lyzr", 1.0, sBcat.p + v, b_str);
   if (do_m) {
-    sMv.reset(new Scratch(e.pool, n_ov3)); sMo.reset(new Scratch(e.pool, n_o3v));
-    Mv = TView(sMv->p, {v, v, v, o}); Mo = TView(sMo->p, {o, v, o, o});
-    transpose(e, "dkbc->dbck", 1.0, s.get("I_vovv_pp").view(), 0.0, Mv);  // I_vovv_pp(d,k,b,c)
-    transpose(e, "jklc->lcjk", 1.0, s.get("I_ooov_pp").view(), 0.0, Mo);  // I_ooov_pp(j,k,l,c)
+    sAcatM.reset(new Scratch(e.pool, n_acat)); sBcatM.reset(new Scratch(e.pool, n_bcat));
+    put(s.t2.view(), "pqxd", "xdpq", 1.0, sAcatM->p, a_str);
+    put(s.get("I_ooov_pp").view(), "qplx", "xlpq", -1.0, sAcatM->p + (size_t)v * v, a_str);
+    put(s.get("I_vovv_pp").view(), "dryz", "dyzr", 1.0, sBcatM->p, b_str);
+    put(s.t2.view(), "lryz", "lyzr", 1.0, sBcatM->p + v, b_str);
   }
 
   std::vector<TripleDesc> tri = my_triples(o, s.opt.triples_ijk_symmetry, false, rank, nranks);
@@ -455,40 +472,31 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
     const int cb = (int)std::min<size_t>(nb, tri.size() - t0);
     AFESP_CUDA_CHECK(cudaMemcpyAsync(descs.p, &tri[t0], (size_t)cb * sizeof(TripleDesc), cudaMemcpyHostToDevice, st));
     const int ng = cb * 6;
-    auto run_gemms = [&](const TView& Bv, const TView& Bo, double* out) {
-      std::vector<const double*> hp((size_t)ng * 5);
+    auto run_gemms = [&](const double* Acat, const double* Bcat, double* out) {
+      std::vector<const double*> hp((size_t)ng * 3);
       for (int tb = 0; tb < cb; ++tb) {
         const TripleDesc& td = tri[t0 + tb];
         const int idx[3] = {td.i, td.j, td.k};
         for (int t = 0; t < 6; ++t) {
           const int p = idx[perm6[t][0]], q = idx[perm6[t][1]], r = idx[perm6[t][2]];
           const int g = tb * 6 + t;
-          hp[0 * ng + g] = T2v.p + ((long long)p + (long long)o * q) * v2;            // A1 (a x d)
-          hp[1 * ng + g] = Bv.p + (long long)r * v3;                                  // B1 (d x bc)
-          hp[2 * ng + g] = out + (long long)g * v3;                                   // C
-          hp[3 * ng + g] = T2o.p + (long long)p * o * v2;                             // A2 (l x ab), used transposed
-          hp[4 * ng + g] = Bo.p + ((long long)q + (long long)o * r) * o * v;          // B2 (l x c)
+          hp[0 * ng + g] = Acat + ((long long)p + (long long)o * q) * v * n;   // (x  x [d|l])
+          hp[1 * ng + g] = Bcat + (long long)r * n * v2;                       // ([d|l] x (y,z))
+          hp[2 * ng + g] = out + (long long)g * v3;                            // C(x,(y,z))
         }
       }
       AFESP_CUDA_CHECK(cudaMemcpyAsync(ptrs_shim.p, hp.data(), hp.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
       AFESP_CUDA_CHECK(cudaStreamSynchronize(st));  // hp is a stack-scoped staging vector
       tr.lap(2);
       const double* const* dp = reinterpret_cast<const double* const*>(ptrs_shim.p);
-      // hole term first, write-only (bandwidth-bound, K = o); the particle GEMM then accumulates on top of it so the
-      // read-modify-write of X hides inside a compute-bound kernel.
-      GemmBatch b2;
-      b2.count = ng; b2.Aptr = dp + 3 * ng; b2.Bptr = dp + 4 * ng;
-      b2.Cptr = (double* const*)(dp + 2 * ng); b2.ptr_aligned16 = al16;
-      dgemm(st, 'T', 'N', (int)v2, v, o, -1.0, nullptr, o, nullptr, o, 0.0, nullptr, v2, &b2);
-      tr.lap(3);
       GemmBatch b1;
       b1.count = ng; b1.Aptr = dp + 0 * ng; b1.Bptr = dp + 1 * ng;
       b1.Cptr = (double* const*)(dp + 2 * ng); b1.ptr_aligned16 = al16;
-      dgemm(st, 'N', 'N', v, (int)v2, v, 1.0, nullptr, v, nullptr, v, 1.0, nullptr, v, &b1);
+      dgemm(st, 'N', 'N', v, (int)v2, n, 1.0, nullptr, v, nullptr, n, 0.0, nullptr, v, &b1);
       tr.lap(4);
     };
-    run_gemms(Vv, Vo, X.p);
-    if (do_m) run_gemms(Mv, Mo, XM->p);
+    run_gemms(sAcat.p, sBcat.p, X.p);
+    if (do_m) run_gemms(sAcatM->p, sBcatM->p, XM->p);
     FusedArgs fa{};
     fa.X = X.p; fa.XM = do_m ? XM->p : nullptr; fa.t1 = s.t1.p(); fa.t2 = s.t2.p(); fa.vo = s.get("v_oovv").p();
     fa.eo = s.eo.p(); fa.ev = s.ev.p(); fa.tr = reinterpret_cast<const TripleDesc*>(descs.p);
@@ -522,7 +530,7 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
     tr.lap(6);
   }
   {
-    const char* names[] = {"layouts", "setup", "ptr upload", "gemm hole", "gemm particle", "fused epilogue", "finish"};
+    const char* names[] = {"operands", "setup", "ptr upload", "-", "gemm (K=v+o)", "fused epilogue", "finish"};
     tr.report(names, 7);
   }
   std::vector<double> h(nbatches * 6);
