@@ -31,6 +31,17 @@ METRIC = "ccsd_iter_plus_T_seconds"
 UNIT = "s"
 
 
+# Keep stdout clean for the single JSON line: libraries loaded later (NCCL prints its version banner on stdout) write
+# to fd 1, so fd 1 is pointed at stderr for the whole run and the JSON goes to the saved original descriptor.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -100,7 +111,7 @@ def run_reference(args, rank):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -281,7 +292,7 @@ def run_ours(args, rank, world, local):
             "gpu_launches": int(l1 - l0),
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     gpu.close()
     if world > 1:
         dist.destroy_process_group()
