@@ -313,7 +313,7 @@ int afesp_gpu_ccsd_finalize(afesp_handle hv, int want_cr, double* t1_diag, doubl
       return;
     }
     s.diis = CCDiis();
-    for (const char* nm : {"v_vvvv", "W_efab", "vvvv", "ovvv", "W_vvov", "I_oooo", "I_ovov", "I_voov", "I_ooov_p",
+    for (const char* nm : {"v_vvvv", "V_plus", "V_minus", "W_efab", "vvvv", "ovvv", "I_oooo", "I_ovov", "I_voov", "I_ooov_p",
                            "x_voov", "c_oovv", "A_oovv", "W_ijmn", "W_ovvo", "tau", "tau_tilde"})
       s.drop(nm);
     s.t1n.free(); s.t2n.free(); s.t2_old.free();

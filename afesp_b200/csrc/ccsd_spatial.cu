@@ -8,7 +8,10 @@
 //
 // Deviations that do not change results beyond rounding:
 //  * the in-place antisymmetrise/deantisymmetrise round trips on the integral slices (:1089-1126) are replaced by
-//    constant tensors built once (A_oovv = 2 v_oovv - v_oovv^(ab), W_vvov = 2 v_vvov^(T) - v_vvov);
+//    a constant tensor built once (A_oovv = 2 v_oovv - v_oovv^(ab)) and by two-step contractions for the v_vvov term;
+//  * the particle-particle ladder (:1669) runs in (+/-)-symmetrised virtual-pair form, 1/2 [S Vp + A Vm]: two GEMMs
+//    o^2 x P x P with P ~ v^2/2 -- half the flop and half the memory of the dense v^4 slice, which is never formed
+//    (it would be 134 GB at nbf=400);
 //  * I_vovv_p (o v^3, :1261-1299) is never materialised: its only consumer, t1 * I_vovv_p (:1700), is expanded into
 //    one o^2v^3 GEMM against v_vvov and two o^3v^2 two-step products;
 //  * energy denominators are evaluated from the orbital energies inside the divide kernel.
@@ -32,7 +35,7 @@ void ccsd_spatial_init(CCState& s, int diis_n) {
   // integral slices, physicist order (src/ccsd.f90:507-512)
   struct Sl { const char* name; char k[5]; };
   const Sl sl[] = {{"v_oovv", "oovv"}, {"v_ovov", "ovov"}, {"v_vvov", "vvov"},
-                   {"v_oovo", "oovo"}, {"v_oooo", "oooo"}, {"v_vvvv", "vvvv"}};
+                   {"v_oovo", "oovo"}, {"v_oooo", "oooo"}};
   for (const Sl& x : sl) {
     int lo[4], cnt[4];
     std::vector<int> dims;
@@ -49,10 +52,17 @@ void ccsd_spatial_init(CCState& s, int diis_n) {
   Tensor& A = s.make("A_oovv", {o, o, v, v});
   transpose(e, "ijab->ijba", -1.0, V(v_oovv), 0.0, V(A));
   axpby(e.stream, A.size(), 2.0, v_oovv.p(), 1.0, A.p());
-  // W_vvov(b,a,m,e) = 2 v_vvov(e,b,m,a) - v_vvov(b,e,m,a)      (antisymmetrise '2134' + reshape '2431', :1101-1104)
-  Tensor& W = s.make("W_vvov", {v, v, o, v});
-  transpose(e, "ebma->bame", 2.0, V(s.get("v_vvov")), 0.0, V(W));
-  transpose(e, "bema->bame", -1.0, V(s.get("v_vvov")), 1.0, V(W));
+  // (+/-)-symmetrised <ef|ab> over virtual pairs for the ladder (replaces the dense v_vvvv slice of :512)
+  {
+    const long long Pp = (long long)v * (v + 1) / 2, Pm = (long long)v * (v - 1) / 2;
+    AFESP_REQUIRE(Pp < (1LL << 31), "too many virtual pairs");
+    Tensor& Vp = s.make("V_plus", {(int)Pp, (int)Pp});
+    build_vpm(e, Vp.p(), s.eri_mo.p, o, v, +1);
+    if (Pm > 0) {
+      Tensor& Vm = s.make("V_minus", {(int)Pm, (int)Pm});
+      build_vpm(e, Vm.p(), s.eri_mo.p, o, v, -1);
+    }
+  }
 
   s.t1.init({o, v}); s.t1n.init({o, v});
   s.t2.init({o, o, v, v}); s.t2n.init({o, o, v, v}); s.t2_old.init({o, o, v, v});
@@ -76,7 +86,7 @@ void ccsd_spatial_iterate(CCState& s) {
   const int o = s.o, v = s.v;
   Tensor &t1 = s.t1, &t2 = s.t2;
   Tensor &v_oovv = s.get("v_oovv"), &v_ovov = s.get("v_ovov"), &v_vvov = s.get("v_vvov"), &v_oovo = s.get("v_oovo"),
-         &v_oooo = s.get("v_oooo"), &v_vvvv = s.get("v_vvvv"), &A = s.get("A_oovv"), &W = s.get("W_vvov");
+         &v_oooo = s.get("v_oooo"), &A = s.get("A_oovv");
   Tensor &I_vo = s.get("I_vo"), &I_vv = s.get("I_vv"), &I_oo_p = s.get("I_oo_p"), &I_oo = s.get("I_oo"),
          &c = s.get("c_oovv"), &asym = s.get("asym_t2"), &x_voov = s.get("x_voov"), &I_oooo = s.get("I_oooo"),
          &I_ovov = s.get("I_ovov"), &I_voov = s.get("I_voov"), &I_ooov_p = s.get("I_ooov_p");
@@ -95,7 +105,20 @@ void ccsd_spatial_iterate(CCState& s) {
   // I_vo(a,i) = A(i,m,a,e) t1(m,e)                                                        (:1089-1092)
   E("imae,me->ai", 1.0, A, t1, 0.0, I_vo);
   // I_vv(b,a) = [2v(e,b,m,a) - v(b,e,m,a)] t1(m,e) - A(m,n,e,b) c(m,n,e,a)                (:1101-1111)
-  E("bame,me->ba", 1.0, W, t1, 0.0, I_vv);
+  {
+    // 2 v(e,b,m,a) t1(m,e): Z(n,b,m,a) = t1(n,e) v_vvov(e,b,m,a) (one GEMM on v_vvov in place), then the n == m diagonal
+    Scratch z(e.pool, (size_t)t2.size());
+    TView Z(z.p, {o, v, o, v});
+    einsum(e, "ne,ebma->nbma", 1.0, V(t1), V(v_vvov), 0.0, Z);
+    diag_sum_nbma(st, I_vv.p(), z.p, o, v, 2.0);
+    // - v(b,e,m,a) t1(m,e): for each a, I_vv(:,a) -= v_vvov(:,(e,m),a) t1^T(e,m)   (batched GEMV on v_vvov in place)
+    Tensor t1T({v, o});
+    transpose(e, "me->em", 1.0, V(t1), 0.0, V(t1T));
+    GemmBatch bt;
+    bt.count = v; bt.strideA = (long long)v * v * o; bt.strideB = 0; bt.strideC = v;
+    dgemm(st, 'N', 'N', v, 1, v * o, -1.0, v_vvov.p(), v, t1T.p(), (long long)v * o, 1.0, I_vv.p(), v, &bt);
+    AFESP_CUDA_CHECK(cudaStreamSynchronize(st));  // t1T is freed at scope exit
+  }
   E("mneb,mnea->ba", -1.0, A, c, 1.0, I_vv);
   // I_oo_p(j,i) = [2v_oovo(m,i,e,j) - v_oovo(i,m,e,j)] t1(m,e) + asym_t2(j,m,f,e) v_oovv(m,i,e,f)   (:1121-1131)
   E("miej,me->ji", 2.0, v_oovo, t1, 0.0, I_oo_p);
@@ -143,7 +166,17 @@ void ccsd_spatial_iterate(CCState& s) {
   E("efma,mief->ia", 1.0, v_vvov, asym, 1.0, r1);         // :1618-1630
   E("ijae,eb->ijab", 1.0, t2, I_vv, 0.0, X);              // :1647
   E("miba,jm->ijab", -1.0, t2, I_oo, 1.0, X);             // :1654-1664
-  E("ijef,efab->ijab", 0.5, c, v_vvvv, 1.0, X);           // :1669  particle-particle ladder (dominant)
+  {
+    // :1669  particle-particle ladder (dominant): 1/2 c(ij,ef) <ef|ab> = 1/4 [S Vp + A Vm] unpacked over (a,b)
+    const long long Pp = (long long)v * (v + 1) / 2, Pm = (long long)v * (v - 1) / 2;
+    const int oo = o * o;
+    Scratch sS(e.pool, (size_t)(oo * Pp)), sA(e.pool, (size_t)std::max<long long>(oo * Pm, 1));
+    Scratch sLp(e.pool, (size_t)(oo * Pp)), sLm(e.pool, (size_t)std::max<long long>(oo * Pm, 1));
+    pack_c(e, sS.p, sA.p, c.p(), oo, v);
+    dgemm(st, 'N', 'N', oo, (int)Pp, (int)Pp, 1.0, sS.p, oo, s.get("V_plus").p(), Pp, 0.0, sLp.p, oo);
+    if (Pm > 0) dgemm(st, 'N', 'N', oo, (int)Pm, (int)Pm, 1.0, sA.p, oo, s.get("V_minus").p(), Pm, 0.0, sLm.p, oo);
+    unpack_ladder(e, X.p(), sLp.p, sLm.p, oo, v, 0.5);
+  }
   E("ijmn,mnab->ijab", 0.5, I_oooo, c, 1.0, X);           // :1673
   E("mjae,iemb->ijab", -1.0, t2, I_ovov, 1.0, X);         // :1680-1695 (three o^3v^3 rings)
   E("iema,mjeb->ijab", -1.0, I_ovov, t2, 1.0, X);
@@ -188,7 +221,14 @@ void ccsd_spatial_cr_intermediates(CCState& s) {
   const int o = s.o, v = s.v;
   Tensor &t1 = s.t1, &t2 = s.t2;
   Tensor &v_oovv = s.get("v_oovv"), &v_ovov = s.get("v_ovov"), &v_vvov = s.get("v_vvov"), &v_oovo = s.get("v_oovo"),
-         &v_oooo = s.get("v_oooo"), &v_vvvv = s.get("v_vvvv");
+         &v_oooo = s.get("v_oooo");
+  // the CR intermediates need the dense <ab|cd> slice once (v_vvvv . t1, :2515); built here, dropped at the end
+  s.drop("V_plus"); s.drop("V_minus");
+  Tensor& v_vvvv = s.make("v_vvvv", {v, v, v, v});
+  {
+    const int lo4[4] = {o, o, o, o}, cnt4[4] = {v, v, v, v};
+    slice_phys(e, v_vvvv.p(), s.eri_mo.p, lo4, cnt4);
+  }
   Tensor &I_vo = s.get("I_vo"), &asym = s.get("asym_t2");
   if (!s.opt.q3b_stale_intermediates) {
     transpose(e, "ijab->jiab", -1.0, V(t2), 0.0, V(asym));
@@ -199,7 +239,7 @@ void ccsd_spatial_cr_intermediates(CCState& s) {
     einsum(e, spec, alpha, a, b, beta, cc);
   };
   // free what the reference frees (:2364-2365) to make room
-  for (const char* nm : {"I_oooo", "I_ovov", "I_voov", "I_ooov_p", "x_voov", "c_oovv", "W_vvov"}) s.drop(nm);
+  for (const char* nm : {"I_oooo", "I_ovov", "I_voov", "I_ooov_p", "x_voov", "c_oovv"}) s.drop(nm);
   Tensor x_vvvo_p({v, v, v, o}), x_vvvo({v, v, v, o}), x_ovov_p({o, v, o, v}), x_voov_p({v, o, o, v}),
       x_ovoo({o, v, o, o}), x_ovov_pp({o, v, o, v}), x_voov_pp({v, o, o, v});
   // x_vvvo_p(b,c,a,i) = v_vvov(c,b,i,a) - 1/2 t1(m,a) v_oovv(m,i,b,c)                     (:2425-2435)
@@ -231,6 +271,8 @@ void ccsd_spatial_cr_intermediates(CCState& s) {
   Tensor& Ivv = s.make("I_vovv_pp", {v, o, v, v});
   transpose(e, "baic->ciab", 1.0, V(v_vvov), 0.0, V(Ivv));
   E("ecba,ie->ciab", 1.0, V(v_vvvv), V(t1), 1.0, V(Ivv));
+  AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
+  s.drop("v_vvvv");
   E("icma,mb->ciab", -1.0, V(x_ovov_p), V(t1), 1.0, V(Ivv));
   E("ma,cimb->ciab", -1.0, V(t1), V(x_voov_p), 1.0, V(Ivv));
   E("cm,miab->ciab", -1.0, V(I_vo), V(t2), 1.0, V(Ivv));

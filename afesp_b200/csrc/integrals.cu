@@ -151,6 +151,85 @@ __global__ void k_slice_spinorb(double* __restrict__ out, const double* __restri
   }
 }
 
+// (+/-)-symmetrised virtual-pair integrals for the particle-particle ladder:
+//   Vp(ef, ab) = <ef|ab> + <ef|ba>,  e<=f, a<=b   (P+ = v(v+1)/2 pairs, pair(a,b) = b(b+1)/2 + a)
+//   Vm(ef, ab) = <ef|ab> - <ef|ba>,  e<f,  a<b    (P- = v(v-1)/2 pairs, pair(a,b) = b(b-1)/2 + a)
+// <ef|ab> = (ea|fb), virtual indices offset by nocc in the packed MO array.
+__global__ void k_build_vpm(double* __restrict__ V, const double* __restrict__ g, int o, int v, int sign) {
+  const long long P = sign > 0 ? (long long)v * (v + 1) / 2 : (long long)v * (v - 1) / 2;
+  const long long total = P * P;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long ef = idx % P, ab = idx / P;
+    long long f, e, b, a;
+    if (sign > 0) {
+      f = (long long)((sqrt(8.0 * (double)ef + 1.0) - 1.0) * 0.5);
+      while (f * (f + 1) / 2 > ef) --f;
+      while ((f + 1) * (f + 2) / 2 <= ef) ++f;
+      e = ef - f * (f + 1) / 2;
+      b = (long long)((sqrt(8.0 * (double)ab + 1.0) - 1.0) * 0.5);
+      while (b * (b + 1) / 2 > ab) --b;
+      while ((b + 1) * (b + 2) / 2 <= ab) ++b;
+      a = ab - b * (b + 1) / 2;
+    } else {
+      f = (long long)((sqrt(8.0 * (double)ef + 1.0) + 1.0) * 0.5);
+      while (f * (f - 1) / 2 > ef) --f;
+      while ((f + 1) * f / 2 <= ef) ++f;
+      e = ef - f * (f - 1) / 2;
+      b = (long long)((sqrt(8.0 * (double)ab + 1.0) + 1.0) * 0.5);
+      while (b * (b - 1) / 2 > ab) --b;
+      while ((b + 1) * b / 2 <= ab) ++b;
+      a = ab - b * (b - 1) / 2;
+    }
+    const long long E = e + o, F = f + o, A = a + o, B = b + o;
+    const double x = g[tri(tri(E, A), tri(F, B))];   // <ef|ab>
+    const double y = g[tri(tri(E, B), tri(F, A))];   // <ef|ba>
+    V[idx] = sign > 0 ? x + y : x - y;
+  }
+}
+
+// S(ij, e<=f) = c(ij,ef) + c(ij,fe) (e<f), c(ij,ee) (e==f);   A(ij, e<f) = c(ij,ef) - c(ij,fe)
+__global__ void k_pack_c(double* __restrict__ S, double* __restrict__ A, const double* __restrict__ c, int oo, int v) {
+  const long long Pp = (long long)v * (v + 1) / 2, Pm = (long long)v * (v - 1) / 2;
+  const long long total = (long long)oo * v * v;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int ij = (int)(idx % oo);
+    long long ef = idx / oo;
+    int e = (int)(ef % v), f = (int)(ef / v);
+    if (e > f) continue;
+    double x = c[idx];
+    if (e == f) {
+      S[ij + (long long)oo * ((long long)f * (f + 1) / 2 + e)] = x;
+    } else {
+      double y = c[ij + (long long)oo * (f + (long long)v * e)];
+      S[ij + (long long)oo * ((long long)f * (f + 1) / 2 + e)] = x + y;
+      A[ij + (long long)oo * ((long long)f * (f - 1) / 2 + e)] = x - y;
+    }
+  }
+  (void)Pp; (void)Pm;
+}
+
+// X(ij,a,b) += alpha/2 (Lp + Lm), X(ij,b,a) += alpha/2 (Lp - Lm) for a<b;  X(ij,a,a) += alpha/2 Lp
+__global__ void k_unpack_ladder(double* __restrict__ X, const double* __restrict__ Lp, const double* __restrict__ Lm,
+                                int oo, int v, double alpha) {
+  const long long total = (long long)oo * v * v;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int ij = (int)(idx % oo);
+    long long ab = idx / oo;
+    int a = (int)(ab % v), b = (int)(ab / v);
+    int lo = a < b ? a : b, hi = a < b ? b : a;
+    double lp = Lp[ij + (long long)oo * ((long long)hi * (hi + 1) / 2 + lo)];
+    double r = 0.5 * lp;
+    if (a != b) {
+      double lm = Lm[ij + (long long)oo * ((long long)hi * (hi - 1) / 2 + lo)];
+      r += (a < b ? 0.5 : -0.5) * lm;
+    }
+    X[idx] += alpha * r;
+  }
+}
+
 inline int grid_for(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 16)); }
 
 // One half transform over spectator blocks (see file header).
@@ -203,6 +282,23 @@ void mp2_energy(Engine& e, int n, int nocc, const double* eri_mo, const double* 
   k_mp2<<<nb, 256, 0, e.stream>>>(eri_mo, eps, n, nocc, part);
   count_launch();
   finish_partials(e, part, nb, 1, out_dev);
+}
+
+void build_vpm(Engine& e, double* V, const double* eri_mo, int o, int v, int sign) {
+  const long long P = sign > 0 ? (long long)v * (v + 1) / 2 : (long long)v * (v - 1) / 2;
+  if (P == 0) return;
+  k_build_vpm<<<grid_for(P * P), 256, 0, e.stream>>>(V, eri_mo, o, v, sign);
+  count_launch();
+}
+
+void pack_c(Engine& e, double* S, double* A, const double* c, int oo, int v) {
+  k_pack_c<<<grid_for((long long)oo * v * v), 256, 0, e.stream>>>(S, A, c, oo, v);
+  count_launch();
+}
+
+void unpack_ladder(Engine& e, double* X, const double* Lp, const double* Lm, int oo, int v, double alpha) {
+  k_unpack_ladder<<<grid_for((long long)oo * v * v), 256, 0, e.stream>>>(X, Lp, Lm, oo, v, alpha);
+  count_launch();
 }
 
 void slice_phys(Engine& e, double* out, const double* eri_mo, const int lo[4], const int cnt[4]) {

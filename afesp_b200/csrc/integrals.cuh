@@ -19,4 +19,10 @@ void slice_phys(Engine& e, double* out, const double* eri_mo, const int lo[4], c
 // out(P,Q,R,S) = <PQ||RS> over spin-orbital index ranges (src/ccsd.f90:111-143, 182-194)
 void slice_spinorb(Engine& e, double* out, const double* eri_mo, const int lo[4], const int cnt[4]);
 
+// Particle-particle ladder in (+/-)-symmetrised virtual-pair form (half the flop and memory of the dense v^4 slice):
+//   sum_ef c(ij,ef) <ef|ab> = 1/2 [ S Vp + A Vm ](ij,ab),  S/A = symmetric/antisymmetric parts of c in (e,f)
+void build_vpm(Engine& e, double* V, const double* eri_mo, int o, int v, int sign);   // sign +1: Vp (P+ x P+), -1: Vm
+void pack_c(Engine& e, double* S, double* A, const double* c, int oo, int v);
+void unpack_ladder(Engine& e, double* X, const double* Lp, const double* Lm, int oo, int v, double alpha);
+
 }  // namespace afesp

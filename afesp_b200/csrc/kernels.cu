@@ -45,6 +45,16 @@ __global__ void k_t2_plus_t1t1(double* __restrict__ out, const double* __restric
   }
 }
 
+__global__ void k_diag_sum_nbma(double* __restrict__ out, const double* __restrict__ Z, int o, int v, double alpha) {
+  const int total = v * v;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    int b = idx % v, a = idx / v;
+    double s = 0.0;
+    for (int m = 0; m < o; ++m) s += Z[m + (long long)o * (b + (long long)v * (m + (long long)o * a))];
+    out[idx] = alpha * s;
+  }
+}
+
 __global__ void k_axpby(long long n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = (b == 0.0) ? a * x[i] : a * x[i] + b * y[i];
@@ -170,6 +180,11 @@ void t2_plus_t1t1(cudaStream_t st, double* out, const double* t2, const double* 
   k_t2_plus_t1t1<<<grid_for((long long)o * o * v * v), 256, 0, st>>>(out, t2, t1, o, v, ca, cb);
   count_launch();
 }
+void diag_sum_nbma(cudaStream_t st, double* out, const double* Z, int o, int v, double alpha) {
+  k_diag_sum_nbma<<<grid_for((long long)v * v), 256, 0, st>>>(out, Z, o, v, alpha);
+  count_launch();
+}
+
 void axpby(cudaStream_t st, long long n, double a, const double* x, double b, double* y) {
   if (n <= 0) return;
   k_axpby<<<grid_for(n), 256, 0, st>>>(n, a, x, b, y);

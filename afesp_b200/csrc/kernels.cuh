@@ -13,6 +13,9 @@ void divide_d1(cudaStream_t st, double* out, const double* x, const double* eo, 
 //   spin-free c_oovv: ca=1, cb=0 (src/ccsd.f90:1071-1079); tau: ca=1, cb=-1; tau_tilde: ca=.5, cb=-.5 (:701-711)
 void t2_plus_t1t1(cudaStream_t st, double* out, const double* t2, const double* t1, int o, int v, double ca, double cb);
 
+// out(b,a) = alpha * sum_m Z(m,b,m,a) for Z(o,v,o,v)   (diagonal of a two-step contraction, see ccsd_spatial.cu)
+void diag_sum_nbma(cudaStream_t st, double* out, const double* Z, int o, int v, double alpha);
+
 // y = a*x + b*y ; y = a*x (b == 0 never reads y)
 void axpby(cudaStream_t st, long long n, double a, const double* x, double b, double* y);
 void fill(cudaStream_t st, long long n, double val, double* y);
