@@ -20,6 +20,9 @@ SIGNATURES = {
     "afesp_gpu_counters": [_H, C.POINTER(C.c_longlong), _dp],
     "afesp_gpu_ao2mo": [_H, C.c_int, _dp, _dp, _dp],
     "afesp_gpu_set_eri_mo": [_H, C.c_int, _dp],
+    "afesp_gpu_synth_eri_ao": [_H, C.c_int, C.c_int, _dp, _dp],
+    "afesp_gpu_get_eri_mo": [_H, _dp],
+    "afesp_gpu_release": [_H, C.c_char_p],
     "afesp_gpu_mp2_energy": [_H, C.c_int, _dp, _dp],
     "afesp_gpu_ccsd_init": [_H, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp],
     "afesp_gpu_ccsd_iterate": [_H, _dp, _dp],
@@ -149,6 +152,24 @@ class AfespGpu:
         self._check("ao2mo", rc)
         self.n = nbasis
         return out
+
+    def synth_eri_ao(self, nbasis, factors, coeff):
+        """factors: (npair, naux) array in pair order; the packed AO integrals are built on the device."""
+        f = fortran_flat(factors)
+        c = fortran_flat(coeff)
+        self._check("synth_eri_ao", self.lib.afesp_gpu_synth_eri_ao(self.h, int(nbasis), int(factors.shape[1]),
+                                                                    _ptr(f), _ptr(c)))
+        self.n = int(nbasis)
+
+    def get_eri_mo(self, out=None):
+        npair = self.n * (self.n + 1) // 2
+        if out is None:
+            out = np.empty(npair * (npair + 1) // 2)
+        self._check("get_eri_mo", self.lib.afesp_gpu_get_eri_mo(self.h, _ptr(out)))
+        return out
+
+    def release(self, what):
+        self._check("release", self.lib.afesp_gpu_release(self.h, what.encode()))
 
     def set_eri_mo(self, nbasis, eri_mo):
         e = np.ascontiguousarray(eri_mo, dtype=np.float64)

@@ -210,10 +210,48 @@ int afesp_gpu_ao2mo(afesp_handle hv, int n, const double* eri_ao, const double* 
     StageTimer tm(&h);
     ao2mo_packed(h.s.eng, n, h.eri_ao.p, h.coeff.p, h.s.eri_mo.p);
     tm.stop();
+    h.s.eng.pool.clear();  // the npair^2 half-transformed matrix goes back to the driver
     if (eri_mo) {
       AFESP_CUDA_CHECK(cudaMemcpyAsync(eri_mo, h.s.eri_mo.p, np * 8, cudaMemcpyDeviceToHost, st));
       AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
     }
+  });
+}
+
+int afesp_gpu_synth_eri_ao(afesp_handle hv, int n, int naux, const double* factors, const double* coeff) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(n > 0 && naux > 0 && factors && coeff, "synth_eri_ao: bad arguments");
+    const long long np = npacked_of(n), npair = npair_of(n);
+    cudaStream_t st = h.s.eng.stream;
+    DBuf B((size_t)npair * naux);
+    AFESP_CUDA_CHECK(cudaMemcpyAsync(B.p, factors, (size_t)npair * naux * 8, cudaMemcpyHostToDevice, st));
+    if ((long long)h.eri_ao.n != np) h.eri_ao.alloc((size_t)np);
+    if ((long long)h.coeff.n != (long long)n * n) h.coeff.alloc((size_t)n * n);
+    AFESP_CUDA_CHECK(cudaMemcpyAsync(h.coeff.p, coeff, (size_t)n * n * 8, cudaMemcpyHostToDevice, st));
+    StageTimer tm(&h);
+    synth_eri_from_factors(h.s.eng, n, naux, B.p, h.eri_ao.p);
+    tm.stop();
+    h.n_ao = n;
+    h.s.eng.pool.clear();
+  });
+}
+
+int afesp_gpu_get_eri_mo(afesp_handle hv, double* eri_mo) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(eri_mo && h.s.eri_mo.p, "get_eri_mo: no MO integrals on the device");
+    AFESP_CUDA_CHECK(cudaMemcpy(eri_mo, h.s.eri_mo.p, h.s.eri_mo.n * 8, cudaMemcpyDeviceToHost));
+  });
+}
+
+int afesp_gpu_release(afesp_handle hv, const char* what) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(what != nullptr, "release: null argument");
+    std::string w(what);
+    AFESP_CUDA_CHECK(cudaStreamSynchronize(h.s.eng.stream));
+    if (w == "eri_ao") { h.eri_ao.release(); h.coeff.release(); h.n_ao = 0; }
+    else if (w == "eri_mo") h.s.eri_mo.release();
+    else if (w == "scratch") h.s.eng.pool.clear();
+    else throw Error(1, "release: unknown object " + w);
   });
 }
 

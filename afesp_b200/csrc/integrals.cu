@@ -263,6 +263,36 @@ void half_transform(Engine& e, int n, const double* C, const double* src, int sr
 
 }  // namespace
 
+namespace {
+// eri[tri(ij,kl)] = G(ij, kl0 + c) for ij >= kl  (G block: npair x nb, ij fastest)
+__global__ void k_pack_lower_block(double* __restrict__ eri, const double* __restrict__ G, long long npair, long long kl0,
+                                   int nb) {
+  const long long total = npair * nb;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long ij = idx % npair, kl = kl0 + idx / npair;
+    if (ij >= kl) eri[ij * (ij + 1) / 2 + kl] = G[idx];
+  }
+}
+}  // namespace
+
+// Synthetic AO integrals on the device: eri[packed] = sum_P B(ij,P) B(kl,P), B is (npair x naux) column-major.
+void synth_eri_from_factors(Engine& e, int n, int naux, const double* B, double* eri, long long block_bytes) {
+  const long long npair = (long long)n * (n + 1) / 2;
+  long long nb = std::max<long long>(1, std::min<long long>(npair, block_bytes / (npair * 8)));
+  if (nb > 16) nb = nb / 16 * 16;
+  Scratch G(e.pool, (size_t)(npair * nb));
+  for (long long kl0 = 0; kl0 < npair; kl0 += nb) {
+    const int cb = (int)std::min<long long>(nb, npair - kl0);
+    // G(ij, c) = sum_P B(ij,P) B(kl0+c, P)
+    dgemm(e.stream, 'N', 'T', (int)npair, cb, naux, 1.0, B, npair, B + kl0, npair, 0.0, G.p, npair);
+    k_pack_lower_block<<<(int)std::min<long long>((npair * cb + 255) / 256, 148LL * 16), 256, 0, e.stream>>>(
+        eri, G.p, npair, kl0, cb);
+    count_launch();
+  }
+  AFESP_CUDA_CHECK(cudaGetLastError());
+}
+
 long long npair_of(int n) { return (long long)n * (n + 1) / 2; }
 long long npacked_of(int n) { long long m = npair_of(n); return m * (m + 1) / 2; }
 

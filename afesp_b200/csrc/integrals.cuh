@@ -11,6 +11,9 @@ long long npacked_of(int n);  // npair(npair+1)/2
 void ao2mo_packed(Engine& e, int n, const double* eri_ao, const double* C, double* eri_mo,
                   long long block_bytes = 3LL << 30);
 
+// Synthetic packed AO integrals eri = sum_P B(ij,P) B(kl,P) from device-resident factors B (npair x naux).
+void synth_eri_from_factors(Engine& e, int n, int naux, const double* B, double* eri, long long block_bytes = 2LL << 30);
+
 // MP2 correlation energy (src/mp2.f90:418-438) from packed MO integrals; result in out_dev[0].
 void mp2_energy(Engine& e, int n, int nocc, const double* eri_mo, const double* eps, double* out_dev);
 

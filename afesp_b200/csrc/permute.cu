@@ -57,8 +57,11 @@ struct TransParams {
 __global__ void permute_transpose(const TransParams p, const double* __restrict__ in, double* __restrict__ out) {
   __shared__ double tile[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int i0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  const int i0 = blockIdx.x * 32;
+  const int tiles_b = (p.nb + 31) / 32;
+  for (int by = blockIdx.y; by < tiles_b; by += gridDim.y)
   for (long long rest = blockIdx.z; rest < p.rest_total; rest += gridDim.z) {
+    const int b0 = by * 32;
     long long rem = rest, ibase = 0, obase = 0;
     for (int d = 0; d < p.nrest; ++d) {
       long long q = rem / p.rdims[d];
@@ -162,8 +165,8 @@ void permute_strided(cudaStream_t st, int rank, const int* dims, const int* perm
       ++p.nrest;
     }
     p.alpha = alpha; p.beta = beta;
-    dim3 grid((p.n0 + 31) / 32, (p.nb + 31) / 32, (unsigned)std::min<long long>(p.rest_total, 65535));
-    AFESP_REQUIRE(grid.y <= 65535, "permute: grid too large");
+    dim3 grid((p.n0 + 31) / 32, (unsigned)std::min<long long>((p.nb + 31) / 32, 65535),
+              (unsigned)std::min<long long>(p.rest_total, 65535));
     permute_transpose<<<grid, dim3(32, 8), 0, st>>>(p, in, out);
   }
   count_launch();

@@ -13,6 +13,25 @@ from __future__ import annotations
 import numpy as np
 
 
+def make_factors(nbf: int, nocc: int, seed: int = 20260, w: float = 6.0, target_emp2_per_occ: float = 0.02):
+    """Returns (B[npair, naux], C[mo,ao], eps): the same system as make(), with the ERIs left in factored form
+    (ij|kl) = sum_P B[ij,P] B[kl,P] so that large shapes can be expanded on the device (afesp_gpu_synth_eri_ao)."""
+    rng = np.random.default_rng(seed)
+    n, o, v = nbf, nocc, nbf - nocc
+    naux = n
+    ii, jj = np.tril_indices(n)
+    damp = np.exp(-(ii - jj) / w)
+    B = rng.standard_normal((ii.size, naux)) * damp[:, None]
+    full_ms = (2.0 * np.sum(B * B) - np.sum(B[ii == jj] ** 2)) / (n * n * naux)
+    sigma4 = 3.0 * target_emp2_per_occ / (o * v * v * naux)
+    B *= (sigma4 ** 0.25) / np.sqrt(full_ms)
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    eps = np.concatenate([np.linspace(-2.0, -0.5, o), np.linspace(0.5, 3.0, v)])
+    eps += 0.01 * rng.standard_normal(n)
+    eps = np.sort(eps)
+    return B, np.ascontiguousarray(q.T), eps
+
+
 def make(nbf: int, nocc: int, seed: int = 20260, w: float = 6.0, target_emp2_per_occ: float = 0.02):
     """Returns (eri_ao_packed, C[mo,ao], eps)."""
     rng = np.random.default_rng(seed)

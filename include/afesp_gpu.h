@@ -51,6 +51,15 @@ int afesp_gpu_counters(afesp_handle h, long long* launches, double* gemm_flops);
 /* eri_ao[npacked], coeff(n,n) = C(mo,ao) (sys%canon_coeff, src/hf.f90:102,127) -> eri_mo[npacked] (host, optional).
  * Passing eri_ao == NULL and coeff == NULL repeats the transform on the copies already resident on the device. */
 int afesp_gpu_ao2mo(afesp_handle h, int nbasis, const double* eri_ao, const double* coeff, double* eri_mo);
+/* Synthetic workload input: build the packed AO integrals on the device from a low-rank
+ * factor, eri[(ij|kl)] = sum_P B(ij,P) B(kl,P), B = factors(npair, naux) column-major in pair order, and upload
+ * coeff(n,n); afterwards afesp_gpu_ao2mo(h, n, NULL, NULL, ...) transforms the resident copy.  (A text eri.dat at
+ * nbf=400 would be ~3e9 lines.) */
+int afesp_gpu_synth_eri_ao(afesp_handle h, int nbasis, int naux, const double* factors, const double* coeff);
+/* Copy the device-resident packed MO integrals to the host (npacked doubles). */
+int afesp_gpu_get_eri_mo(afesp_handle h, double* eri_mo);
+/* Free device memory the next stage does not need: what = "eri_ao" | "eri_mo" | "scratch". */
+int afesp_gpu_release(afesp_handle h, const char* what);
 /* Load packed MO integrals directly (a host that already holds int_store%eri_mo). */
 int afesp_gpu_set_eri_mo(afesp_handle h, int nbasis, const double* eri_mo);
 /* MP2 correlation energy from the device-resident MO integrals (src/mp2.f90:418-438); eps = sys%canon_levels(n). */

@@ -216,3 +216,29 @@ def test_triples_partition_sums_and_symmetry_switch(gpu, oracle_runs):
     finally:
         gpu.set_option("triples_batch_bytes", 6 << 30)
     assert np.max(np.abs(small - full)) < 1e-11
+
+
+# ---------------------------------------------------------------- synthetic workload path (device-generated integrals)
+def test_synthetic_chain_matches_oracle_and_device_generated_integrals(gpu):
+    from afesp_b200 import host, synthetic
+
+    n, o = 26, 4
+    eri, Cm, eps = synthetic.make(n, o, seed=11)
+    B, C2, eps2 = synthetic.make_factors(n, o, seed=11)
+    mo_ref = orc.ao2mo_packed(eri, Cm)
+    gpu.synth_eri_ao(n, B, C2)           # integrals expanded on the device from the low-rank factors
+    mo = gpu.ao2mo(n)                    # transform of the resident copy
+    assert np.max(np.abs(mo - mo_ref)) < 1e-12
+    assert np.max(np.abs(gpu.get_eri_mo() - mo)) == 0.0
+    assert abs(gpu.mp2_energy(o, eps) - orc.mp2_energy(mo_ref, eps, o)) < E_TOL
+    cc = orc.ccsd_spatial(mo_ref, eps, o, 1e-8, 1e-9, 8, 50, want_cr=True)
+    table, conv, e, _ = host.ccsd_loop(gpu, o, True, eps, 1e-8, 1e-9, 8, 50)
+    assert conv and len(table) == len(cc["table"]) and abs(e - cc["e_ccsd"]) < E_TOL
+    gpu.release("eri_ao")
+    gpu.ccsd_finalize(want_cr=True)
+    sums, const = gpu.ccsd_t_spatial(True, False, True)
+    en, osums = orc.triples_spatial(cc, eps, True, False, True)
+    assert np.max(np.abs(sums - np.array(osums))) < E_TOL
+    got = host.assemble_triples(e, sums, const, True, False, True)
+    for k in ["e_ccsd_t", "e_ccsd_tt", "e_rccsd_t", "e_rccsd_tt", "e_crccsd_t", "e_crccsd_tt", "D_T", "D_TT"]:
+        assert abs(got[k] - en[k]) < E_TOL, k
