@@ -102,6 +102,7 @@ struct Params {
   int kchunk;            // K extent per split (multiple of BK)
   double* ws;
   int cvec;              // 1: C base 16-byte aligned and ldc even -> 16-byte epilogue accesses
+  int tiles_m;           // CTA tiles along M; blockIdx.x enumerates (m-tile fastest, n-tile)
 };
 
 template <int BM, int BN, int BK, int WM, int WN, int STAGES, int MINB, bool AK, bool BKM, int VEC>
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) gemm_f64_dmm
   const int gid = lane >> 2, tig = lane & 3;
   const int wm0 = (warp % (BM / WM)) * WM;
   const int wn0 = (warp / (BM / WM)) * WN;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int m0 = (blockIdx.x % p.tiles_m) * BM, n0 = (blockIdx.x / p.tiles_m) * BN;
 
   int batch = blockIdx.z, split = 0;
   if (p.splitk > 1) { split = blockIdx.z % p.splitk; batch = blockIdx.z / p.splitk; }
@@ -320,9 +321,13 @@ void launch_cfg(cudaStream_t st, const Params& p, int nbatch) {
     AFESP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     attr_set = true;
   }
-  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, nbatch * (p.splitk > 1 ? p.splitk : 1));
-  AFESP_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm grid too large");
-  kern<<<grid, NT, SMEM, st>>>(p);
+  Params q = p;
+  q.tiles_m = (p.M + BM - 1) / BM;
+  const long long tiles = (long long)q.tiles_m * ((p.N + BN - 1) / BN);
+  AFESP_REQUIRE(tiles < (1LL << 31), "gemm: too many tiles");
+  dim3 grid((unsigned)tiles, 1, nbatch * (p.splitk > 1 ? p.splitk : 1));
+  AFESP_REQUIRE(grid.z <= 65535, "gemm: batch too large");
+  kern<<<grid, NT, SMEM, st>>>(q);
   count_launch();
   AFESP_CUDA_CHECK(cudaGetLastError());
 }
