@@ -179,6 +179,7 @@ int afesp_gpu_set_option(afesp_handle hv, const char* key, double value) {
     else if (k == "finalize_keep_ccsd") o.finalize_keep_ccsd = value != 0.0;
     else if (k == "gemm_timing") gemm_timing_enable(value != 0.0);
     else if (k == "gemm_force_config") gemm_force_config((int)value);
+    else if (k == "gemm_use_tma") gemm_tma_enable(value != 0.0);
     else throw Error(1, "set_option: unknown key " + k);
   });
 }

@@ -67,6 +67,13 @@ struct GemmBatch {
   const double* const* Bptr = nullptr;
   double* const* Cptr = nullptr;
   bool ptr_aligned16 = false;  // caller guarantees every A/B pointer in the arrays is 16-byte aligned
+  // Optional "gather" description of the pointer arrays (enables the TMA path): Aptr[g] == Abase + Aidx[g]*Ablock, etc.
+  const double* Abase = nullptr;
+  const double* Bbase = nullptr;
+  long long Ablock = 0, Bblock = 0;     // elements between consecutive blocks
+  long long Anblocks = 0, Bnblocks = 0; // number of blocks addressable through the index arrays
+  const int* Aidx = nullptr;            // device arrays of `count` block indices
+  const int* Bidx = nullptr;
 };
 void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, double alpha, const double* A,
            long long lda, const double* B, long long ldb, double beta, double* C, long long ldc,
@@ -77,6 +84,9 @@ extern double g_gemm_flops;
 // the live roofline figure.  gemm_timing_collect() synchronises and returns the accumulated milliseconds.
 void gemm_timing_enable(bool on);
 void gemm_force_config(int cfg);  // tuning aid: -1 = automatic tile selection
+void gemm_tma_enable(bool on);     // TMA-staged operand path for aligned problems (default on)
+bool dgemm_tma(cudaStream_t st, bool ak, bool bk, int M, int N, int K, double alpha, const double* A, long long lda,
+               const double* B, long long ldb, double beta, double* C, long long ldc, const GemmBatch* batch, int cvec);
 double gemm_timing_collect(double* flops_out);
 
 // ---- permute (permute.cu): out = alpha * permute(in) + beta * out for rank <= 6 ----

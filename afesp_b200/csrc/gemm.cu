@@ -455,7 +455,11 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
   }
   std::pair<cudaEvent_t, cudaEvent_t>* evs = g_timing ? next_events() : nullptr;
   if (evs) { cudaEventRecord(evs->first, st); g_timed_flops += 2.0 * M * N * (double)K * nbatch; }
-  launch_by_cfg(cfg, st, p, nbatch, ak, bk, vec2);
+  // aligned problems on the 64x64 tile go through the TMA-staged kernel (gemm_tma.cu); everything else through cp.async
+  bool used_tma = false;
+  if (cfg == 3 && p.splitk == 1 && vec2)
+    used_tma = dgemm_tma(st, ak, bk, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, batch, p.cvec);
+  if (!used_tma) launch_by_cfg(cfg, st, p, nbatch, ak, bk, vec2);
   if (p.splitk > 1) {
     long long MN = (long long)M * N;
     splitk_reduce<<<(int)std::min<long long>((MN + 255) / 256, 2048), 256, 0, st>>>(p.ws, p.splitk, M, N, alpha,

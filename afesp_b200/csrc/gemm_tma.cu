@@ -1,0 +1,348 @@
+// FP64 DMMA GEMM with TMA-staged operands (sm_100a): the aligned fast path of dgemm().
+//
+// Same math and epilogue as gemm_f64_dmma (gemm.cu); what changes is how operand tiles reach shared memory:
+//   * one producer warp: an elected lane arms an mbarrier with the stage's byte count and issues two
+//     cp.async.bulk.tensor (TMA) copies per k-tile -- no per-thread address arithmetic, no cp.async groups;
+//   * four consumer warps (32x32 DMMA sub-tiles of a 64x64 CTA tile) wait on the stage's "full" mbarrier, issue the
+//     DMMAs and release the slot through its "empty" mbarrier: the main loop has no CTA-wide barrier at all;
+//   * tiles land in the 128-byte-swizzled layout TMA produces.  Bank conflicts are avoided by choosing WHICH four
+//     k-indices feed each DMMA: the 16 k's of a tile are split into the sets {0,3,12,15} {1,2,13,14} {4,7,8,11}
+//     {5,6,9,10}; with that assignment every fragment load of a half-warp touches 16 distinct 8-byte banks for both
+//     the MN-major box layout [mn/16][k][16] and the K-major layout [mn][16 k] (derivation in DESIGN.md §4.1).
+// Operands may be batched three ways: plain, strided, or gathered through per-batch block indices (the (T) driver
+// gathers A by occupied pair and B by occupied index); tensor maps carry the batch as the outermost dimension.
+// Requirements (checked by the caller, otherwise the cp.async kernel runs): 16-byte aligned bases, even leading
+// dimensions and batch strides.  Out-of-range k is zero-filled by TMA; out-of-range m/n only ever feeds masked outputs.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace afesp {
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, STAGES = 4;
+constexpr int TILE_BYTES = BM * BK * 8;          // 8 KB per operand per stage
+constexpr int STAGE_BYTES = 2 * TILE_BYTES;
+constexpr int NCONS = 4;                         // consumer warps
+constexpr int NT = (NCONS + 1) * 32;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// byte offset of logical element (mn, k) inside a swizzled operand tile
+template <bool KMAJOR>
+__device__ __forceinline__ int tile_off(int mn, int k) {
+  if (KMAJOR) return mn * 128 + ((((k >> 1) ^ (mn & 7)) << 4) | ((k & 1) << 3));
+  return (mn >> 4) * 2048 + k * 128 + (((((mn & 15) >> 1) ^ (k & 7)) << 4) | ((mn & 1) << 3));
+}
+
+// k-index sets of the four DMMAs of one k-tile (see file header): {0,3,12,15} {1,2,13,14} {4,7,8,11} {5,6,9,10}
+__host__ __device__ constexpr int kslot(int s, int t) {
+  return ((s & 1) ? 1 + (t & 1) : 3 * (t & 1)) + ((t >> 1) ? (((s >> 1) ^ 1) * 4 + 8) : (s >> 1) * 4);
+}
+static_assert(kslot(0, 0) == 0 && kslot(0, 1) == 3 && kslot(0, 2) == 12 && kslot(0, 3) == 15, "k-set 0");
+static_assert(kslot(1, 0) == 1 && kslot(1, 1) == 2 && kslot(1, 2) == 13 && kslot(1, 3) == 14, "k-set 1");
+static_assert(kslot(2, 0) == 4 && kslot(2, 1) == 7 && kslot(2, 2) == 8 && kslot(2, 3) == 11, "k-set 2");
+static_assert(kslot(3, 0) == 5 && kslot(3, 1) == 6 && kslot(3, 2) == 9 && kslot(3, 3) == 10, "k-set 3");
+
+struct TmaParams {
+  double* C;
+  double* const* Cp;
+  long long sC, ldc;
+  const int* Aidx;   // per-batch block index into the A map's outermost dimension (null: batch index)
+  const int* Bidx;
+  int M, N, K, tiles_m;
+  double alpha, beta;
+  int cvec;
+};
+
+template <bool AK, bool BKM>
+__global__ void __launch_bounds__(NT, 3) gemm_f64_tma(const __grid_constant__ CUtensorMap tmA,
+                                                       const __grid_constant__ CUtensorMap tmB, const TmaParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle; the launch adds slack for the round-up
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + STAGES * STAGE_BYTES);
+  unsigned long long* empty = full + STAGES;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = (blockIdx.x % p.tiles_m) * BM, n0 = (blockIdx.x / p.tiles_m) * BN;
+  const int batch = blockIdx.z;
+  const int nk = (p.K + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NCONS) {
+    // ---------------- producer warp ----------------
+    if (lane == 0) {
+      const int ai = p.Aidx ? p.Aidx[batch] : batch;
+      const int bi = p.Bidx ? p.Bidx[batch] : batch;
+      for (int kt = 0; kt < nk; ++kt) {
+        const int s = kt % STAGES;
+        mbar_wait(&empty[s], ((kt / STAGES) & 1) ^ 1);   // first pass falls through (fresh barrier)
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        unsigned char* sa = smem + s * STAGE_BYTES;
+        unsigned char* sb = sa + TILE_BYTES;
+        const int k0 = kt * BK;
+        if (AK) tma_load_3d(sa, &tmA, &full[s], k0, m0, ai);
+        else tma_load_4d(sa, &tmA, &full[s], 0, k0, m0 >> 4, ai);
+        if (BKM) tma_load_3d(sb, &tmB, &full[s], k0, n0, bi);
+        else tma_load_4d(sb, &tmB, &full[s], 0, k0, n0 >> 4, bi);
+      }
+    }
+    return;
+  }
+  // ---------------- consumer warps ----------------
+  const int gid = lane >> 2, tig = lane & 3;
+  const int wm0 = (warp & 1) * 32, wn0 = (warp >> 1) * 32;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  // per-thread fragment offsets (bytes) for the four k-sets; tile rows advance by 8*i
+  int aoff[4][4], boff[4][4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int k = kslot(s, tig);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      aoff[s][i] = tile_off<AK>(wm0 + 8 * i + gid, k);
+      boff[s][i] = tile_off<BKM>(wn0 + 8 * i + gid, k);
+    }
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    const int s = kt % STAGES;
+    mbar_wait(&full[s], (kt / STAGES) & 1);
+    const unsigned char* sa = smem + s * STAGE_BYTES;
+    const unsigned char* sb = sa + TILE_BYTES;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = *reinterpret_cast<const double*>(sa + aoff[g][i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = *reinterpret_cast<const double*>(sb + boff[g][j]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  // ---------------- epilogue (same fragment ownership as gemm_f64_dmma) ----------------
+  double* C = p.Cp ? p.Cp[batch] : p.C + batch * p.sC;
+  const double alpha = p.alpha, beta = p.beta;
+  if (p.cvec) {
+    const bool odd = gid & 1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + wm0 + 8 * i + (gid & ~1);
+      double2 oldv[4];
+      if (beta != 0.0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = n0 + wn0 + 8 * j + 2 * tig + (odd ? 1 : 0);
+          oldv[j] = make_double2(0.0, 0.0);
+          if (n < p.N && m < p.M) {
+            const double* c = C + m + (long long)n * p.ldc;
+            if (m + 1 < p.M) oldv[j] = *reinterpret_cast<const double2*>(c);
+            else oldv[j].x = *c;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double send = odd ? acc[i][j][0] : acc[i][j][1];
+        const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
+        const double lo = odd ? recv : acc[i][j][0];
+        const double hi = odd ? acc[i][j][1] : recv;
+        const int n = n0 + wn0 + 8 * j + 2 * tig + (odd ? 1 : 0);
+        if (n < p.N && m < p.M) {
+          double* c = C + m + (long long)n * p.ldc;
+          double2 v = make_double2(alpha * lo, alpha * hi);
+          if (beta != 0.0) { v.x += beta * oldv[j].x; v.y += beta * oldv[j].y; }
+          if (m + 1 < p.M) *reinterpret_cast<double2*>(c) = v;
+          else *c = v.x;
+        }
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + wm0 + 8 * i + gid;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + wn0 + 8 * j + 2 * tig;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (n + e < p.N) {
+          double* c = C + m + (long long)(n + e) * p.ldc;
+          double v = alpha * acc[i][j][e];
+          if (beta != 0.0) v += beta * (*c);
+          *c = v;
+        }
+      }
+    }
+  }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn g_encode = nullptr;
+bool g_encode_tried = false;
+
+EncodeFn get_encode() {
+  if (!g_encode_tried) {
+    g_encode_tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<EncodeFn>(fn);
+    cudaGetLastError();
+  }
+  return g_encode;
+}
+
+// Tensor map of one operand: logical (MN x K), element (mn,k) at base[mn*smn + k*sk] with smn == 1 (MN-major, ld = sk)
+// or sk == 1 (K-major, ld = smn); nblk batches `bstride` elements apart.
+bool make_map(CUtensorMap* map, bool kmajor, const double* base, long long MN, long long K, long long ld, long long nblk,
+              long long bstride, int box_mn) {
+  EncodeFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
+  int rank;
+  if (kmajor) {
+    rank = 3;
+    dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)MN; dims[2] = (cuuint64_t)nblk;
+    strides[0] = (cuuint64_t)ld * 8; strides[1] = (cuuint64_t)(nblk > 1 ? bstride : ld * MN) * 8;
+    box[0] = BK; box[1] = box_mn; box[2] = 1;
+  } else {
+    rank = 4;
+    dims[0] = 16; dims[1] = (cuuint64_t)K; dims[2] = (cuuint64_t)((MN + 15) / 16); dims[3] = (cuuint64_t)nblk;
+    strides[0] = (cuuint64_t)ld * 8; strides[1] = 128; strides[2] = (cuuint64_t)(nblk > 1 ? bstride : ld * K) * 8;
+    box[0] = 16; box[1] = BK; box[2] = box_mn / 16; box[3] = 1;
+  }
+  for (int d = 0; d < rank - 1; ++d)
+    if (strides[d] % 16 != 0 || strides[d] == 0) return false;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, const_cast<double*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool g_use_tma = true;
+
+}  // namespace
+
+void gemm_tma_enable(bool on) { g_use_tma = on; }
+
+// Returns false when the TMA path does not apply (the caller then runs the cp.async kernel).
+bool dgemm_tma(cudaStream_t st, bool ak, bool bk, int M, int N, int K, double alpha, const double* A, long long lda,
+               const double* B, long long ldb, double beta, double* C, long long ldc, const GemmBatch* batch, int cvec) {
+  if (!g_use_tma || K < 1) return false;
+  const int nbatch = batch ? batch->count : 1;
+  const double* Abase = A;
+  const double* Bbase = B;
+  long long sA = 0, sB = 0, nA = 1, nB = 1;
+  const int *Aidx = nullptr, *Bidx = nullptr;
+  if (batch) {
+    if (batch->Aptr || batch->Bptr) {
+      if (!batch->Abase || !batch->Bbase || !batch->Aidx || !batch->Bidx) return false;  // gather form not provided
+      Abase = batch->Abase; Bbase = batch->Bbase;
+      sA = batch->Ablock; sB = batch->Bblock; nA = batch->Anblocks; nB = batch->Bnblocks;
+      Aidx = batch->Aidx; Bidx = batch->Bidx;
+    } else {
+      sA = batch->strideA; sB = batch->strideB; nA = nB = nbatch;
+      if (sA == 0) nA = 1;
+      if (sB == 0) nB = 1;
+      if ((sA == 0 || sB == 0) && nbatch > 1) return false;  // broadcast operands: keep the simple kernel
+    }
+  }
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al16(Abase) || !al16(Bbase) || (lda & 1) || (ldb & 1) || (sA & 1) || (sB & 1)) return false;
+  CUtensorMap tmA, tmB;
+  if (!make_map(&tmA, ak, Abase, M, K, lda, nA, sA, BM)) return false;
+  if (!make_map(&tmB, bk, Bbase, N, K, ldb, nB, sB, BN)) return false;
+  TmaParams p{};
+  p.C = C; p.Cp = batch ? batch->Cptr : nullptr; p.sC = batch ? batch->strideC : 0; p.ldc = ldc;
+  p.Aidx = Aidx; p.Bidx = Bidx; p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.cvec = cvec;
+  p.tiles_m = (M + BM - 1) / BM;
+  const long long tiles = (long long)p.tiles_m * ((N + BN - 1) / BN);
+  if (tiles >= (1LL << 31) || nbatch > 65535) return false;
+  constexpr size_t SMEM = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;
+  dim3 grid((unsigned)tiles, 1, nbatch);
+  // all four instantiations share one function-pointer type: raise their dynamic shared-memory limit together, once
+  static std::once_flag once;
+  std::call_once(once, [&] {
+    cudaFuncSetAttribute(gemm_f64_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    cudaFuncSetAttribute(gemm_f64_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    cudaFuncSetAttribute(gemm_f64_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    cudaFuncSetAttribute(gemm_f64_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+  });
+  auto launch = [&](auto kern) { kern<<<grid, NT, SMEM, st>>>(tmA, tmB, p); };
+  if (ak) { if (bk) launch(gemm_f64_tma<true, true>); else launch(gemm_f64_tma<true, false>); }
+  else    { if (bk) launch(gemm_f64_tma<false, true>); else launch(gemm_f64_tma<false, false>); }
+  count_launch();
+  AFESP_CUDA_CHECK(cudaGetLastError());
+  return true;
+}
+
+}  // namespace afesp
