@@ -21,6 +21,11 @@ struct NcclApi {
   int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*CommDestroy)(NcclComm) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool load(std::string& err) {
     if (lib) return true;
@@ -34,13 +39,34 @@ struct NcclApi {
     AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(lib, "ncclAllReduce");
     CommDestroy = (int (*)(NcclComm))dlsym(lib, "ncclCommDestroy");
     GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
-    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "NCCL symbols missing"; return false; }
+    Broadcast = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(lib, "ncclBroadcast");
+    Send = (int (*)(const void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(lib, "ncclSend");
+    Recv = (int (*)(void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(lib, "ncclRecv");
+    GroupStart = (int (*)())dlsym(lib, "ncclGroupStart");
+    GroupEnd = (int (*)())dlsym(lib, "ncclGroupEnd");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy || !Broadcast || !Send || !Recv || !GroupStart ||
+        !GroupEnd) {
+      err = "NCCL symbols missing";
+      return false;
+    }
     return true;
   }
 };
 NcclApi g_nccl;
 constexpr int kNcclDouble = 8;  // ncclFloat64
 constexpr int kNcclSum = 0;
+// adapters installed into Engine::dist (tensor.cuh): doubles only
+int dist_group_start() { return g_nccl.GroupStart(); }
+int dist_group_end() { return g_nccl.GroupEnd(); }
+int dist_bcast(const void* s, void* r, size_t n, int root, void* comm, cudaStream_t st) {
+  return g_nccl.Broadcast(s, r, n, kNcclDouble, root, comm, st);
+}
+int dist_send(const void* b, size_t n, int peer, void* comm, cudaStream_t st) {
+  return g_nccl.Send(b, n, kNcclDouble, peer, comm, st);
+}
+int dist_recv(void* b, size_t n, int peer, void* comm, cudaStream_t st) {
+  return g_nccl.Recv(b, n, kNcclDouble, peer, comm, st);
+}
 
 struct Handle {
   int device = 0;
@@ -180,6 +206,8 @@ int afesp_gpu_set_option(afesp_handle hv, const char* key, double value) {
     else if (k == "gemm_timing") gemm_timing_enable(value != 0.0);
     else if (k == "gemm_force_config") gemm_force_config((int)value);
     else if (k == "gemm_use_tma") gemm_tma_enable(value != 0.0);
+    else if (k == "dist_min_flops") h.s.eng.dist.min_flops = value;   // GEMMs below this stay replicated
+    else if (k == "dist_ccsd") h.s.eng.dist.enabled = value != 0.0;       // 0: replicate CCSD / AO->MO, shard only (T)
     else throw Error(1, "set_option: unknown key " + k);
   });
 }
@@ -421,6 +449,10 @@ int afesp_gpu_comm_init(afesp_handle hv, int rank, int nranks, const char id[128
     int rc = g_nccl.CommInitRank(&h.comm, nranks, nid, rank);
     if (rc != 0) throw Error(4, std::string("ncclCommInitRank failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
     h.rank = rank; h.nranks = nranks;
+    Dist& d = h.s.eng.dist;
+    d.rank = rank; d.nranks = nranks; d.comm = h.comm;
+    d.group_start = dist_group_start; d.group_end = dist_group_end;
+    d.bcast = dist_bcast; d.send = dist_send; d.recv = dist_recv;
   });
 }
 

@@ -68,6 +68,7 @@ struct CCState {
 
   bool finalized = false;
   bool have_cr = false;
+  bool vpm_sharded = false;  // V_plus / V_minus hold only this rank's column slab (ccsd_spatial_init)
 };
 
 // ---- spin-free (ccsd_spatial.cu)

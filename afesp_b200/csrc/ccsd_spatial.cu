@@ -52,15 +52,21 @@ void ccsd_spatial_init(CCState& s, int diis_n) {
   Tensor& A = s.make("A_oovv", {o, o, v, v});
   transpose(e, "ijab->ijba", -1.0, V(v_oovv), 0.0, V(A));
   axpby(e.stream, A.size(), 2.0, v_oovv.p(), 1.0, A.p());
-  // (+/-)-symmetrised <ef|ab> over virtual pairs for the ladder (replaces the dense v_vvvv slice of :512)
+  // (+/-)-symmetrised <ef|ab> over virtual pairs for the ladder (replaces the dense v_vvvv slice of :512).
+  // With several GPUs each rank builds and keeps only its column slab (ab in its range): W_abef-type memory and flop
+  // are divided by the number of ranks; the o^2 x P result slabs are exchanged over NVLink after the GEMM.
   {
     const long long Pp = (long long)v * (v + 1) / 2, Pm = (long long)v * (v - 1) / 2;
     AFESP_REQUIRE(Pp < (1LL << 31), "too many virtual pairs");
-    Tensor& Vp = s.make("V_plus", {(int)Pp, (int)Pp});
-    build_vpm(e, Vp.p(), s.eri_mo.p, o, v, +1);
+    const Dist& d = e.dist;
+    s.vpm_sharded = d.active() && Pm >= 64LL * d.nranks;
+    long long p0 = 0, p1 = Pp, m0 = 0, m1 = Pm;
+    if (s.vpm_sharded) { d.col_range(Pp, d.rank, &p0, &p1); d.col_range(Pm, d.rank, &m0, &m1); }
+    Tensor& Vp = s.make("V_plus", {(int)Pp, (int)std::max<long long>(p1 - p0, 1)});
+    build_vpm(e, Vp.p(), s.eri_mo.p, o, v, +1, p0, p1 - p0);
     if (Pm > 0) {
-      Tensor& Vm = s.make("V_minus", {(int)Pm, (int)Pm});
-      build_vpm(e, Vm.p(), s.eri_mo.p, o, v, -1);
+      Tensor& Vm = s.make("V_minus", {(int)Pm, (int)std::max<long long>(m1 - m0, 1)});
+      build_vpm(e, Vm.p(), s.eri_mo.p, o, v, -1, m0, m1 - m0);
     }
   }
 
@@ -173,8 +179,10 @@ void ccsd_spatial_iterate(CCState& s) {
     Scratch sS(e.pool, (size_t)(oo * Pp)), sA(e.pool, (size_t)std::max<long long>(oo * Pm, 1));
     Scratch sLp(e.pool, (size_t)(oo * Pp)), sLm(e.pool, (size_t)std::max<long long>(oo * Pm, 1));
     pack_c(e, sS.p, sA.p, c.p(), oo, v);
-    dgemm(st, 'N', 'N', oo, (int)Pp, (int)Pp, 1.0, sS.p, oo, s.get("V_plus").p(), Pp, 0.0, sLp.p, oo);
-    if (Pm > 0) dgemm(st, 'N', 'N', oo, (int)Pm, (int)Pm, 1.0, sA.p, oo, s.get("V_minus").p(), Pm, 0.0, sLm.p, oo);
+    const bool sh = s.vpm_sharded;   // V_plus / V_minus hold this rank's column slab only
+    dgemm_sharded(e, 'N', 'N', oo, (int)Pp, (int)Pp, 1.0, sS.p, oo, s.get("V_plus").p(), Pp, 0.0, sLp.p, sh, sh);
+    if (Pm > 0)
+      dgemm_sharded(e, 'N', 'N', oo, (int)Pm, (int)Pm, 1.0, sA.p, oo, s.get("V_minus").p(), Pm, 0.0, sLm.p, sh, sh);
     unpack_ladder(e, X.p(), sLp.p, sLm.p, oo, v, 0.5);
   }
   E("ijmn,mnab->ijab", 0.5, I_oooo, c, 1.0, X);           // :1673

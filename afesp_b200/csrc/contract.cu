@@ -8,6 +8,7 @@
 #include <cstring>
 #include <memory>
 
+#include "kernels.cuh"
 #include "tensor.cuh"
 
 namespace afesp {
@@ -48,6 +49,52 @@ void Pool::clear() {
   free_.clear();
   live_.clear();
   held_ = 0;
+}
+
+// ---------------------------------------------------------------- column-sharded GEMM over the ranks of one node
+void Dist::exchange(double* base, const std::vector<std::pair<long long, long long>>& ranges, cudaStream_t st) {
+  AFESP_REQUIRE(active() && (int)ranges.size() == nranks, "exchange: no communicator");
+  AFESP_REQUIRE(group_start() == 0, "ncclGroupStart failed");
+  for (int r = 0; r < nranks; ++r) {
+    const long long cnt = ranges[r].second - ranges[r].first;
+    if (cnt <= 0) continue;
+    double* q = base + ranges[r].first;
+    AFESP_REQUIRE(bcast(q, q, (size_t)cnt, r, comm, st) == 0, "ncclBroadcast failed");
+    if (r != rank) exchanged_bytes += 8.0 * cnt;
+  }
+  AFESP_REQUIRE(group_end() == 0, "ncclGroupEnd failed");
+}
+
+void dgemm_sharded(Engine& e, char ta, char tb, int M, int N, int K, double alpha, const double* A, long long lda,
+                   const double* B, long long ldb, double beta, double* C, bool b_local, bool force) {
+  Dist& d = e.dist;
+  const bool shard = d.active() && (force || (2.0 * M * (double)N * K >= d.min_flops && N >= 64LL * d.nranks));
+  if (!shard) {
+    AFESP_REQUIRE(!b_local, "dgemm_sharded: a local B slab needs the sharded path (communicator detached or disabled)");
+    dgemm(e.stream, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, M);
+    return;
+  }
+  long long c0, c1;
+  d.col_range(N, d.rank, &c0, &c1);
+  // beta != 0: the slabs are gathered in a scratch matrix and then folded into C (every rank applies the same update)
+  std::unique_ptr<Scratch> tmp;
+  double* out = C;
+  if (beta != 0.0) { tmp.reset(new Scratch(e.pool, (size_t)M * N)); out = tmp->p; }
+  if (c1 > c0) {
+    const bool tB = (tb == 'T' || tb == 't');
+    const double* Bs = b_local ? B : (tB ? B + c0 : B + c0 * ldb);
+    dgemm(e.stream, ta, tb, M, (int)(c1 - c0), K, alpha, A, lda, Bs, ldb, 0.0, out + c0 * M, M);
+  }
+  std::vector<std::pair<long long, long long>> ranges(d.nranks);
+  for (int r = 0; r < d.nranks; ++r) {
+    long long a, b;
+    d.col_range(N, r, &a, &b);
+    ranges[r] = {a * M, b * M};
+  }
+  d.exchange(out, ranges, e.stream);
+  if (beta != 0.0) {
+    axpby(e.stream, (long long)M * N, 1.0, out, beta, C);   // tmp returns to the pool: reuse is stream-ordered
+  }
 }
 
 // ---------------------------------------------------------------- helpers
@@ -197,10 +244,10 @@ void einsum(Engine& e, const char* spec, double alpha, const TView& A_, const TV
   if (ldb < 1) ldb = 1;
 
   if (direct) {
-    dgemm(e.stream, ta, tb, (int)M, (int)N, (int)Kd, alpha, pa, lda, pb, ldb, beta, C.p, M);
+    dgemm_sharded(e, ta, tb, (int)M, (int)N, (int)Kd, alpha, pa, lda, pb, ldb, beta, C.p);
   } else {
     sT.reset(new Scratch(e.pool, (size_t)(M * N)));
-    dgemm(e.stream, ta, tb, (int)M, (int)N, (int)Kd, alpha, pa, lda, pb, ldb, 0.0, sT->p, M);
+    dgemm_sharded(e, ta, tb, (int)M, (int)N, (int)Kd, alpha, pa, lda, pb, ldb, 0.0, sT->p);
     std::string st = Iord + Jord;
     std::vector<int> tdims;
     for (char c : st) tdims.push_back(ext[(unsigned char)c]);

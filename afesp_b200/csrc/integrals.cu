@@ -42,17 +42,19 @@ __global__ void k_unpack_pairs(double* __restrict__ X, const double* __restrict_
 
 // Variant for mode 1 that reads S coalesced along kl and writes X coalesced along xb (32x32 smem transpose over
 // (pair index, spectator)).  Grid: (ceil(npair/32), ceil(nb/32)).  Writes both X(xb,k,l) and X(xb,l,k).
+// Only pairs pr in [pr_lo, npair) are handled (grid.x covers that range): with several GPUs the rows of S arrive in
+// one chunk per source rank, each with its own base pointer and leading dimension.
 __global__ void k_unpack_pairs_T(double* __restrict__ X, const double* __restrict__ S, long long ld, long long x0,
-                                 int nb, int n, long long npair) {
+                                 int nb, int n, long long npair, long long pr_lo) {
   __shared__ double tile[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const long long pr0 = (long long)blockIdx.x * 32;
+  const long long pr0 = pr_lo + (long long)blockIdx.x * 32;
   const int xb0 = blockIdx.y * 32;
 #pragma unroll
   for (int r = ty; r < 32; r += 8) {
     long long pr = pr0 + tx;
     int xb = xb0 + r;
-    if (pr < npair && xb < nb) tile[r][tx] = S[pr + ld * (x0 + xb)];
+    if (pr < npair && xb < nb) tile[r][tx] = S[(pr - pr_lo) + ld * (x0 + xb)];
   }
   __syncthreads();
 #pragma unroll
@@ -73,10 +75,11 @@ __global__ void k_unpack_pairs_T(double* __restrict__ X, const double* __restric
 }
 
 // dest(x0+xb ; pair(r,s)) = Z(xb, r, s) for r >= s.
-// mode 0: dest is a full matrix D[x + ld * pair]   (phase 1: H(kl,pq), spectator = row, coalesced along xb)
+// mode 0: dest is a matrix D[(x - xoff) + ld * pair]   (phase 1: H(kl,pq), spectator = row, coalesced along xb;
+//         xoff = first spectator this rank owns)
 // mode 1: dest is the packed triangular array, only pair <= x is stored: D[tri(x, pair)]   (phase 2)
 __global__ void k_pack_pairs(double* __restrict__ D, const double* __restrict__ Z, int mode, long long ld, long long x0,
-                             int nb, int n) {
+                             int nb, int n, long long xoff) {
   const long long total = (long long)nb * n * n;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -85,7 +88,7 @@ __global__ void k_pack_pairs(double* __restrict__ D, const double* __restrict__ 
     int r = (int)(rs % n), s = (int)(rs / n);
     if (r < s) continue;
     long long pr = tri(r, s), x = x0 + xb;
-    if (mode == 0) D[x + ld * pr] = Z[idx];
+    if (mode == 0) D[(x - xoff) + ld * pr] = Z[idx];
     else if (pr <= x) D[x * (x + 1) / 2 + pr] = Z[idx];
   }
 }
@@ -155,12 +158,13 @@ __global__ void k_slice_spinorb(double* __restrict__ out, const double* __restri
 //   Vp(ef, ab) = <ef|ab> + <ef|ba>,  e<=f, a<=b   (P+ = v(v+1)/2 pairs, pair(a,b) = b(b+1)/2 + a)
 //   Vm(ef, ab) = <ef|ab> - <ef|ba>,  e<f,  a<b    (P- = v(v-1)/2 pairs, pair(a,b) = b(b-1)/2 + a)
 // <ef|ab> = (ea|fb), virtual indices offset by nocc in the packed MO array.
-__global__ void k_build_vpm(double* __restrict__ V, const double* __restrict__ g, int o, int v, int sign) {
+__global__ void k_build_vpm(double* __restrict__ V, const double* __restrict__ g, int o, int v, int sign,
+                            long long col0, long long ncols) {
   const long long P = sign > 0 ? (long long)v * (v + 1) / 2 : (long long)v * (v - 1) / 2;
-  const long long total = P * P;
+  const long long total = P * ncols;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    long long ef = idx % P, ab = idx / P;
+    long long ef = idx % P, ab = col0 + idx / P;
     long long f, e, b, a;
     if (sign > 0) {
       f = (long long)((sqrt(8.0 * (double)ef + 1.0) - 1.0) * 0.5);
@@ -232,30 +236,42 @@ __global__ void k_unpack_ladder(double* __restrict__ X, const double* __restrict
 
 inline int grid_for(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 16)); }
 
-// One half transform over spectator blocks (see file header).
-void half_transform(Engine& e, int n, const double* C, const double* src, int src_mode, long long src_ld, double* dst,
-                    int dst_mode, long long dst_ld, long long nspect, long long max_block_bytes) {
+// Rows [pr_lo, pr_hi) of the half-transformed matrix as they sit in memory: element (pr, x) at
+// p[(pr - pr_lo) + ld * (x - xoff)].  One chunk on a single GPU; one chunk per source rank after the exchange.
+struct HChunk { const double* p; long long ld, pr_lo, pr_hi, xoff; };
+
+// One half transform over the spectator range [xs0, xs1), in blocks (see file header).
+//   src_mode 0: packed triangular source src[tri(x, pair)];  src_mode 1: matrix chunks (spectator = column)
+//   dst_mode 0: matrix dst[(x - dst_xoff) + dst_ld * pair];  dst_mode 1: packed triangular dst[tri(x, pair)], pair <= x
+void half_transform(Engine& e, int n, const double* C, const double* src, int src_mode, const std::vector<HChunk>& chunks,
+                    double* dst, int dst_mode, long long dst_ld, long long dst_xoff, long long xs0, long long xs1,
+                    long long max_block_bytes) {
   const long long n2 = (long long)n * n;
-  const long long npair = (long long)n * (n + 1) / 2;
+  const long long nspect = xs1 - xs0;
+  if (nspect <= 0) return;
   long long nb = std::max<long long>(1, std::min<long long>(nspect, max_block_bytes / (3 * n2 * 8)));
   if (nb > 16) nb = nb / 16 * 16;
   Scratch X(e.pool, (size_t)(nb * n2)), Y(e.pool, (size_t)(nb * n2)), Z(e.pool, (size_t)(nb * n2));
-  for (long long x0 = 0; x0 < nspect; x0 += nb) {
-    const int cb = (int)std::min<long long>(nb, nspect - x0);
+  for (long long x0 = xs0; x0 < xs1; x0 += nb) {
+    const int cb = (int)std::min<long long>(nb, xs1 - x0);
     if (src_mode == 0) {
       k_unpack_pairs<<<grid_for((long long)cb * n2), 256, 0, e.stream>>>(X.p, src, 0, 0, x0, cb, n);
+      count_launch();
     } else {
-      dim3 grid((unsigned)((npair + 31) / 32), (unsigned)((cb + 31) / 32));
-      k_unpack_pairs_T<<<grid, dim3(32, 8), 0, e.stream>>>(X.p, src, src_ld, x0, cb, n, npair);
+      for (const HChunk& c : chunks) {
+        if (c.pr_hi <= c.pr_lo) continue;
+        dim3 grid((unsigned)((c.pr_hi - c.pr_lo + 31) / 32), (unsigned)((cb + 31) / 32));
+        k_unpack_pairs_T<<<grid, dim3(32, 8), 0, e.stream>>>(X.p, c.p, c.ld, x0 - c.xoff, cb, n, c.pr_hi, c.pr_lo);
+        count_launch();
+      }
     }
-    count_launch();
     // Y(xb,k,s) = sum_l X(xb,k,l) C(s,l):  (cb*n x n) = X (cb*n x n) * C^T
     dgemm(e.stream, 'N', 'T', cb * n, n, n, 1.0, X.p, (long long)cb * n, C, n, 0.0, Y.p, (long long)cb * n);
     // Z(xb,r,s) = sum_k Y(xb,k,s) C(r,k):  for each s, (cb x n) = Y_s (cb x n) * C^T
     GemmBatch bt;
     bt.count = n; bt.strideA = (long long)cb * n; bt.strideB = 0; bt.strideC = (long long)cb * n;
     dgemm(e.stream, 'N', 'T', cb, n, n, 1.0, Y.p, cb, C, n, 0.0, Z.p, cb, &bt);
-    k_pack_pairs<<<grid_for((long long)cb * n2), 256, 0, e.stream>>>(dst, Z.p, dst_mode, dst_ld, x0, cb, n);
+    k_pack_pairs<<<grid_for((long long)cb * n2), 256, 0, e.stream>>>(dst, Z.p, dst_mode, dst_ld, x0, cb, n, dst_xoff);
     count_launch();
     AFESP_CUDA_CHECK(cudaGetLastError());
   }
@@ -298,11 +314,48 @@ long long npacked_of(int n) { long long m = npair_of(n); return m * (m + 1) / 2;
 
 void ao2mo_packed(Engine& e, int n, const double* eri_ao, const double* C, double* eri_mo, long long block_bytes) {
   const long long npair = npair_of(n);
-  Scratch H(e.pool, (size_t)(npair * npair));
-  // phase 1: spectator = kl (AO pair), transform (ij) -> (pq): H(kl, pq), kl fastest
-  half_transform(e, n, C, eri_ao, 0, 0, H.p, 0, npair, npair, block_bytes);
-  // phase 2: spectator = pq (MO pair = column of H), transform (kl) -> (rs): eri_mo[tri(pq, rs)], rs <= pq
-  half_transform(e, n, C, H.p, 1, npair, eri_mo, 1, 0, npair, block_bytes);
+  Dist& d = e.dist;
+  if (!d.active() || npair < 64LL * d.nranks) {
+    Scratch H(e.pool, (size_t)(npair * npair));
+    // phase 1: spectator = kl (AO pair), transform (ij) -> (pq): H(kl, pq), kl fastest
+    half_transform(e, n, C, eri_ao, 0, {}, H.p, 0, npair, 0, 0, npair, block_bytes);
+    // phase 2: spectator = pq (MO pair = column of H), transform (kl) -> (rs): eri_mo[tri(pq, rs)], rs <= pq
+    half_transform(e, n, C, nullptr, 1, {HChunk{H.p, npair, 0, npair, 0}}, eri_mo, 1, 0, 0, 0, npair, block_bytes);
+    return;
+  }
+  // ---- several GPUs: phase 1 over this rank's kl spectators, all-to-all of the half-transformed blocks, phase 2 over
+  //      this rank's pq spectators, then every rank broadcasts its rows of the packed result.
+  const int R = d.nranks, me = d.rank;
+  std::vector<long long> lo(R), hi(R);
+  for (int r = 0; r < R; ++r) d.col_range(npair, r, &lo[r], &hi[r], 16);
+  const long long mine = hi[me] - lo[me];
+  Scratch Hloc(e.pool, (size_t)std::max<long long>(mine * npair, 1));   // H(kl in mine, all pq), ld = mine
+  half_transform(e, n, C, eri_ao, 0, {}, Hloc.p, 0, mine, lo[me], lo[me], hi[me], block_bytes);
+  Scratch Rcv(e.pool, (size_t)std::max<long long>(npair * mine, 1));    // chunk g: (hi[g]-lo[g]) x mine, kl fastest
+  std::vector<HChunk> chunks;
+  AFESP_REQUIRE(d.group_start() == 0, "ncclGroupStart failed");
+  for (int g = 0; g < R; ++g) {
+    const long long rows_g = hi[g] - lo[g];
+    double* slot = Rcv.p + lo[g] * mine;
+    chunks.push_back(HChunk{slot, rows_g, lo[g], hi[g], lo[me]});
+    if (g == me) {
+      if (mine > 0)
+        AFESP_CUDA_CHECK(cudaMemcpyAsync(slot, Hloc.p + mine * lo[me], (size_t)(mine * mine) * 8,
+                                         cudaMemcpyDeviceToDevice, e.stream));
+      continue;
+    }
+    if (mine > 0 && rows_g > 0) {
+      // my rows of the columns rank g owns: contiguous (mine x rows_g) block of Hloc
+      AFESP_REQUIRE(d.send(Hloc.p + mine * lo[g], (size_t)(mine * rows_g), g, d.comm, e.stream) == 0, "ncclSend failed");
+      AFESP_REQUIRE(d.recv(slot, (size_t)(rows_g * mine), g, d.comm, e.stream) == 0, "ncclRecv failed");
+      d.exchanged_bytes += 8.0 * rows_g * mine;
+    }
+  }
+  AFESP_REQUIRE(d.group_end() == 0, "ncclGroupEnd failed");
+  half_transform(e, n, C, nullptr, 1, chunks, eri_mo, 1, 0, 0, lo[me], hi[me], block_bytes);
+  std::vector<std::pair<long long, long long>> ranges(R);
+  for (int r = 0; r < R; ++r) ranges[r] = {lo[r] * (lo[r] + 1) / 2, hi[r] * (hi[r] + 1) / 2};
+  d.exchange(eri_mo, ranges, e.stream);
 }
 
 void mp2_energy(Engine& e, int n, int nocc, const double* eri_mo, const double* eps, double* out_dev) {
@@ -314,10 +367,11 @@ void mp2_energy(Engine& e, int n, int nocc, const double* eri_mo, const double* 
   finish_partials(e, part, nb, 1, out_dev);
 }
 
-void build_vpm(Engine& e, double* V, const double* eri_mo, int o, int v, int sign) {
+void build_vpm(Engine& e, double* V, const double* eri_mo, int o, int v, int sign, long long col0, long long ncols) {
   const long long P = sign > 0 ? (long long)v * (v + 1) / 2 : (long long)v * (v - 1) / 2;
-  if (P == 0) return;
-  k_build_vpm<<<grid_for(P * P), 256, 0, e.stream>>>(V, eri_mo, o, v, sign);
+  if (ncols < 0) ncols = P - col0;
+  if (P == 0 || ncols <= 0) return;
+  k_build_vpm<<<grid_for(P * ncols), 256, 0, e.stream>>>(V, eri_mo, o, v, sign, col0, ncols);
   count_launch();
 }
 

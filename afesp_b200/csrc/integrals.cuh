@@ -24,7 +24,10 @@ void slice_spinorb(Engine& e, double* out, const double* eri_mo, const int lo[4]
 
 // Particle-particle ladder in (+/-)-symmetrised virtual-pair form (half the flop and memory of the dense v^4 slice):
 //   sum_ef c(ij,ef) <ef|ab> = 1/2 [ S Vp + A Vm ](ij,ab),  S/A = symmetric/antisymmetric parts of c in (e,f)
-void build_vpm(Engine& e, double* V, const double* eri_mo, int o, int v, int sign);   // sign +1: Vp (P+ x P+), -1: Vm
+// sign +1: Vp (P+ x P+), -1: Vm (P- x P-); columns [col0, col0 + ncols) only (ncols < 0: through the last column) --
+// with several GPUs each rank keeps just the column slab of Vp / Vm its share of the ladder GEMM reads.
+void build_vpm(Engine& e, double* V, const double* eri_mo, int o, int v, int sign, long long col0 = 0,
+               long long ncols = -1);
 void pack_c(Engine& e, double* S, double* A, const double* c, int oo, int v);
 void unpack_ladder(Engine& e, double* X, const double* Lp, const double* Lm, int oo, int v, double alpha);
 

@@ -1,7 +1,9 @@
 // Device tensors, scratch pool and the einsum-style contraction front end used by the CC drivers.
 #pragma once
+#include <algorithm>
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -64,11 +66,44 @@ struct Scratch {  // RAII lease from the pool
   Scratch& operator=(const Scratch&) = delete;
 };
 
+// Multi-GPU context of one rank (one process per GPU).  The CCSD state is replicated; the heavy GEMMs are sharded over
+// output columns and the computed slabs are exchanged over NVLink with NCCL (installed by afesp_gpu_comm_init; the
+// function pointers keep NCCL behind dlopen in capi.cu).  Every rank ends each exchange with bit-identical data, so the
+// replicated state never diverges and the host-side convergence test gives the same answer on every rank.
+struct Dist {
+  int rank = 0, nranks = 1;
+  void* comm = nullptr;
+  int (*group_start)() = nullptr;
+  int (*group_end)() = nullptr;
+  int (*bcast)(const void* send, void* recv, size_t count, int root, void* comm, cudaStream_t st) = nullptr;  // doubles
+  int (*send)(const void* buf, size_t count, int peer, void* comm, cudaStream_t st) = nullptr;
+  int (*recv)(void* buf, size_t count, int peer, void* comm, cudaStream_t st) = nullptr;
+  double min_flops = 4e9;   // GEMMs below this stay replicated (exchange latency would dominate)
+  double exchanged_bytes = 0.0;  // bytes this rank received through slab exchanges (bench accounting)
+  bool enabled = true;           // option dist_ccsd: 0 keeps CCSD / AO->MO replicated (only (T) is partitioned)
+  bool active() const { return enabled && nranks > 1 && comm != nullptr; }
+  // contiguous column range [c0, c1) of `ncols` owned by rank r, in multiples of `gran` columns
+  void col_range(long long ncols, int r, long long* c0, long long* c1, long long gran = 64) const {
+    const long long units = (ncols + gran - 1) / gran;
+    const long long per = (units + nranks - 1) / nranks;
+    *c0 = std::min(ncols, per * r * gran);
+    *c1 = std::min(ncols, per * (r + 1) * gran);
+  }
+  // every rank broadcasts the element range it owns of a replicated array: ranges[r] = [begin, end) in doubles
+  void exchange(double* base, const std::vector<std::pair<long long, long long>>& ranges, cudaStream_t st);
+};
+
 struct Engine {
   cudaStream_t stream = nullptr;
   Pool pool;
   DBuf red;  // per-block partial sums of the deterministic reductions (kernels.cu)
+  Dist dist;
 };
+
+// dgemm with ldc == M whose output columns are sharded over the ranks of e.dist (falls back to a plain dgemm when the
+// context is inactive or the problem is small).  `b_local`: B already holds only this rank's column slab (tb = 'N').
+void dgemm_sharded(Engine& e, char ta, char tb, int M, int N, int K, double alpha, const double* A, long long lda,
+                   const double* B, long long ldb, double beta, double* C, bool b_local = false, bool force = false);
 
 // C[ic] = alpha * sum_k A[ia] * B[ib] + beta * C[ic]; spec "ia,ib->ic" with one letter per axis.
 // Every label appears in exactly two of the three tensors (no batch or trace labels).

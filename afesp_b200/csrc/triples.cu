@@ -415,7 +415,7 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
   // (the reference's reshapes at :2056-2066, re-aimed at GEMM blocks).  M3 uses I_ooov_pp / I_vovv_pp instead (:2188-2193).
   const int n = v + o;
   const size_t n_acat = (size_t)v * n * o * o, n_bcat = (size_t)n * v2 * o;
-  Scratch sAcat(e.pool, n_acat), sBcat(e.pool, n_bcat);
+  Scratch sAcat(e.pool, n_acat + 16), sBcat(e.pool, n_bcat + 16);  // +16: TMA boxes over-read the last 16-row chunk
   std::unique_ptr<Scratch> sAcatM, sBcatM;
   auto put = [&](const TView& in, const char* from, const char* to, double alpha, double* out, const long long* ostr) {
     int rank = (int)std::strlen(from), perm[4], dims[4];
@@ -432,7 +432,7 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
   put(s.get("v_vvov").view(), "zyrd", "dyzr", 1.0, sBcat.p, b_str);
   put(s.t2.view(), "lryz", "lyzr", 1.0, sBcat.p + v, b_str);
   if (do_m) {
-    sAcatM.reset(new Scratch(e.pool, n_acat)); sBcatM.reset(new Scratch(e.pool, n_bcat));
+    sAcatM.reset(new Scratch(e.pool, n_acat + 16)); sBcatM.reset(new Scratch(e.pool, n_bcat + 16));
     put(s.t2.view(), "pqxd", "xdpq", 1.0, sAcatM->p, a_str);
     put(s.get("I_ooov_pp").view(), "qplx", "xlpq", -1.0, sAcatM->p + (size_t)v * v, a_str);
     put(s.get("I_vovv_pp").view(), "dryz", "dyzr", 1.0, sBcatM->p, b_str);
@@ -459,7 +459,7 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
   AFESP_CUDA_CHECK(cudaMemcpyAsync(tiles_d.p, tiles_h.data(), tiles_h.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   Scratch descs(e.pool, (size_t)nb * 3);  // TripleDesc is 24 bytes = 3 doubles
   static_assert(sizeof(TripleDesc) == 24, "TripleDesc layout");
-  Scratch ptrs_raw(e.pool, (size_t)nb * 6 * 5);
+  Scratch ptrs_raw(e.pool, (size_t)nb * 6 * 5);   // 3 pointer arrays + 2 int32 block-index arrays (TMA gather form)
   struct { double* p; } ptrs_shim{ptrs_raw.p};
   const size_t nbatches = (tri.size() + nb - 1) / nb;
   Scratch batch_sums(e.pool, nbatches * 6);
@@ -485,13 +485,26 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
           hp[2 * ng + g] = out + (long long)g * v3;                            // C(x,(y,z))
         }
       }
+      std::vector<int> hidx((size_t)ng * 2);
+      for (int tb = 0; tb < cb; ++tb) {
+        const TripleDesc& td = tri[t0 + tb];
+        const int idx[3] = {td.i, td.j, td.k};
+        for (int t = 0; t < 6; ++t) {
+          hidx[tb * 6 + t] = idx[perm6[t][0]] + o * idx[perm6[t][1]];
+          hidx[(size_t)ng + tb * 6 + t] = idx[perm6[t][2]];
+        }
+      }
+      int* didx = reinterpret_cast<int*>(ptrs_shim.p + (size_t)ng * 3);
       AFESP_CUDA_CHECK(cudaMemcpyAsync(ptrs_shim.p, hp.data(), hp.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
+      AFESP_CUDA_CHECK(cudaMemcpyAsync(didx, hidx.data(), hidx.size() * sizeof(int), cudaMemcpyHostToDevice, st));
       AFESP_CUDA_CHECK(cudaStreamSynchronize(st));  // hp is a stack-scoped staging vector
       tr.lap(2);
       const double* const* dp = reinterpret_cast<const double* const*>(ptrs_shim.p);
       GemmBatch b1;
       b1.count = ng; b1.Aptr = dp + 0 * ng; b1.Bptr = dp + 1 * ng;
       b1.Cptr = (double* const*)(dp + 2 * ng); b1.ptr_aligned16 = al16;
+      b1.Abase = Acat; b1.Ablock = (long long)v * n; b1.Anblocks = (long long)o * o; b1.Aidx = didx;
+      b1.Bbase = Bcat; b1.Bblock = (long long)n * v2; b1.Bnblocks = o; b1.Bidx = didx + ng;
       dgemm(st, 'N', 'N', v, (int)v2, n, 1.0, nullptr, v, nullptr, n, 0.0, nullptr, v, &b1);
       tr.lap(4);
     };

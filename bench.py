@@ -290,7 +290,9 @@ def run_ours(args, rank, world, local):
             "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"synthetic integrals nbf={n} nocc={o} CCSD(T)_spatial", "nbf": n, "nocc": o,
-                       "calc_type": "CCSD(T)_spatial", "parallelism": f"(T) ijk round-robin x{world}, CCSD replicated",
+                       "calc_type": "CCSD(T)_spatial", "parallelism": (f"(T) ijk round-robin x{world}; CCSD GEMMs column-sharded x{world} with NCCL slab "
+                                       f"exchange, V+/- ladder integrals sharded by column block") if world > 1
+                       else "single GPU",
                        "l2": "inputs larger than L2 (packed ladder integrals %.1f GB, (T) work buffers %.1f GB)" % (
                            v ** 4 * 4 / 1e9, 6.0)},
             "ccsd_s_per_iter": (float(np.mean(comp["ccsd"])) + float(np.mean(comp["diis"]))) / 1e3,
