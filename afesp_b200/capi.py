@@ -34,6 +34,7 @@ SIGNATURES = {
     "afesp_gpu_comm_init": [_H, C.c_int, C.c_int, C.c_char_p],
     "afesp_gpu_set_partition": [_H, C.c_int, C.c_int],
     "afesp_gpu_triples_partition": [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)],
+    "afesp_gpu_column_partition": [C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)],
     "afesp_gpu_dgemm_wrapper": [_H, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double],
     "afesp_gpu_omp_reshape": [_H, _dp, _dp, _ip, C.c_char_p, C.c_int, C.c_double],
     "afesp_gpu_bench_dgemm": [_H, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, _dp],
@@ -253,6 +254,16 @@ class AfespGpu:
         if rc != 0:
             raise AfespError("triples_partition", rc, "bad arguments")
         return list(counts)
+
+    @staticmethod
+    def column_partition(ncols, nranks, granularity=64):
+        """[(lo, hi)] per rank: the column split of the sharded GEMMs (64) and of the AO->MO pair blocks (16)."""
+        lib = load_library()
+        lo, hi = (C.c_longlong * nranks)(), (C.c_longlong * nranks)()
+        rc = lib.afesp_gpu_column_partition(int(ncols), int(nranks), int(granularity), lo, hi)
+        if rc != 0:
+            raise AfespError("column_partition", rc, "bad arguments")
+        return list(zip(lo, hi))
 
     # -- linalg.fpp operators
     def dgemm_wrapper(self, transA, transB, M, N, K, A, B, Cmat=None, alpha=1.0, beta=0.0):

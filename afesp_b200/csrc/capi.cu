@@ -470,6 +470,14 @@ int afesp_gpu_triples_partition(int nocc_active, int symmetric, int strict, int 
   return 0;
 }
 
+int afesp_gpu_column_partition(long long ncols, int nranks, int granularity, long long* lo, long long* hi) {
+  if (ncols < 0 || nranks < 1 || granularity < 1 || !lo || !hi) return 1;
+  Dist d;
+  d.nranks = nranks;
+  for (int r = 0; r < nranks; ++r) d.col_range(ncols, r, &lo[r], &hi[r], granularity);
+  return 0;
+}
+
 int afesp_gpu_dgemm_wrapper(afesp_handle hv, char ta, char tb, int M, int N, int K, const double* A, const double* B,
                             double* C, double alpha, double beta) {
   return guarded(hv, [&](Handle& h) {

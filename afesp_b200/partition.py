@@ -26,3 +26,10 @@ def orbit(i: int, j: int, k: int):
     import itertools
 
     return sorted(set(itertools.permutations((i, j, k))))
+
+
+def column_range(ncols: int, rank: int, nranks: int, gran: int = 64):
+    """Mirror of Dist::col_range (afesp_b200/csrc/tensor.cuh): contiguous [lo, hi) in multiples of `gran` columns."""
+    units = (ncols + gran - 1) // gran
+    per = (units + nranks - 1) // nranks
+    return min(ncols, per * rank * gran), min(ncols, per * (rank + 1) * gran)

@@ -90,14 +90,23 @@ int afesp_gpu_ccsd_t_spatial(afesp_handle h, int paren, int renorm, int comp_ren
 /* e_T of src/ccsd.f90:1910 (host adds sys%e_ccsd). */
 int afesp_gpu_ccsd_t_spinorb(afesp_handle h, double* e_T);
 
-/* Multi-GPU: one process (or handle) per device; (T) triples are dealt round-robin over ranks and the six sums are
- * combined with one ncclAllReduce.  The 128-byte id comes from rank 0 and is broadcast by the host (MPI, torchrun...). */
+/* Multi-GPU: one process (or handle) per device.  (T) triples are dealt round-robin over ranks and the six sums are
+ * combined with one ncclAllReduce.  With a communicator attached the CCSD state stays replicated but the heavy GEMMs
+ * (ladder, rings, AO->MO half transforms) are sharded over output columns -- each rank keeps only its column slab of
+ * the (+/-)-symmetrised <ef|ab> ladder integrals -- and the computed slabs are exchanged over NVLink (grouped
+ * ncclBroadcast; ncclSend/ncclRecv all-to-all between the two AO->MO half transforms).  Every call that touches the
+ * communicator (ao2mo, ccsd_init, ccsd_iterate, ccsd_finalize, ccsd_t_*) is collective: all ranks make it with the
+ * same arguments.  Options: "dist_ccsd" (1/0, default 1) and "dist_min_flops" (GEMMs below stay replicated).
+ * The 128-byte id comes from rank 0 and is broadcast by the host (MPI, torchrun...). */
 int afesp_gpu_comm_unique_id(char id[128]);
 int afesp_gpu_comm_init(afesp_handle h, int rank, int nranks, const char id[128]);
 /* Without NCCL: give the handle a (rank, nranks) share only; the caller sums the partial results itself. */
 int afesp_gpu_set_partition(afesp_handle h, int rank, int nranks);
 /* Host-only: number of (i,j,k) work units per rank (no device needed). */
 int afesp_gpu_triples_partition(int nocc_active, int symmetric, int strict, int nranks, long long* counts);
+/* Host-only: contiguous column range [lo[r], hi[r]) of `ncols` columns owned by rank r (multiples of `granularity`),
+ * the split used by the sharded GEMMs (granularity 64) and the AO->MO pair blocks (granularity 16). */
+int afesp_gpu_column_partition(long long ncols, int nranks, int granularity, long long* lo, long long* hi);
 
 /* Operators of src/linalg.fpp on host arrays (used by the parity tests; the CC drivers call the same kernels) ---- */
 /* dgemm_wrapper (src/linalg.fpp:58-89): C(MxN) = alpha*op(A)(MxK)*op(B)(KxN) + beta*C, leading dimensions inferred
