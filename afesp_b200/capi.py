@@ -40,7 +40,9 @@ SIGNATURES = {
     "afesp_gpu_bench_dgemm": [_H, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, _dp],
     "afesp_gpu_dmma_peak": [_H, _dp],
     "afesp_gpu_last_stage_ms": [_H, _dp],
+    "afesp_gpu_timer": [_H, C.c_int, _dp],
     "afesp_gpu_gemm_time": [_H, _dp, _dp],
+    "afesp_gpu_gemm_stats": [_H, _dp, _dp, C.POINTER(C.c_longlong)],
 }
 
 _lib = None
@@ -300,6 +302,21 @@ class AfespGpu:
         ms, fl = C.c_double(0), C.c_double(0)
         self._check("gemm_time", self.lib.afesp_gpu_gemm_time(self.h, C.byref(ms), C.byref(fl)))
         return ms.value, fl.value
+
+    def timer_start(self):
+        self._check("timer", self.lib.afesp_gpu_timer(self.h, 0, None))
+
+    def timer_stop(self):
+        """Device milliseconds on the engine's stream since timer_start()."""
+        ms = C.c_double(0)
+        self._check("timer", self.lib.afesp_gpu_timer(self.h, 1, C.byref(ms)))
+        return ms.value
+
+    def gemm_stats(self):
+        """(milliseconds, executed flop, launches) of the DMMA GEMM launches since gemm_timing was set / last call."""
+        ms, fl, nl = C.c_double(0), C.c_double(0), C.c_longlong(0)
+        self._check("gemm_stats", self.lib.afesp_gpu_gemm_stats(self.h, C.byref(ms), C.byref(fl), C.byref(nl)))
+        return ms.value, fl.value, nl.value
 
     def dmma_peak(self):
         t = C.c_double(0)

@@ -77,12 +77,19 @@ struct Handle {
   int rank = 0, nranks = 1;
   NcclComm comm = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t tm0 = nullptr, tm1 = nullptr;  // afesp_gpu_timer
   double last_ms = 0.0;
   long long launches0 = 0;
   double flops0 = 0.0;
 };
 
 std::string g_open_error;
+
+// Cached free blocks go back to the driver only when they add up to a sizeable part of the HBM (large shapes, where
+// the next stage needs the room); small runs keep them so repeated init/finalize cycles never touch cudaMalloc.
+void trim_if_large(size_t threshold = (size_t)48 << 30) {
+  if (device_cached_bytes() > threshold) device_trim();
+}
 
 struct StageTimer {  // device time of one API stage, on the stream the kernels run on
   Handle* h;
@@ -181,9 +188,12 @@ int afesp_gpu_close(afesp_handle hv) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->tm0) cudaEventDestroy(h->tm0);
+  if (h->tm1) cudaEventDestroy(h->tm1);
   cudaStream_t st = h->s.eng.stream;
   delete h;
   if (st) cudaStreamDestroy(st);
+  device_trim();
   return 0;
 }
 
@@ -239,7 +249,7 @@ int afesp_gpu_ao2mo(afesp_handle hv, int n, const double* eri_ao, const double* 
     StageTimer tm(&h);
     ao2mo_packed(h.s.eng, n, h.eri_ao.p, h.coeff.p, h.s.eri_mo.p);
     tm.stop();
-    h.s.eng.pool.clear();  // the npair^2 half-transformed matrix goes back to the driver
+    trim_if_large();  // the npair^2 half-transformed matrix goes back to the driver when it is big
     if (eri_mo) {
       AFESP_CUDA_CHECK(cudaMemcpyAsync(eri_mo, h.s.eri_mo.p, np * 8, cudaMemcpyDeviceToHost, st));
       AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -261,7 +271,7 @@ int afesp_gpu_synth_eri_ao(afesp_handle hv, int n, int naux, const double* facto
     synth_eri_from_factors(h.s.eng, n, naux, B.p, h.eri_ao.p);
     tm.stop();
     h.n_ao = n;
-    h.s.eng.pool.clear();
+    trim_if_large();
   });
 }
 
@@ -324,7 +334,13 @@ int afesp_gpu_ccsd_init(afesp_handle hv, int nocc, int restricted, const double*
     AFESP_REQUIRE(nocc > 0 && nocc < h.s.n, "ccsd_init: bad nocc");
     upload_eps(h, eps);
     h.s.nocc_spatial = nocc;
-    h.s.T.clear();
+    {
+      Trace tr(h.s.eng.stream);
+      h.s.T.clear();
+      tr.lap(0);
+      const char* names[] = {"init free old"};
+      tr.report(names, 1);
+    }
     StageTimer tm(&h);
     if (restricted) ccsd_spatial_init(h.s, diis_n);
     else ccsd_spinorb_init(h.s, diis_n);
@@ -384,7 +400,7 @@ int afesp_gpu_ccsd_finalize(afesp_handle hv, int want_cr, double* t1_diag, doubl
                            "x_voov", "c_oovv", "A_oovv", "W_ijmn", "W_ovvo", "tau", "tau_tilde"})
       s.drop(nm);
     s.t1n.free(); s.t2n.free(); s.t2_old.free();
-    s.eng.pool.clear();
+    trim_if_large();
     s.finalized = true;
     tm.stop();
     if (t1) AFESP_CUDA_CHECK(cudaMemcpy(t1, s.t1.p(), s.t1.size() * 8, cudaMemcpyDeviceToHost));
@@ -570,6 +586,31 @@ int afesp_gpu_gemm_time(afesp_handle hv, double* ms, double* flops) {
     AFESP_REQUIRE(ms && flops, "gemm_time: null output");
     AFESP_CUDA_CHECK(cudaStreamSynchronize(h.s.eng.stream));
     *ms = gemm_timing_collect(flops);
+  });
+}
+
+int afesp_gpu_gemm_stats(afesp_handle hv, double* ms, double* flops, long long* launches) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(ms && flops && launches, "gemm_stats: null output");
+    AFESP_CUDA_CHECK(cudaStreamSynchronize(h.s.eng.stream));
+    *ms = gemm_timing_collect(flops, launches);
+  });
+}
+
+int afesp_gpu_timer(afesp_handle hv, int stop, double* ms) {
+  return guarded(hv, [&](Handle& h) {
+    if (!h.tm0) { AFESP_CUDA_CHECK(cudaEventCreate(&h.tm0)); AFESP_CUDA_CHECK(cudaEventCreate(&h.tm1)); }
+    cudaStream_t st = h.s.eng.stream;
+    if (!stop) {
+      AFESP_CUDA_CHECK(cudaEventRecord(h.tm0, st));
+      return;
+    }
+    AFESP_REQUIRE(ms != nullptr, "timer: null output");
+    AFESP_CUDA_CHECK(cudaEventRecord(h.tm1, st));
+    AFESP_CUDA_CHECK(cudaEventSynchronize(h.tm1));
+    float t = 0.f;
+    AFESP_CUDA_CHECK(cudaEventElapsedTime(&t, h.tm0, h.tm1));
+    *ms = t;
   });
 }
 

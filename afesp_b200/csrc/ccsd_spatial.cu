@@ -29,6 +29,7 @@ void ccsd_spatial_init(CCState& s, int diis_n) {
   s.o = o; s.v = v;
   AFESP_REQUIRE(o > 0 && v > 0, "ccsd init: need at least one occupied and one virtual orbital");
   Engine& e = s.eng;
+  Trace tr(e.stream);
   s.eo.init({o}); s.ev.init({v});
   AFESP_CUDA_CHECK(cudaMemcpyAsync(s.eo.p(), s.eps.p, o * 8, cudaMemcpyDeviceToDevice, e.stream));
   AFESP_CUDA_CHECK(cudaMemcpyAsync(s.ev.p(), s.eps.p + o, v * 8, cudaMemcpyDeviceToDevice, e.stream));
@@ -47,6 +48,7 @@ void ccsd_spatial_init(CCState& s, int diis_n) {
     Tensor& t = s.make(x.name, dims);
     slice_phys(e, t.p(), s.eri_mo.p, lo, cnt);
   }
+  tr.lap(0);
   Tensor& v_oovv = s.get("v_oovv");
   // A_oovv(i,j,a,b) = 2 v_oovv(i,j,a,b) - v_oovv(i,j,b,a)      (antisymmetrise '1243', :1089)
   Tensor& A = s.make("A_oovv", {o, o, v, v});
@@ -70,6 +72,7 @@ void ccsd_spatial_init(CCState& s, int diis_n) {
     }
   }
 
+  tr.lap(1);
   s.t1.init({o, v}); s.t1n.init({o, v});
   s.t2.init({o, o, v, v}); s.t2n.init({o, o, v, v}); s.t2_old.init({o, o, v, v});
   fill(e.stream, s.t1.size(), 0.0, s.t1.p());
@@ -80,10 +83,16 @@ void ccsd_spatial_init(CCState& s, int diis_n) {
   s.make("c_oovv", {o, o, v, v}); s.make("asym_t2", {o, o, v, v});
   s.make("x_voov", {v, o, o, v}); s.make("I_oooo", {o, o, o, o}); s.make("I_ovov", {o, v, o, v});
   s.make("I_voov", {v, o, o, v}); s.make("I_ooov_p", {o, o, o, v});
+  tr.lap(2);
   s.diis.init(diis_n, o, v);
   s.energy = s.energy_old = 0.0;
   s.iterations = 0;
   s.finalized = false; s.have_cr = false;
+  tr.lap(3);
+  {
+    const char* names[] = {"init slices", "init V+/-", "init amps", "init diis"};
+    tr.report(names, 4);
+  }
 }
 
 void ccsd_spatial_iterate(CCState& s) {
@@ -230,13 +239,10 @@ void ccsd_spatial_cr_intermediates(CCState& s) {
   Tensor &t1 = s.t1, &t2 = s.t2;
   Tensor &v_oovv = s.get("v_oovv"), &v_ovov = s.get("v_ovov"), &v_vvov = s.get("v_vvov"), &v_oovo = s.get("v_oovo"),
          &v_oooo = s.get("v_oooo");
-  // the CR intermediates need the dense <ab|cd> slice once (v_vvvv . t1, :2515); built here, dropped at the end
-  s.drop("V_plus"); s.drop("V_minus");
-  Tensor& v_vvvv = s.make("v_vvvv", {v, v, v, v});
-  {
-    const int lo4[4] = {o, o, o, o}, cnt4[4] = {v, v, v, v};
-    slice_phys(e, v_vvvv.p(), s.eri_mo.p, lo4, cnt4);
-  }
+  // The CR intermediates need <ec|ba> t1(i,e) once (:2515).  The dense v^4 slice (134 GB at nbf=400) is never formed:
+  // the term is accumulated below from slabs over the last virtual index, gathered from the packed MO integrals.
+  AFESP_REQUIRE(s.eri_mo.p != nullptr, "CR intermediates need the packed MO integrals on the device");
+  s.drop("V_plus"); s.drop("V_minus");   // the iterations are over: make room (67 GB at nbf=400)
   Tensor &I_vo = s.get("I_vo"), &asym = s.get("asym_t2");
   if (!s.opt.q3b_stale_intermediates) {
     transpose(e, "ijab->jiab", -1.0, V(t2), 0.0, V(asym));
@@ -278,9 +284,23 @@ void ccsd_spatial_cr_intermediates(CCState& s) {
   // I_vovv_pp(c,i,a,b)                                                                     (:2509-2525)
   Tensor& Ivv = s.make("I_vovv_pp", {v, o, v, v});
   transpose(e, "baic->ciab", 1.0, V(v_vvov), 0.0, V(Ivv));
-  E("ecba,ie->ciab", 1.0, V(v_vvvv), V(t1), 1.0, V(Ivv));
-  AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
-  s.drop("v_vvvv");
+  {
+    // Ivv(c,i,a,b) += sum_e <ec|ba> t1(i,e), slab by slab over a:  Y(i; c,b,a') = t1(i,e) <ec|b a0+a'>  (one GEMM on
+    // the gathered slab in place), then a strided permute-add into Ivv(c,i,a0+a',b).
+    const long long v3 = (long long)v * v * v;
+    const int nb = (int)std::max<long long>(1, std::min<long long>(v, (4LL << 30) / (v3 * 8)));
+    Scratch slab(e.pool, (size_t)(v3 * nb)), y(e.pool, (size_t)((long long)o * v * v * nb));
+    const long long ostr[4] = {1, v, (long long)v * o * v, (long long)v * o};   // out axes (c, i, b, a') inside Ivv
+    for (int a0 = 0; a0 < v; a0 += nb) {
+      const int cb = std::min(nb, v - a0);
+      const int lo4[4] = {o, o, o, o + a0}, cnt4[4] = {v, v, v, cb};
+      slice_phys(e, slab.p, s.eri_mo.p, lo4, cnt4);                       // slab(e,c,b,a')
+      TView SL(slab.p, {v, v, v, cb}), Y(y.p, {o, v, v, cb});
+      einsum(e, "ie,ecba->icba", 1.0, V(t1), SL, 0.0, Y);
+      const int dims[4] = {o, v, v, cb}, perm[4] = {1, 0, 2, 3};           // Y(i,c,b,a') -> (c,i,b,a')
+      permute_strided(st, 4, dims, perm, 1.0, y.p, 1.0, Ivv.p() + (long long)a0 * v * o, ostr);
+    }
+  }
   E("icma,mb->ciab", -1.0, V(x_ovov_p), V(t1), 1.0, V(Ivv));
   E("ma,cimb->ciab", -1.0, V(t1), V(x_voov_p), 1.0, V(Ivv));
   E("cm,miab->ciab", -1.0, V(I_vo), V(t2), 1.0, V(Ivv));

@@ -34,6 +34,17 @@ struct Error : std::runtime_error {
 extern long long g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count += n; }
 
+// ---- caching device allocator (contract.cu) ----
+// cudaMalloc / cudaFree synchronise the device and cost up to ~1 s per call pattern once tens of GB are mapped, so
+// every device block (named tensors and scratch alike) comes from a per-device size-bucketed cache: a freed block is
+// kept and handed to the next request of a similar size.  All work of a handle is issued on one stream, so reuse is
+// stream-ordered.  device_trim() returns the cached free blocks to the driver (phase boundaries of large runs; it is
+// also what an allocation failure does before retrying).
+double* device_alloc(size_t count);
+void device_free(double* p);
+void device_trim();
+size_t device_cached_bytes();
+
 // ---- device buffer with ownership ----
 struct DBuf {
   double* p = nullptr;
@@ -51,10 +62,10 @@ struct DBuf {
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) AFESP_CUDA_CHECK(cudaMalloc(&p, count * sizeof(double)));
+    if (count) p = device_alloc(count);
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) device_free(p);
     p = nullptr; n = 0;
   }
 };
@@ -87,7 +98,7 @@ void gemm_force_config(int cfg);  // tuning aid: -1 = automatic tile selection
 void gemm_tma_enable(bool on);     // TMA-staged operand path for aligned problems (default on)
 bool dgemm_tma(cudaStream_t st, bool ak, bool bk, int M, int N, int K, double alpha, const double* A, long long lda,
                const double* B, long long ldb, double beta, double* C, long long ldc, const GemmBatch* batch, int cvec);
-double gemm_timing_collect(double* flops_out);
+double gemm_timing_collect(double* flops_out, long long* launches_out = nullptr);
 
 // ---- permute (permute.cu): out = alpha * permute(in) + beta * out for rank <= 6 ----
 // perm[d] = which input axis becomes output axis d (numpy transpose convention), dims = input extents,

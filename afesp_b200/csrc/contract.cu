@@ -6,49 +6,96 @@
 // ladder c(ij,ef)*v(ef,ab) runs with no data movement besides the GEMM itself.
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 
 #include "kernels.cuh"
 #include "tensor.cuh"
 
 namespace afesp {
 
-// ---------------------------------------------------------------- Pool
-double* Pool::get(size_t n) {
+// ---------------------------------------------------------------- caching device allocator
+namespace {
+struct DeviceCache {
+  std::multimap<size_t, double*> free_;   // size (doubles) -> block
+  std::map<double*, size_t> live_;
+  size_t cached_ = 0;                     // bytes sitting in free_
+  void trim() {
+    for (auto& kv : free_) cudaFree(kv.second);
+    free_.clear();
+    cached_ = 0;
+  }
+};
+// Leaked singletons: buffers with static storage in other translation units (split-K workspace, pointer tables) are
+// released during static destruction and must still find the cache alive.
+std::mutex& g_cache_mu = *new std::mutex;
+std::map<int, DeviceCache>& g_cache = *new std::map<int, DeviceCache>;   // one cache per device ordinal
+DeviceCache& cache_here() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return g_cache[dev];
+}
+}  // namespace
+
+double* device_alloc(size_t n) {
   if (n == 0) n = 1;
-  auto it = free_.lower_bound(n);
-  if (it != free_.end() && it->first <= 2 * n + 1024) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  DeviceCache& c = cache_here();
+  // reuse a cached block that is not much larger than the request (big blocks: <= 1.25x, small ones: <= 2x)
+  auto it = c.free_.lower_bound(n);
+  const size_t limit = n >= (8u << 20) ? n + n / 4 : 2 * n + 1024;
+  if (it != c.free_.end() && it->first <= limit) {
     double* p = it->second;
-    live_[p] = it->first;
-    free_.erase(it);
+    c.live_[p] = it->first;
+    c.cached_ -= it->first * sizeof(double);
+    c.free_.erase(it);
     return p;
   }
   double* p = nullptr;
   cudaError_t err = cudaMalloc(&p, n * sizeof(double));
   if (err != cudaSuccess) {
     cudaGetLastError();
-    for (auto& kv : free_) { cudaFree(kv.second); held_ -= kv.first * sizeof(double); }
-    free_.clear();
+    c.trim();
     AFESP_CUDA_CHECK(cudaMalloc(&p, n * sizeof(double)));
   }
-  held_ += n * sizeof(double);
-  live_[p] = n;
+  c.live_[p] = n;
   return p;
 }
 
-void Pool::put(double* p) {
-  auto it = live_.find(p);
-  if (it == live_.end()) return;
-  free_.emplace(it->second, p);
-  live_.erase(it);
+void device_free(double* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  DeviceCache& c = cache_here();
+  auto it = c.live_.find(p);
+  if (it == c.live_.end()) {
+    // allocated while another device was current: search the other caches
+    for (auto& kv : g_cache) {
+      auto jt = kv.second.live_.find(p);
+      if (jt != kv.second.live_.end()) {
+        kv.second.free_.emplace(jt->second, p);
+        kv.second.cached_ += jt->second * sizeof(double);
+        kv.second.live_.erase(jt);
+        return;
+      }
+    }
+    cudaFree(p);
+    return;
+  }
+  c.free_.emplace(it->second, p);
+  c.cached_ += it->second * sizeof(double);
+  c.live_.erase(it);
 }
 
-void Pool::clear() {
-  for (auto& kv : free_) cudaFree(kv.second);
-  for (auto& kv : live_) cudaFree(kv.first);
-  free_.clear();
-  live_.clear();
-  held_ = 0;
+void device_trim() {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  cudaDeviceSynchronize();
+  cache_here().trim();
+}
+
+size_t device_cached_bytes() {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  return cache_here().cached_;
 }
 
 // ---------------------------------------------------------------- column-sharded GEMM over the ranks of one node

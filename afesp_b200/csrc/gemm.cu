@@ -281,6 +281,7 @@ bool g_timing = false;
 std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_ev_pool;
 size_t g_ev_used = 0;
 double g_timed_ms = 0.0, g_timed_flops = 0.0;
+long long g_timed_launches = 0;
 double drain_events() {
   double ms = 0.0;
   for (size_t i = 0; i < g_ev_used; ++i) {
@@ -454,7 +455,7 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
     }
   }
   std::pair<cudaEvent_t, cudaEvent_t>* evs = g_timing ? next_events() : nullptr;
-  if (evs) { cudaEventRecord(evs->first, st); g_timed_flops += 2.0 * M * N * (double)K * nbatch; }
+  if (evs) { cudaEventRecord(evs->first, st); g_timed_flops += 2.0 * M * N * (double)K * nbatch; g_timed_launches += 1; }
   // aligned problems on the 64x64 tile go through the TMA-staged kernel (gemm_tma.cu); everything else through cp.async
   bool used_tma = false;
   if (cfg == 3 && p.splitk == 1 && vec2)
@@ -473,15 +474,16 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
 void gemm_force_config(int cfg) { g_force_cfg = cfg; }
 
 void gemm_timing_enable(bool on) {
-  if (on && !g_timing) { g_timed_ms = 0.0; g_timed_flops = 0.0; g_ev_used = 0; }
+  if (on && !g_timing) { g_timed_ms = 0.0; g_timed_flops = 0.0; g_timed_launches = 0; g_ev_used = 0; }
   g_timing = on;
 }
 
-double gemm_timing_collect(double* flops_out) {
+double gemm_timing_collect(double* flops_out, long long* launches_out) {
   g_timed_ms += drain_events();
   double ms = g_timed_ms;
   if (flops_out) *flops_out = g_timed_flops;
-  g_timed_ms = 0.0; g_timed_flops = 0.0;
+  if (launches_out) *launches_out = g_timed_launches;
+  g_timed_ms = 0.0; g_timed_flops = 0.0; g_timed_launches = 0;
   return ms;
 }
 

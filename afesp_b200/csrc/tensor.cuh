@@ -1,6 +1,8 @@
 // Device tensors, scratch pool and the einsum-style contraction front end used by the CC drivers.
 #pragma once
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <utility>
@@ -42,19 +44,13 @@ struct Tensor {
   operator TView() const { return view(); }
 };
 
-// Size-bucketed cache of device scratch blocks (cudaMalloc/cudaFree synchronise; the CC loop reuses blocks).
+// Scratch leases of the engine: a thin front over the caching device allocator (common.cuh).
 class Pool {
  public:
-  ~Pool() { clear(); }
-  double* get(size_t n);
-  void put(double* p);
-  void clear();
-  size_t bytes_held() const { return held_; }
-
- private:
-  std::multimap<size_t, double*> free_;
-  std::map<double*, size_t> live_;
-  size_t held_ = 0;
+  double* get(size_t n) { return device_alloc(n == 0 ? 1 : n); }
+  void put(double* p) { device_free(p); }
+  void clear() { device_trim(); }   // give the cached free blocks back to the driver (phase boundaries of large runs)
+  size_t bytes_held() const { return device_cached_bytes(); }
 };
 
 struct Scratch {  // RAII lease from the pool
@@ -98,6 +94,26 @@ struct Engine {
   Pool pool;
   DBuf red;  // per-block partial sums of the deterministic reductions (kernels.cu)
   Dist dist;
+};
+
+// Wall-clock stage tracer (environment AFESP_TRACE=1 -> stderr); off by default: no synchronisation, no output.
+struct Trace {
+  bool on;
+  cudaStream_t st;
+  std::chrono::steady_clock::time_point t0;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  explicit Trace(cudaStream_t s) : on(std::getenv("AFESP_TRACE") != nullptr), st(s) { t0 = std::chrono::steady_clock::now(); }
+  void lap(int k) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    auto t1 = std::chrono::steady_clock::now();
+    acc[k] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    t0 = t1;
+  }
+  void report(const char* names[], int n) {
+    if (!on) return;
+    for (int k = 0; k < n; ++k) std::fprintf(stderr, "[afesp trace] %-14s %10.3f ms\n", names[k], acc[k]);
+  }
 };
 
 // dgemm with ldc == M whose output columns are sharded over the ranks of e.dist (falls back to a plain dgemm when the

@@ -347,26 +347,6 @@ std::vector<TripleDesc> my_triples(int o, bool symmetric, bool strict, int rank,
 
 static_assert(sizeof(double) == sizeof(void*), "pointer arrays are carried in double buffers");
 
-// Developer trace (AFESP_TRACE=1): host wall-clock of the phases of one (T) call, stream-synchronised. Off by default
-// (the library prints nothing in normal operation).
-struct Trace {
-  bool on;
-  cudaStream_t st;
-  std::chrono::steady_clock::time_point t0;
-  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  explicit Trace(cudaStream_t s) : on(std::getenv("AFESP_TRACE") != nullptr), st(s) { t0 = std::chrono::steady_clock::now(); }
-  void lap(int k) {
-    if (!on) return;
-    cudaStreamSynchronize(st);
-    auto t1 = std::chrono::steady_clock::now();
-    acc[k] += std::chrono::duration<double, std::milli>(t1 - t0).count();
-    t0 = t1;
-  }
-  void report(const char* names[], int n) {
-    if (!on) return;
-    for (int k = 0; k < n; ++k) std::fprintf(stderr, "[afesp trace] %-14s %10.3f ms\n", names[k], acc[k]);
-  }
-};
 
 }  // namespace
 

@@ -211,6 +211,7 @@ def run_ours(args, rank, world, local):
     if big:
         gpu.release("eri_mo")
     comp = {"ccsd": [], "diis": [], "t": []}
+    gstat = {"ccsd": [0.0, 0.0, 0], "t": [0.0, 0.0, 0]}   # DMMA GEMM (ms, flop, launches) per stage of the timed region
     last = {}
 
     def step(record):
@@ -219,8 +220,14 @@ def run_ours(args, rank, world, local):
         gpu.ccsd_diis()
         b = gpu.last_stage_ms()
         gpu.ccsd_finalize()
+        if record:
+            ms, fl, nl = gpu.gemm_stats()
+            gstat["ccsd"][0] += ms; gstat["ccsd"][1] += fl; gstat["ccsd"][2] += nl
         sums, _ = gpu.ccsd_t_spatial(True, False, False)
         c = gpu.last_stage_ms()
+        if record:
+            ms, fl, nl = gpu.gemm_stats()
+            gstat["t"][0] += ms; gstat["t"][1] += fl; gstat["t"][2] += nl
         last.update(e_ccsd=e, rms=rms, e_T=float(sums[0]))
         if record:
             comp["ccsd"].append(a); comp["diis"].append(b); comp["t"].append(c)
@@ -231,36 +238,50 @@ def run_ours(args, rank, world, local):
     sampler = ClockSampler(local) if rank == 0 else None
     l0, f0 = gpu.counters()
     gpu.set_option("gemm_timing", 1)
+    gpu.timer_start()                      # CUDA events on the stream the kernels are launched on
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step(True)
+    dev_ms = gpu.timer_stop()
     barrier()
-    elapsed = time.perf_counter() - t0
-    gemm_ms, gemm_flops = gpu.gemm_time()
+    wall = time.perf_counter() - t0
     gpu.set_option("gemm_timing", 0)
     l1, f1 = gpu.counters()
     clocks = sampler.stop() if sampler else None
-    tt = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([dev_ms * 1e-3, wall], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    elapsed = float(tt.item())
+    elapsed, wall = float(tt[0].item()), float(tt[1].item())
     value = elapsed / args.steps
 
     # ---- end-to-end leg through the C ABI with host buffers (pinned): H2D of the step's MO integrals, D2H of amplitudes
     if big:
         gpu.set_option("finalize_keep_ccsd", 0)   # free the CCSD work arrays before (T): the next step re-initialises
     ksteps = args.steps
+    parts = {"h2d_set_eri_mo": 0.0, "ccsd_init": 0.0, "iterate+diis": 0.0, "finalize_d2h": 0.0, "ccsd_t": 0.0}
+
+    def lap(key, t_prev):
+        t = time.perf_counter()
+        parts[key] += t - t_prev
+        return t
+
     barrier()
     t0 = time.perf_counter()
     for _ in range(ksteps):
+        t = time.perf_counter()
         gpu.set_eri_mo(n, src)
+        t = lap("h2d_set_eri_mo", t)
         gpu.ccsd_init(o, True, eps, 8)
         if big:
             gpu.release("eri_mo")
+        t = lap("ccsd_init", t)
         gpu.ccsd_iterate()
         gpu.ccsd_diis()
+        t = lap("iterate+diis", t)
         _, t1h, t2h = gpu.ccsd_finalize(want_amplitudes=True)
+        t = lap("finalize_d2h", t)
         gpu.ccsd_t_spatial(True, False, False)
+        t = lap("ccsd_t", t)
     barrier()
     e2e_elapsed = time.perf_counter() - t0
     te = torch.tensor([e2e_elapsed], dtype=torch.float64, device="cuda")
@@ -281,38 +302,57 @@ def run_ours(args, rank, world, local):
         tpath = os.path.join(ROOT, "profiles", "ncu_gemm_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch", {}).get(f"nbf{n}")
             except Exception:
                 traffic = None
-        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        tot_ms = gstat["ccsd"][0] + gstat["t"][0]
+        tot_fl = gstat["ccsd"][1] + gstat["t"][1]
+        tf = lambda g: (g[1] / (g[0] * 1e-3) / 1e12) if g[0] > 0 else None
+        # dominant kernel: the batched (T) GEMM  C_pqr(x,(y,z)) = Acat(x,[d|l]) Bcat([d|l],(y,z)), M=v, N=v^2, K=nbf
+        t_ms, t_fl, t_nl = gstat["t"]
+        achieved = tf(gstat["t"])
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"synthetic integrals nbf={n} nocc={o} CCSD(T)_spatial", "nbf": n, "nocc": o,
-                       "calc_type": "CCSD(T)_spatial", "parallelism": (f"(T) ijk round-robin x{world}; CCSD GEMMs column-sharded x{world} with NCCL slab "
+                       "calc_type": "CCSD(T)_spatial",
+                       "parallelism": (f"(T) ijk round-robin x{world}; CCSD GEMMs column-sharded x{world} with NCCL slab "
                                        f"exchange, V+/- ladder integrals sharded by column block") if world > 1
                        else "single GPU",
                        "l2": "inputs larger than L2 (packed ladder integrals %.1f GB, (T) work buffers %.1f GB)" % (
-                           v ** 4 * 4 / 1e9, 6.0)},
+                           v ** 4 * 4 / 1e9, 6.0),
+                       "timing": "CUDA events on the engine's stream around the K steps, max over ranks"},
+            "wall_s_per_step": wall / args.steps,
             "ccsd_s_per_iter": (float(np.mean(comp["ccsd"])) + float(np.mean(comp["diis"]))) / 1e3,
             "t_wall_s": float(np.mean(comp["t"])) / 1e3, "ao2mo_s": ao2mo_ms / 1e3,
             "energies": {"e_mp2": e_mp2, "e_mp1": e_mp1, **last},
-            "gemm_tflops_executed": achieved,
+            "gemm_tflops_executed": {"all": (tot_fl / (tot_ms * 1e-3) / 1e12) if tot_ms > 0 else None,
+                                     "ccsd": tf(gstat["ccsd"]), "t": tf(gstat["t"]),
+                                     "gemm_share_of_step": tot_ms * 1e-3 / elapsed if elapsed > 0 else None},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "kernel": "gemm_f64_dmma (all DMMA GEMM launches of the timed region: CCSD contractions + (T))",
-                         "flops_per_step": gemm_flops / args.steps, "gemm_ms_per_step": gemm_ms / args.steps,
+                         "kernel": "gemm_f64_tma<N,N> batched over (ijk-permutations): (T) contraction "
+                                   f"M={v} N={v * v} K={n} per block (the cp.async twin gemm_f64_dmma runs when v or "
+                                   "nbf is odd)",
+                         "launches": t_nl, "flops_per_launch": (t_fl / t_nl) if t_nl else None,
+                         "ms_per_launch": (t_ms / t_nl) if t_nl else None,
+                         "share_of_step": t_ms * 1e-3 / elapsed if elapsed > 0 else None,
+                         "all_gemms": {"achieved": (tot_fl / (tot_ms * 1e-3) / 1e12) if tot_ms > 0 else None,
+                                       "flops_per_step": tot_fl / args.steps, "ms_per_step": tot_ms / args.steps},
                          "peak_source": "in-run register-resident DMMA.8x8x4 issue-rate probe (MEASURED_PEAKS.json has "
                                         "no FP64 entry; vendor FP64 tensor figure 40 TFLOP/s)"},
             "cpu_baseline": ({"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": cpu["kind"],
                               "sample": cpu["sample"], "ccsd_s_per_iter": cpu.get("ccsd_s_per_iter"),
                               "t_wall_s": cpu.get("t_wall_s")} if cpu else None),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "set_eri_mo(H2D, pinned) + ccsd_init + iterate + diis + finalize(D2H t1,t2) + ccsd_t"},
+                    "what": "set_eri_mo(H2D, pinned) + ccsd_init + iterate + diis + finalize(D2H t1,t2) + ccsd_t",
+                    "breakdown_s": {k: x / ksteps for k, x in parts.items()}},
             "gpu_launches": int(l1 - l0),
             "clocks": clocks,
         }
+        if world > 1:
+            line["exchange"] = "NCCL grouped broadcasts of GEMM column slabs on the compute stream"
         emit(line)
     gpu.close()
     if world > 1:

@@ -125,9 +125,14 @@ int afesp_gpu_bench_dgemm(afesp_handle h, char transA, char transB, int M, int N
 int afesp_gpu_dmma_peak(afesp_handle h, double* tflops);
 /* Device time (CUDA events on the engine's stream) of the last stage call on this handle, milliseconds. */
 int afesp_gpu_last_stage_ms(afesp_handle h, double* ms);
+/* Stopwatch on the engine's stream: stop == 0 records the start event; stop != 0 records the end event, waits for it
+ * and returns the device milliseconds between the two (spans any number of stage calls, idle gaps included). */
+int afesp_gpu_timer(afesp_handle h, int stop, double* ms);
 /* With option "gemm_timing" on: accumulated device milliseconds and executed flop of all DMMA GEMM launches since the
  * option was switched on or since the previous call (synchronises the stream). */
 int afesp_gpu_gemm_time(afesp_handle h, double* ms, double* flops);
+/* Same, plus the number of GEMM launches bracketed (per-launch averages for the roofline line of bench.py). */
+int afesp_gpu_gemm_stats(afesp_handle h, double* ms, double* flops, long long* launches);
 
 #ifdef __cplusplus
 }

@@ -1,20 +1,35 @@
-"""Short program for ncu captures: the ladder-shaped and (T)-shaped DMMA GEMMs, then one full (T) on the synthetic
-nbf=200/nocc=20 system (so the fused epilogue kernel runs at its real shape)."""
+"""Short program for ncu captures on the synthetic system (NBF/NOCC env, default 200/20).
+
+PROFILE=T     cudaProfilerStart right before the (T) call: the batched (T) GEMM (gemm_f64_tma), the fused
+              combine+energy kernel and the partial-sum finish are the first kernels captured.
+PROFILE=CCSD  cudaProfilerStart right before one CCSD iteration (ladder, rings, permutes, divide).
+Run under `ncu --profile-from-start off ...`; without ncu it just runs the chain."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
 from afesp_b200 import AfespGpu, synthetic
 
 n, o = int(os.environ.get("NBF", 200)), int(os.environ.get("NOCC", 20))
-v = n - o
+what = os.environ.get("PROFILE", "T")
+rt = torch.cuda.cudart()
 g = AfespGpu(0)
-print("ladder", g.bench_dgemm("N", "N", o * o, v * v, v * v, reps=2, beta=1.0))
-print("T1", g.bench_dgemm("N", "N", v, v * v * 8, v, reps=2))
-print("T2", g.bench_dgemm("T", "N", v * v * 8, v, o, reps=2, beta=1.0))
 eri, C, eps = synthetic.make(n, o)
 g.ao2mo(n, eri, C, want_result=False)
+g.release("eri_ao")
 g.ccsd_init(o, True, eps, 8)
 g.ccsd_iterate()
+g.ccsd_diis()
+if what == "CCSD":
+    rt.cudaProfilerStart()
+    g.ccsd_iterate()
+    rt.cudaProfilerStop()
+    print("ccsd iter ms", g.last_stage_ms())
 g.ccsd_finalize()
+if what == "T":
+    g.set_option("triples_batch_bytes", float(6 << 30))
+    rt.cudaProfilerStart()
 sums, _ = g.ccsd_t_spatial(True, False, False)
+if what == "T":
+    rt.cudaProfilerStop()
 print("T ms", g.last_stage_ms(), sums[:2])
 g.close()
