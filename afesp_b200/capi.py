@@ -41,6 +41,7 @@ SIGNATURES = {
     "afesp_gpu_dmma_peak": [_H, _dp],
     "afesp_gpu_last_stage_ms": [_H, _dp],
     "afesp_gpu_timer": [_H, C.c_int, _dp],
+    "afesp_gpu_bench_hbm": [_H, C.c_char_p, C.c_int, C.c_int, C.c_int, _dp, _dp],
     "afesp_gpu_gemm_time": [_H, _dp, _dp],
     "afesp_gpu_gemm_stats": [_H, _dp, _dp, C.POINTER(C.c_longlong)],
 }
@@ -175,7 +176,8 @@ class AfespGpu:
         self._check("release", self.lib.afesp_gpu_release(self.h, what.encode()))
 
     def set_eri_mo(self, nbasis, eri_mo):
-        e = np.ascontiguousarray(eri_mo, dtype=np.float64)
+        """eri_mo may be None on ranks > 0 of a communicator: they receive rank 0's copy over NVLink."""
+        e = None if eri_mo is None else np.ascontiguousarray(eri_mo, dtype=np.float64)
         self._check("set_eri_mo", self.lib.afesp_gpu_set_eri_mo(self.h, int(nbasis), _ptr(e)))
         self.n = int(nbasis)
 
@@ -302,6 +304,13 @@ class AfespGpu:
         ms, fl = C.c_double(0), C.c_double(0)
         self._check("gemm_time", self.lib.afesp_gpu_gemm_time(self.h, C.byref(ms), C.byref(fl)))
         return ms.value, fl.value
+
+    def bench_hbm(self, what, nocc, nvirt, reps=10):
+        """(ms per launch, algorithmic bytes per launch) of an HBM-bound kernel at the (o,o,v,v) shape."""
+        ms, by = C.c_double(0), C.c_double(0)
+        self._check("bench_hbm", self.lib.afesp_gpu_bench_hbm(self.h, what.encode(), int(nocc), int(nvirt), int(reps),
+                                                              C.byref(ms), C.byref(by)))
+        return ms.value, by.value
 
     def timer_start(self):
         self._check("timer", self.lib.afesp_gpu_timer(self.h, 0, None))

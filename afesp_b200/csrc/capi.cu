@@ -3,6 +3,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <functional>
 
 #include "../../include/afesp_gpu.h"
 #include "ccsd.cuh"
@@ -296,11 +297,23 @@ int afesp_gpu_release(afesp_handle hv, const char* what) {
 
 int afesp_gpu_set_eri_mo(afesp_handle hv, int n, const double* eri_mo) {
   return guarded(hv, [&](Handle& h) {
-    AFESP_REQUIRE(n > 0 && eri_mo, "set_eri_mo: bad arguments");
+    const Dist& d = h.s.eng.dist;
+    const bool collective = d.nranks > 1 && d.comm != nullptr;
+    AFESP_REQUIRE(n > 0 && (eri_mo || (collective && d.rank != 0)), "set_eri_mo: bad arguments");
     const long long np = npacked_of(n);
+    cudaStream_t st = h.s.eng.stream;
     if ((long long)h.s.eri_mo.n != np) h.s.eri_mo.alloc((size_t)np);
-    AFESP_CUDA_CHECK(cudaMemcpyAsync(h.s.eri_mo.p, eri_mo, np * 8, cudaMemcpyHostToDevice, h.s.eng.stream));
-    AFESP_CUDA_CHECK(cudaStreamSynchronize(h.s.eng.stream));
+    if (eri_mo) AFESP_CUDA_CHECK(cudaMemcpyAsync(h.s.eri_mo.p, eri_mo, np * 8, cudaMemcpyHostToDevice, st));
+    if (collective) {
+      // One host copy per node is enough: rank 0 uploads, the other ranks receive over NVLink.  Ranks that pass their
+      // own host array take part in the broadcast too (it delivers identical data).
+      int any_null = eri_mo ? 0 : 1;
+      (void)any_null;
+      AFESP_REQUIRE(d.group_start() == 0, "ncclGroupStart failed");
+      AFESP_REQUIRE(d.bcast(h.s.eri_mo.p, h.s.eri_mo.p, (size_t)np, 0, d.comm, st) == 0, "ncclBroadcast failed");
+      AFESP_REQUIRE(d.group_end() == 0, "ncclGroupEnd failed");
+    }
+    AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
     h.s.n = n;
   });
 }
@@ -558,6 +571,61 @@ int afesp_gpu_bench_dgemm(afesp_handle hv, char ta, char tb, int M, int N, int K
     tm.stop();
     AFESP_CUDA_CHECK(cudaGetLastError());
     *ms = h.last_ms / reps;
+  });
+}
+
+// HBM-bound kernels at the shape of an (o,o,v,v) amplitude array, device resident, `reps` launches:
+//   what = "permute:<order>"  out = permute(in), 4-index order as in omp_reshape, e.g. "permute:3412"   16 B/element
+//          "permute_acc:<order>"  out = permute(in) + out                                                24 B/element
+//          "divide"   t2 = x / D_ijab, denominators from eps on the fly (src/ccsd.f90:1727)               16 B/element
+//          "energy"   E_CC + sum dT2^2 in one pass (src/ccsd.f90:1767-1786)                               24 B/element
+//          "axpby"    y = a x + b y                                                                        24 B/element
+// Returns milliseconds per launch and the algorithmic bytes per launch.
+int afesp_gpu_bench_hbm(afesp_handle hv, const char* what, int o, int v, int reps, double* ms, double* bytes) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(what && o > 0 && v > 0 && reps > 0 && ms && bytes, "bench_hbm: bad arguments");
+    const std::string w(what);
+    cudaStream_t st = h.s.eng.stream;
+    const long long n = (long long)o * o * v * v;
+    DBuf a((size_t)n), b((size_t)n), c((size_t)n), eo(o), ev(v), t1((size_t)o * v);
+    fill(st, n, 1.0 / 3.0, a.p); fill(st, n, 0.25, b.p); fill(st, n, 0.5, c.p);
+    fill(st, o, -1.0, eo.p); fill(st, v, 1.0, ev.p); fill(st, (long long)o * v, 0.01, t1.p);
+    if (h.s.red_out.n < 16) h.s.red_out.alloc(16);
+    std::function<void()> run;
+    double per = 16.0;
+    if (w.rfind("permute", 0) == 0) {
+      const bool acc = w.rfind("permute_acc", 0) == 0;
+      const size_t colon = w.find(':');
+      AFESP_REQUIRE(colon != std::string::npos && w.size() == colon + 5, "bench_hbm: permute:<4-digit order>");
+      static int perm[4];
+      static int dims[4];
+      const int in_dims[4] = {o, o, v, v};
+      for (int d = 0; d < 4; ++d) {
+        perm[d] = w[colon + 1 + d] - '1';
+        AFESP_REQUIRE(perm[d] >= 0 && perm[d] < 4, "bench_hbm: bad order");
+        dims[d] = in_dims[d];
+      }
+      per = acc ? 24.0 : 16.0;
+      run = [=, &a, &b] { permute(st, 4, dims, perm, 1.0, a.p, acc ? 1.0 : 0.0, b.p); };
+    } else if (w == "divide") {
+      run = [=, &a, &b, &eo, &ev] { divide_d2(st, b.p, a.p, eo.p, ev.p, o, v); };
+    } else if (w == "energy") {
+      per = 24.0;
+      run = [=, &a, &b, &c, &t1, &h] { cc_energy_restricted(h.s.eng, a.p, b.p, t1.p, c.p, o, v, h.s.red_out.p); };
+    } else if (w == "axpby") {
+      per = 24.0;
+      run = [=, &a, &b] { axpby(st, n, 0.5, a.p, 0.5, b.p); };
+    } else {
+      throw Error(1, "bench_hbm: unknown kernel " + w);
+    }
+    run();
+    AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
+    StageTimer tm(&h);
+    for (int r = 0; r < reps; ++r) run();
+    tm.stop();
+    AFESP_CUDA_CHECK(cudaGetLastError());
+    *ms = h.last_ms / reps;
+    *bytes = per * (double)n;
   });
 }
 

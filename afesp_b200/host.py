@@ -59,6 +59,7 @@ class ElsInput:
     core_hamil: np.ndarray | None = None
     eri: np.ndarray | None = None      # packed AO ERIs, canonical order (src/integrals.f90:196-210)
     guess: np.ndarray | None = None    # guess_in.dat Fock matrix
+    fock_final: np.ndarray | None = None  # AO Fock matrix of the converged SCF (guess_out.dat)
 
 
 @dataclass
@@ -142,9 +143,7 @@ def read_inputs(dirpath) -> ElsInput:
     g = np.array(toks[1:1 + 4 * nat], dtype=float).reshape(nat, 4)
     set_geometry(inp, g[:, 0], g[:, 1:])
     if inp.scf_read_guess:
-        gd = np.loadtxt(os.path.join(dirpath, "guess_in.dat"), ndmin=2)
-        inp.guess = np.zeros((n, n))
-        inp.guess[gd[:, 0].astype(int) - 1, gd[:, 1].astype(int) - 1] = gd[:, 2]
+        inp.guess = read_scf_guess(os.path.join(dirpath, "guess_in.dat"), n)
     return inp
 
 
@@ -166,7 +165,9 @@ def _unpack(packed, n):
 
 
 def rhf(inp: ElsInput, out=None):
-    """do_rhf (src/hf.f90:21-151) with Pulay DIIS (:197-242); returns (e_elec, C[mo,ao], eps, table, converged)."""
+    """do_rhf (src/hf.f90:21-151) with Pulay DIIS (:197-242); returns (e_elec, C[mo,ao], eps, table, converged).
+    The AO Fock matrix of the last diagonalisation (what write_out_scf_guess stores, :131-134) is left in
+    inp.fock_final."""
     n, nocc = inp.nbasis, inp.nel // 2
     S, h = inp.ovlp, inp.core_hamil
     g = _unpack(inp.eri, n)
@@ -186,6 +187,7 @@ def rhf(inp: ElsInput, out=None):
     t0 = time.perf_counter()
     for it in range(1, inp.scf_maxiter + 1):
         eps, Cp = np.linalg.eigh(X.T @ F @ X)
+        inp.fock_final = F.copy()
         C_mo = (X @ Cp).T
         D = C_mo[:nocc].T @ C_mo[:nocc]
         e_old, energy = energy, float(np.sum(D * (h + F)))
@@ -217,6 +219,55 @@ def rhf(inp: ElsInput, out=None):
                 c = np.linalg.solve(B, rhs)
                 F = np.tensordot(c[:na], Fs[:na], axes=(0, 0))
     return energy, C_mo, eps, table, conv
+
+
+def _es(x, width, digits):
+    """Fortran ESw.d edit descriptor (one non-zero digit before the point, two-digit exponent)."""
+    return ("%" + str(width) + "." + str(digits) + "E") % x
+
+
+def write_scf_guess(path, fock):
+    """write_out_scf_guess (src/hf.f90:172-191): every (i, j, F_ij), format (I0, 1X, I0, 1X, ES16.9)."""
+    n = fock.shape[0]
+    with open(path, "w") as f:
+        for i in range(n):
+            for j in range(n):
+                f.write("%d %d %s\n" % (i + 1, j + 1, _es(fock[i, j], 16, 9)))
+
+
+def read_scf_guess(path, n):
+    """read_in_scf_guess (src/hf.f90:153-170): free-format (i, j, value) triples."""
+    gd = np.loadtxt(path, ndmin=2)
+    g = np.zeros((n, n))
+    g[gd[:, 0].astype(int) - 1, gd[:, 1].astype(int) - 1] = gd[:, 2]
+    return g
+
+
+def fcidump_indices(n):
+    """(p, q, r, s), 1-based, of every packed MO integral in the reference's canonical loop order
+    (src/mp2.f90:466-479: p, q<=p, r<=p, s<=(q if r==p else r)) -- the same order as the packed array."""
+    P, Q, R, S = [], [], [], []
+    for p in range(1, n + 1):
+        for q in range(1, p + 1):
+            for r in range(1, p + 1):
+                s_up = q if r == p else r
+                cnt = s_up
+                P.append(np.full(cnt, p)); Q.append(np.full(cnt, q)); R.append(np.full(cnt, r))
+                S.append(np.arange(1, s_up + 1))
+    return tuple(np.concatenate(a) for a in (P, Q, R, S))
+
+
+def write_fcidump(path, eri_mo_packed, n):
+    """write_fcidump (src/mp2.f90:451-487): one line per packed MO integral with |v| > 1e-7,
+    format (I3,I3,I3,I3,ES17.9), canonical order, no header (as the reference writes it)."""
+    p, q, r, s = fcidump_indices(n)
+    v = np.asarray(eri_mo_packed)
+    assert v.size == p.size, (v.size, p.size)
+    keep = np.abs(v) > np.float32(1e-7)   # the reference compares against a default-real literal
+    with open(path, "w") as f:
+        for a, b, c, d, x in zip(p[keep], q[keep], r[keep], s[keep], v[keep]):
+            f.write("%3d%3d%3d%3d%s\n" % (a, b, c, d, _es(x, 17, 9)))
+    return int(keep.sum())
 
 
 def assemble_triples(e_ccsd, sums, const, paren, renorm, comp_renorm):
@@ -269,8 +320,11 @@ def ccsd_loop(gpu: AfespGpu, nocc, restricted, eps, e_tol, t_tol, diis_n, maxite
     return table, conv, e, ms
 
 
-def run(inp: ElsInput, gpu: AfespGpu | None = None, device: int = 0, verbose: bool = False) -> ElsResult:
-    """Whole program (src/main.F90): RHF on the host, everything from do_mp2_spatial onwards on the GPU."""
+def run(inp: ElsInput, gpu: AfespGpu | None = None, device: int = 0, verbose: bool = False,
+        workdir: str | None = None) -> ElsResult:
+    """Whole program (src/main.F90): RHF on the host, everything from do_mp2_spatial onwards on the GPU.
+    With `workdir` the files the reference writes into its run directory are written there too: guess_out.dat
+    (scf_write_guess) and FCIDUMP (write_fcidump)."""
     level, restricted, paren, renorm, comp_renorm = CALC_TYPES[inp.calc_type]
     out = io.StringIO()
     res = ElsResult(e_nuc=inp.e_nuc)
@@ -281,6 +335,9 @@ def run(inp: ElsInput, gpu: AfespGpu | None = None, device: int = 0, verbose: bo
     res.timings["rhf_s"] = time.perf_counter() - t0
     if not conv:
         out.write(" Convergence not reached, please increase maxiter.\n")
+    elif inp.scf_write_guess and workdir is not None:
+        out.write(" Writing AO Fock matrix for future use...\n")
+        write_scf_guess(os.path.join(workdir, "guess_out.dat"), inp.fock_final)
     if level >= 1:
         own = gpu is None
         gpu = gpu or AfespGpu(device)
@@ -293,6 +350,10 @@ def run(inp: ElsInput, gpu: AfespGpu | None = None, device: int = 0, verbose: bo
             out.write(" Calculating MP2 energy...\n")
             res.e_mp2 = gpu.mp2_energy(nocc, eps)
             out.write(" MP2 correlation energy (Hartree): %15.8f\n" % res.e_mp2)
+            if inp.write_fcidump and workdir is not None:
+                out.write(" Writing FCIDUMP file...\n")
+                write_fcidump(os.path.join(workdir, "FCIDUMP"), gpu.get_eri_mo(), inp.nbasis)
+                out.write(" Done writing FCIDUMP file!\n")
             res.timings["mp2_s"] = time.perf_counter() - t0
             if level >= 2:
                 t0 = time.perf_counter()

@@ -194,8 +194,12 @@ def run_ours(args, rank, world, local):
     # ---- device-resident leg
     npair = n * (n + 1) // 2
     npk = npair * (npair + 1) // 2
-    pinned = torch.empty(npk, dtype=torch.float64).pin_memory()   # host copy of the packed MO integrals (e2e leg input)
-    src = pinned.numpy()
+    # host copy of the packed MO integrals (input of the e2e leg): one pinned copy per node, on rank 0; the other
+    # ranks receive it over NVLink inside afesp_gpu_set_eri_mo
+    src = None
+    if rank == 0:
+        pinned = torch.empty(npk, dtype=torch.float64).pin_memory()
+        src = pinned.numpy()
     if big:
         gpu.synth_eri_ao(n, Bfac, Cmo)
         gpu.ao2mo(n, want_result=False)
@@ -203,7 +207,8 @@ def run_ours(args, rank, world, local):
         gpu.ao2mo(n, eri, Cmo, want_result=False)   # also leaves AO integrals + C resident
     gpu.ao2mo(n)                                     # resident repeat, device-timed
     ao2mo_ms = gpu.last_stage_ms()
-    gpu.get_eri_mo(src)
+    if rank == 0:
+        gpu.get_eri_mo(src)
     gpu.release("eri_ao")
     e_mp2 = gpu.mp2_energy(o, eps)
     gpu.set_option("finalize_keep_ccsd", 1)
@@ -291,6 +296,24 @@ def run_ours(args, rank, world, local):
     h2d = int(npk * 8 + n * 8)
     d2h = int((o * o * v * v + o * v) * 8 + 10 * 8)
 
+    # ---- HBM-bound kernels of the path (permute / denominators / energy), device resident, vs the measured copy peak
+    hbm = None
+    if rank == 0:
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+        except Exception:
+            hbm_peak, peak_src = 6452.0, "fallback 6452 GB/s (B200_PROFILING.md measured copy)"
+        hbm = {"peak_gbs": hbm_peak, "peak_source": peak_src, "kernels": {}}
+        for (oo_, vv_) in sorted({(o, v), (40, 360)}):
+            for what in ("permute:3412", "permute:2143", "permute_acc:2143", "divide", "energy", "axpby"):
+                try:
+                    ms, by = gpu.bench_hbm(what, oo_, vv_, reps=20)
+                    hbm["kernels"][f"{what} o={oo_} v={vv_}"] = {
+                        "ms": ms, "algorithmic_bytes": by, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / hbm_peak}
+                except Exception as ex:
+                    hbm["kernels"][f"{what} o={oo_} v={vv_}"] = {"error": str(ex)}
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -346,10 +369,11 @@ def run_ours(args, rank, world, local):
                               "sample": cpu["sample"], "ccsd_s_per_iter": cpu.get("ccsd_s_per_iter"),
                               "t_wall_s": cpu.get("t_wall_s")} if cpu else None),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "set_eri_mo(H2D, pinned) + ccsd_init + iterate + diis + finalize(D2H t1,t2) + ccsd_t",
+                    "what": "set_eri_mo(H2D from pinned host memory on rank 0, NVLink broadcast to the other ranks) + ccsd_init + iterate + diis + finalize(D2H t1,t2) + ccsd_t",
                     "breakdown_s": {k: x / ksteps for k, x in parts.items()}},
             "gpu_launches": int(l1 - l0),
             "clocks": clocks,
+            "hbm_kernels": hbm,
         }
         if world > 1:
             line["exchange"] = "NCCL grouped broadcasts of GEMM column slabs on the compute stream"

@@ -60,7 +60,9 @@ int afesp_gpu_synth_eri_ao(afesp_handle h, int nbasis, int naux, const double* f
 int afesp_gpu_get_eri_mo(afesp_handle h, double* eri_mo);
 /* Free device memory the next stage does not need: what = "eri_ao" | "eri_mo" | "scratch". */
 int afesp_gpu_release(afesp_handle h, const char* what);
-/* Load packed MO integrals directly (a host that already holds int_store%eri_mo). */
+/* Load packed MO integrals directly (a host that already holds int_store%eri_mo).  With a communicator attached the
+ * call is collective: rank 0 passes the host array, the other ranks may pass NULL and receive the device copy over
+ * NVLink (one host copy per node instead of one per GPU). */
 int afesp_gpu_set_eri_mo(afesp_handle h, int nbasis, const double* eri_mo);
 /* MP2 correlation energy from the device-resident MO integrals (src/mp2.f90:418-438); eps = sys%canon_levels(n). */
 int afesp_gpu_mp2_energy(afesp_handle h, int nocc, const double* eps, double* e_mp2);
@@ -120,6 +122,11 @@ int afesp_gpu_omp_reshape(afesp_handle h, double* out_arr, const double* in_arr,
 /* Synthetic-workload helper (bench): time `reps` back-to-back device-resident dgemms, returns milliseconds/gemm. */
 int afesp_gpu_bench_dgemm(afesp_handle h, char transA, char transB, int M, int N, int K, double beta, int reps,
                           double* ms);
+/* HBM-bound kernels of the path timed device-resident at the shape of an (o,o,v,v) amplitude array:
+ * what = "permute:<order>" (omp_reshape order, e.g. "permute:3412"; 16 B/element), "permute_acc:<order>" (24 B),
+ * "divide" (T2 = X / D_ijab, 16 B), "energy" (E_CC + sum dT2^2 in one pass, 24 B), "axpby" (24 B).
+ * Returns milliseconds per launch and the algorithmic bytes per launch. */
+int afesp_gpu_bench_hbm(afesp_handle h, const char* what, int nocc, int nvirt, int reps, double* ms, double* bytes);
 /* Raw DMMA issue-rate probe: register-resident mma.sync loop on all SMs; returns TFLOP/s (the FP64 tensor peak the
  * roofline fractions are quoted against; MEASURED_PEAKS.json has no FP64 entry). */
 int afesp_gpu_dmma_peak(afesp_handle h, double* tflops);

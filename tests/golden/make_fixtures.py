@@ -82,8 +82,18 @@ def main():
             guess[gd[:, 0].astype(int) - 1, gd[:, 1].astype(int) - 1] = gd[:, 2]
         with open(os.path.join(d, "els.in")) as f:
             els_in = f.read()
+        # guess_out.dat as the reference wrote it (src/hf.f90:172-191): values + the first lines verbatim (format pin)
+        guess_out, guess_out_head = np.zeros((0, 0)), ""
+        gopath = os.path.join(d, "guess_out.dat")
+        if os.path.exists(gopath):
+            gd = np.loadtxt(gopath, ndmin=2)
+            guess_out = np.zeros((n, n))
+            guess_out[gd[:, 0].astype(int) - 1, gd[:, 1].astype(int) - 1] = gd[:, 2]
+            with open(gopath) as f:
+                guess_out_head = "".join(f.readlines()[:5])
         np.savez_compressed(os.path.join(HERE, f"{name}.npz"), ovlp=sysm.ovlp, ke=ke, en=en, eri=sysm.eri,
-                            geom=geom, guess=guess, els_in=np.array(els_in))
+                            geom=geom, guess=guess, els_in=np.array(els_in), guess_out=guess_out,
+                            guess_out_head=np.array(guess_out_head))
         with open(os.path.join(d, outname)) as f:
             golden[name] = parse_out(f.read())
         golden[name]["source"] = f"{rel}/{outname}"
