@@ -60,6 +60,7 @@ class ElsInput:
     eri: np.ndarray | None = None      # packed AO ERIs, canonical order (src/integrals.f90:196-210)
     guess: np.ndarray | None = None    # guess_in.dat Fock matrix
     fock_final: np.ndarray | None = None  # AO Fock matrix of the converged SCF (guess_out.dat)
+    els_in_text: str = ""              # els.in as read (echoed into the output, src/integrals.f90:240-249)
 
 
 @dataclass
@@ -120,9 +121,10 @@ def read_inputs(dirpath) -> ElsInput:
     """read_system_in, read_integrals_in, read_geometry_in (src/system.f90:81, integrals.f90:48, geometry.f90:8)."""
     inp = ElsInput()
     with open(os.path.join(dirpath, "els.in")) as f:
-        for k, v in parse_namelist(f.read()).items():
-            if hasattr(inp, k):
-                setattr(inp, k, v)
+        inp.els_in_text = f.read()
+    for k, v in parse_namelist(inp.els_in_text).items():
+        if hasattr(inp, k):
+            setattr(inp, k, v)
     if inp.calc_type not in CALC_TYPES:
         raise ValueError("system::read_system_in: Unrecognised calculation type!")
     s = np.loadtxt(os.path.join(dirpath, "s.dat"), ndmin=2)
@@ -184,6 +186,10 @@ def rhf(inp: ElsInput, out=None):
     energy, D_old = 0.0, np.zeros((n, n))
     table, conv = [], False
     C_mo = eps = None
+    if out is not None:
+        if inp.scf_read_guess and inp.guess is not None:
+            out.write(" Reading previous AO Fock matrix as guess...\n")
+        out.write("-" * 75 + "\n Iteration        Energy           deltaE           delta RMS D      Time  \n" + "-" * 75 + "\n")
     t0 = time.perf_counter()
     for it in range(1, inp.scf_maxiter + 1):
         eps, Cp = np.linalg.eigh(X.T @ F @ X)
@@ -200,6 +206,12 @@ def rhf(inp: ElsInput, out=None):
             out.write(" %9d   %15.10f   %15.10f   %15.10f   %8.6f\n" % (it, energy, energy - e_old, rms, t1 - t0))
         t0 = t1
         if conv:
+            if out is not None:   # src/hf.f90:115-122
+                out.write("-" * 75 + "\n Convergence reached within tolerance.\n")
+                out.write(" Final SCF Energy (Hartree): %15.8f\n" % energy)
+                out.write(" Orbital energies (Hartree):\n")
+                for i in range(n, 0, -1):
+                    out.write(" %3d %15.8f\n" % (i, eps[i - 1]))
             break
         F = h + 2.0 * np.einsum("ijkl,kl->ij", J_src, D) - np.einsum("ijkl,kl->ij", K_src, D)
         if use_diis:
@@ -297,9 +309,26 @@ def assemble_triples(e_ccsd, sums, const, paren, renorm, comp_renorm):
 def ccsd_loop(gpu: AfespGpu, nocc, restricted, eps, e_tol, t_tol, diis_n, maxiter, out=None):
     """The iteration loop of do_ccsd_spatial / do_ccsd_spinorb (src/ccsd.f90:339-396 / 229-271) on the host side:
     the GPU does one iteration per call, the host keeps the table, the convergence test (:1805) and the DIIS call."""
+    t_init = time.perf_counter()
     e, rms = gpu.ccsd_init(nocc, restricted, eps, diis_n)
     table = [("MP1", e, e - 0.0, rms)]
     if out is not None:
+        if restricted:   # src/ccsd.f90:312-324 with the prints of init_cc (:427-526)
+            out.write(" Initialise CC intermediate tensors and DIIS auxilliary arrays...\n"
+                      " Forming energy denominator matrices...\n Allocating amplitude tensors...\n"
+                      " Forming ERI slices...\n Forming initial amplitude guesses...\n"
+                      " Allocating stored intermediate tensors...\n")
+        else:            # src/ccsd.f90:106-220
+            dt = time.perf_counter() - t_init
+            out.write(" Forming antisymmetrised spinorbital ERIs...\n Time taken: %8.6f s\n\n" % dt)
+            out.write(" Checking that the permuational symmetry of the antisymmetrised integrals hold...\n"
+                      " Time taken: %8.6f s\n\n" % 0.0)
+            out.write(" Forming slices of antisymmetrised spinorbital ERIs\n Time taken: %8.6f s\n\n" % 0.0)
+            out.write(" Initialise CC intermediate tensors and DIIS auxilliary arrays...\n"
+                      " Forming energy denominator matrices...\n Allocating amplitude tensors...\n"
+                      " Forming initial amplitude guesses...\n Allocating stored intermediate tensors...\n")
+        out.write(" Time taken: %8.6f s\n\n" % (time.perf_counter() - t_init))
+        out.write(" Initialisation done, now entering iterative CC solver...\n")
         out.write("-" * 75 + "\n Iteration        Energy           deltaE          delta RMS T2      Time  \n" + "-" * 75 + "\n")
         out.write(" %9s   %15.12f   %15.12f   %15.12f\n" % ("MP1", e, e, rms))
     conv = False
@@ -328,6 +357,9 @@ def run(inp: ElsInput, gpu: AfespGpu | None = None, device: int = 0, verbose: bo
     level, restricted, paren, renorm, comp_renorm = CALC_TYPES[inp.calc_type]
     out = io.StringIO()
     res = ElsResult(e_nuc=inp.e_nuc)
+    t_glob = time.perf_counter()
+    out.write(header_block(inp))
+    out.write(_taken("system initialisation", time.perf_counter() - t_glob))
     t0 = time.perf_counter()
     out.write(" " + "-" * 23 + "\n Restricted Hartree-Fock\n " + "-" * 23 + "\n")
     res.e_hf, C_mo, eps, res.scf_table, conv = rhf(inp, out)
@@ -335,9 +367,11 @@ def run(inp: ElsInput, gpu: AfespGpu | None = None, device: int = 0, verbose: bo
     res.timings["rhf_s"] = time.perf_counter() - t0
     if not conv:
         out.write(" Convergence not reached, please increase maxiter.\n")
-    elif inp.scf_write_guess and workdir is not None:
+    elif inp.scf_write_guess:
         out.write(" Writing AO Fock matrix for future use...\n")
-        write_scf_guess(os.path.join(workdir, "guess_out.dat"), inp.fock_final)
+        if workdir is not None:
+            write_scf_guess(os.path.join(workdir, "guess_out.dat"), inp.fock_final)
+    out.write(_taken("restricted Hartree-Fock", res.timings["rhf_s"]))
     if level >= 1:
         own = gpu is None
         gpu = gpu or AfespGpu(device)
@@ -350,11 +384,13 @@ def run(inp: ElsInput, gpu: AfespGpu | None = None, device: int = 0, verbose: bo
             out.write(" Calculating MP2 energy...\n")
             res.e_mp2 = gpu.mp2_energy(nocc, eps)
             out.write(" MP2 correlation energy (Hartree): %15.8f\n" % res.e_mp2)
-            if inp.write_fcidump and workdir is not None:
+            if inp.write_fcidump:
                 out.write(" Writing FCIDUMP file...\n")
-                write_fcidump(os.path.join(workdir, "FCIDUMP"), gpu.get_eri_mo(), inp.nbasis)
+                if workdir is not None:
+                    write_fcidump(os.path.join(workdir, "FCIDUMP"), gpu.get_eri_mo(), inp.nbasis)
                 out.write(" Done writing FCIDUMP file!\n")
             res.timings["mp2_s"] = time.perf_counter() - t0
+            out.write(_taken("restricted MP2", res.timings["mp2_s"]))
             if level >= 2:
                 t0 = time.perf_counter()
                 out.write(" ----------\n CCSD\n ----------\n")
@@ -369,6 +405,9 @@ def run(inp: ElsInput, gpu: AfespGpu | None = None, device: int = 0, verbose: bo
                 res.timings["ccsd_s"] = time.perf_counter() - t0
                 if restricted and res.ccsd_converged:
                     out.write(" T1 diagnostic: %8.5f\n" % res.t1_diagnostic)
+                    if res.t1_diagnostic > 0.02:   # src/ccsd.f90:374-376
+                        out.write(" Significant multireference character detected, CCSD result might be unreliable!\n")
+                out.write(_taken("restricted CCSD" if restricted else "unrestricted CCSD", res.timings["ccsd_s"]))
                 if level >= 3 and res.ccsd_converged:
                     t0 = time.perf_counter()
                     out.write(" ----------\n CCSD(T)\n ----------\n")
@@ -376,18 +415,84 @@ def run(inp: ElsInput, gpu: AfespGpu | None = None, device: int = 0, verbose: bo
                         sums, const = gpu.ccsd_t_spatial(paren, renorm, comp_renorm)
                         res.energies = assemble_triples(res.e_ccsd, sums, const, paren, renorm, comp_renorm)
                         res.energies["triples_sums"] = sums
+                        name = triples_calcname(paren, renorm, comp_renorm)
+                        out.write(" Restricted %s correlation energy (Hartree): %15.9f\n" % (
+                            name, highest_energy(res.energies, paren, renorm, comp_renorm)))
                     else:
                         res.energies = {"e_ccsd_t": res.e_ccsd + gpu.ccsd_t_spinorb()}
+                        name = "CCSD(T)"
+                        out.write(" Unrestricted CCSD(T) correlation energy (Hartree): %15.9f\n" % res.energies["e_ccsd_t"])
                     res.timings["triples_device_ms"] = gpu.last_stage_ms()
                     res.timings["triples_s"] = time.perf_counter() - t0
+                    out.write(_taken(("restricted " if restricted else "unrestricted ") + name, res.timings["triples_s"]))
         finally:
             if own:
                 gpu.close()
     out.write(final_table(inp, res))
+    now = time.localtime()
+    out.write(" " + "=" * 64 + "\n Finished running on %02d/%02d/%04d at %02d:%02d:%02d\n\n" % (
+        now.tm_mday, now.tm_mon, now.tm_year, now.tm_hour, now.tm_min, now.tm_sec))
     res.stdout = out.getvalue()
     if verbose:
         print(res.stdout)
     return res
+
+
+def highest_energy(en, paren, renorm, comp_renorm):
+    """sys%e_highest after do_ccsd_t_spatial (src/ccsd.f90:2252-2276): the last energy assigned."""
+    key = "e_ccsd_tt" if paren else "e_ccsd_t"
+    if renorm or comp_renorm:
+        key = "e_rccsd_tt" if paren else "e_rccsd_t"
+        if comp_renorm:
+            key = "e_crccsd_tt" if paren else "e_crccsd_t"
+    return en[key]
+
+
+def _es_f(x, width, digits):
+    """Fortran ESw.d for the system-information block (two-digit exponent)."""
+    return ("%" + str(width) + "." + str(digits) + "E") % x
+
+
+def header_block(inp: ElsInput, when=None) -> str:
+    """Program banner, integral read-in log, system information and the echo of els.in
+    (src/main.F90:26-32, src/integrals.f90:75-163, 223-249), byte for byte apart from the date."""
+    when = when or time.localtime()
+    L = [" " + "=" * 64, " A Fortran Electronic Structure Programme (AFESP)", " " + "=" * 64,
+         " Started running on %02d/%02d/%04d at %02d:%02d:%02d" % (when.tm_mday, when.tm_mon, when.tm_year, when.tm_hour,
+                                                                    when.tm_min, when.tm_sec),
+         " " + "-" * 16, " Integral read-in", " " + "-" * 16,
+         " Getting number of basis functions...", " Allocating integral store...", " Reading overlap matrix...",
+         " Reading kinetic integrals...", " Reading nuclear-electron integrals...", " Constructing core Hamiltonian...",
+         " Reading two-body integrals...", " Done reading integrals!",
+         " " + "-" * 20, " System information", " " + "-" * 20,
+         " Number of electrons: %d" % inp.nel, " Number of basis functions: %d" % inp.nbasis,
+         " Number of occupied orbitals: %d" % (inp.nel // 2),
+         " Number of virtual orbitals: %d" % (inp.nbasis - inp.nel // 2),
+         " E_nuc: " + _es_f(inp.e_nuc, 15, 8),
+         " scf_e_tol: " + _es_f(inp.scf_e_tol, 8, 2), " scf_d_tol: " + _es_f(inp.scf_d_tol, 8, 2),
+         " ccsd_e_tol: " + _es_f(inp.ccsd_e_tol, 8, 2), " ccsd_t_tol: " + _es_f(inp.ccsd_t_tol, 8, 2),
+         " Number of SCF DIIS error matrices: %d" % inp.scf_diis_n_errmat,
+         " Number of CCSD DIIS error matrices: %d" % inp.ccsd_diis_n_errmat,
+         " Maximum number of SCF iterations: %d" % inp.scf_maxiter,
+         " Maximum number of CCSD iterations: %d" % inp.ccsd_maxiter,
+         " Printing out the input file...", "-" * 30]
+    L += [ln.rstrip() for ln in inp.els_in_text.splitlines()]
+    L.append("-" * 30)
+    return "\n".join(L) + "\n"
+
+
+def _taken(label, seconds):
+    return " Time taken for %s: %7.4fs\n" % (label, seconds)
+
+
+def triples_calcname(paren, renorm, comp_renorm):
+    """calcname of src/ccsd.f90:2278-2287."""
+    name = "CCSD(T)" if paren else "CCSD[T]"
+    if renorm:
+        name = "renormalised " + name
+    if comp_renorm:
+        name = "completely renormalised " + name
+    return name
 
 
 def final_table(inp: ElsInput, r: ElsResult) -> str:

@@ -55,15 +55,17 @@ static void make_x_bar(int v, const double* x, double* xb) { /* src/ccsd.f90:231
 }
 
 /* out[0..3] = e_T, e_TT, D_T, D_TT over the listed ordered triples (no CR part). */
-void afesp_ref_triples(int o, int v, const double* t1, const double* t2, const double* t2r, const double* vvovv,
-                       const double* vovoo, const double* voovv, const double* eps, int ntri, const int* ijk,
-                       int doing_T, int doing_R, double* out) {
+/* amax < v restricts the outer virtual loop to a < amax (bounded timing sample of the same loop nest; the sums are then
+ * partial and only the time is meaningful). */
+void afesp_ref_triples_bounded(int o, int v, const double* t1, const double* t2, const double* t2r, const double* vvovv,
+                               const double* vovoo, const double* voovv, const double* eps, int ntri, const int* ijk,
+                               int doing_T, int doing_R, int amax, double* out) {
   double e_T = 0.0, e_TT = 0.0, D_T = 0.0, D_TT = 0.0;
   const size_t v3 = (size_t)v * v * v;
 #pragma omp parallel reduction(+ : e_T, e_TT, D_T, D_TT)
   {
-    double* w = (double*)malloc(v3 * sizeof(double));
-    double* t3 = (double*)malloc(v3 * sizeof(double));
+    double* w = (double*)calloc(v3, sizeof(double));
+    double* t3 = (double*)calloc(v3, sizeof(double));
     double* tb = (double*)malloc(v3 * sizeof(double));
     double* z3 = (double*)calloc(v3, sizeof(double));
     double* zb = (double*)calloc(v3, sizeof(double));
@@ -71,7 +73,7 @@ void afesp_ref_triples(int o, int v, const double* t1, const double* t2, const d
 #pragma omp for schedule(static, 1)
     for (int t = 0; t < ntri; ++t) {
       const int i = ijk[3 * t], j = ijk[3 * t + 1], k = ijk[3 * t + 2];
-      for (int a = 0; a < v; ++a)
+      for (int a = 0; a < amax; ++a)
         for (int b = 0; b < v; ++b)
           for (int c = 0; c < v; ++c) {
             double x = dotv(&T2R(0, a, j, i), &VVOVV(0, k, b, c), v) - dotv(&T2(0, i, b, a), &VOVOO(0, c, j, k), o) +
@@ -103,6 +105,12 @@ void afesp_ref_triples(int o, int v, const double* t1, const double* t2, const d
     free(w); free(t3); free(tb); free(z3); free(zb); free(y);
   }
   out[0] = e_T; out[1] = e_TT; out[2] = D_T; out[3] = D_TT;
+}
+
+void afesp_ref_triples(int o, int v, const double* t1, const double* t2, const double* t2r, const double* vvovv,
+                       const double* vovoo, const double* voovv, const double* eps, int ntri, const int* ijk,
+                       int doing_T, int doing_R, double* out) {
+  afesp_ref_triples_bounded(o, v, t1, t2, t2r, vvovv, vovoo, voovv, eps, ntri, ijk, doing_T, doing_R, v, out);
 }
 
 int afesp_ref_threads(void) { return omp_get_max_threads(); }

@@ -30,6 +30,9 @@ def load():
     lib.afesp_ref_ring.restype = None
     lib.afesp_ref_triples.argtypes = [C.c_int, C.c_int] + [_dp] * 7 + [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, _dp]
     lib.afesp_ref_triples.restype = None
+    lib.afesp_ref_triples_bounded.argtypes = ([C.c_int, C.c_int] + [_dp] * 7 +
+                                              [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, _dp])
+    lib.afesp_ref_triples_bounded.restype = None
     lib.afesp_ref_threads.restype = C.c_int
     return lib
 
@@ -52,8 +55,9 @@ def ring(lib, t2, I_ovov, asym, I_voov, bmax=None):
     return out, time.perf_counter() - t0
 
 
-def triples(lib, t1, t2, v_oovv, v_vvov, v_oovo, eps, ijk, paren, renorm):
-    """(e_T, e_TT, D_T, D_TT) over the listed ordered triples, reference loop (src/ccsd.f90:2152-2233)."""
+def triples(lib, t1, t2, v_oovv, v_vvov, v_oovo, eps, ijk, paren, renorm, amax=None):
+    """(e_T, e_TT, D_T, D_TT) over the listed ordered triples, reference loop (src/ccsd.f90:2152-2233).
+    amax: only the slab a < amax of the outer virtual loop (timing sample; the sums are then partial)."""
     o, v = t1.shape
     t2r = _F(t2.transpose(3, 2, 1, 0))
     vvovv = _F(v_vvov.transpose(3, 2, 1, 0))
@@ -63,8 +67,9 @@ def triples(lib, t1, t2, v_oovv, v_vvov, v_oovo, eps, ijk, paren, renorm):
     tri = np.ascontiguousarray(np.asarray(ijk, dtype=np.int32).reshape(-1, 3))
     out = np.zeros(4)
     t0 = time.perf_counter()
-    lib.afesp_ref_triples(o, v, _p(a1), _p(a2), _p(t2r), _p(vvovv), _p(vovoo), _p(a3), _p(e), tri.shape[0],
-                          tri.ctypes.data_as(C.POINTER(C.c_int)), int(paren), int(renorm), _p(out))
+    lib.afesp_ref_triples_bounded(o, v, _p(a1), _p(a2), _p(t2r), _p(vvovv), _p(vovoo), _p(a3), _p(e), tri.shape[0],
+                                  tri.ctypes.data_as(C.POINTER(C.c_int)), int(paren), int(renorm),
+                                  v if amax is None else int(amax), _p(out))
     return out, time.perf_counter() - t0
 
 

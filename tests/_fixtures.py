@@ -1,6 +1,7 @@
 """Load the committed sample-molecule fixtures (tests/golden/*.npz) into the oracle's System type."""
 import json
 import os
+import re
 
 import numpy as np
 
@@ -59,4 +60,52 @@ def load_els_input(name, calc_type=None):
     host.set_geometry(inp, z["geom"][:, 0], z["geom"][:, 1:])
     if inp.scf_read_guess and z["guess"].size:
         inp.guess = z["guess"]
+    inp.els_in_text = str(z["els_in"])
     return inp
+
+
+def golden_els_out(name):
+    with open(os.path.join(GOLDEN_DIR, f"{name}_els_out.txt")) as f:
+        return f.read()
+
+
+_NUM = re.compile(r"^[-+]?\d+\.\d+(E[-+]\d+)?$")
+
+
+def _mask(line):
+    """Drop what legitimately differs between two runs of the same program: dates and wall-clock times."""
+    if re.match(r"^ (Started|Finished) running on ", line):
+        return line.split(" on ")[0] + " on <date>"
+    if line.startswith(" Time taken"):
+        return line.split(":")[0] + ": <time>"
+    m = re.match(r"^(\s+\d+(?:\s+-?\d+\.\d+){3})\s+\d+\.\d+$", line)   # iteration row: last column is a time
+    return m.group(1) if m else line
+
+
+def compare_els_out(mine, ref, ulps=2.0):
+    """Line-by-line comparison of two program outputs: identical text and layout; numeric fields may differ by
+    `ulps` units of their last printed digit (rounding of independently computed doubles).  Returns a list of
+    differences (empty = same)."""
+    a, b = [_mask(x) for x in mine.splitlines()], [_mask(x) for x in ref.splitlines()]
+    diffs = []
+    if len(a) != len(b):
+        diffs.append(f"line count {len(a)} != {len(b)}")
+    for n, (x, y) in enumerate(zip(a, b), 1):
+        if x == y:
+            continue
+        tx, ty = x.split(), y.split()
+        ok = len(x) == len(y) and len(tx) == len(ty)
+        if ok:
+            for p, q in zip(tx, ty):
+                if p == q:
+                    continue
+                if not (_NUM.match(p) and _NUM.match(q)) or "E" in q:
+                    ok = False
+                    break
+                dec = len(q.split(".")[1])
+                if abs(float(p) - float(q)) > ulps * 10.0 ** (-dec) * 1.0000001:
+                    ok = False
+                    break
+        if not ok:
+            diffs.append(f"{n}: {x!r} != {y!r}")
+    return diffs

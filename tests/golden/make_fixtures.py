@@ -95,7 +95,11 @@ def main():
                             geom=geom, guess=guess, els_in=np.array(els_in), guess_out=guess_out,
                             guess_out_head=np.array(guess_out_head))
         with open(os.path.join(d, outname)) as f:
-            golden[name] = parse_out(f.read())
+            out_text = f.read()
+        golden[name] = parse_out(out_text)
+        if outname == "els.out":   # program output of the current code version, kept verbatim for the layout tests
+            with open(os.path.join(HERE, f"{name}_els_out.txt"), "w") as f:
+                f.write(out_text)
         golden[name]["source"] = f"{rel}/{outname}"
         print(name, n, len(golden[name]["scf"]), len(golden[name]["ccsd"]), sorted(golden[name]["final"])[:3])
     with open(os.path.join(HERE, "golden.json"), "w") as f:

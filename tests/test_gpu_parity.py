@@ -126,6 +126,24 @@ def test_crccsd_t_spatial_matches_shipped_els_out(gpu, name):
         assert label in res.stdout
 
 
+@pytest.mark.parametrize("name", ["n2", "f2"])
+def test_whole_program_output_matches_shipped_els_out(gpu, name, tmp_path):
+    """els.out of the drop-in (Python host + GPU library) against the file the reference shipped for the same
+    inputs: same lines, same layout, every printed number equal to within 2 units of its last printed digit
+    (12 decimals in the CCSD table, 10 in the final table); only dates and wall-clock times are masked.
+    Also writes guess_out.dat into the run directory as the reference does (scf_write_guess)."""
+    import os
+
+    from afesp_b200 import host
+    from tests._fixtures import compare_els_out, golden_els_out
+
+    inp = load_els_input(name)
+    res = host.run(inp, gpu=gpu, workdir=str(tmp_path))
+    diffs = compare_els_out(res.stdout, golden_els_out(name), ulps=2.0)
+    assert diffs == [], "\n".join(diffs[:20])
+    assert os.path.exists(tmp_path / "guess_out.dat") == bool(inp.scf_write_guess)
+
+
 @pytest.mark.parametrize("calc", ["CCSD(T)_spatial", "CCSD[T]_spatial", "RCCSD(T)_spatial", "RCCSD[T]_spatial",
                                   "CRCCSD[T]_spatial"])
 def test_spatial_calc_types_match_oracle(gpu, calc, oracle_runs):

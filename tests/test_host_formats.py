@@ -62,3 +62,16 @@ def test_fcidump_format_order_and_threshold(tmp_path):
     pq = P * (P - 1) // 2 + Q
     rs = R * (R - 1) // 2 + S
     assert np.array_equal(pq * (pq - 1) // 2 + rs - 1, np.arange(mo.size))
+
+
+def test_program_output_up_to_the_hot_path_matches_the_shipped_els_out():
+    """Banner, read-in log, system information, els.in echo, the whole SCF section (12 iteration rows, orbital
+    energies) of sample_data/n2-cc-pvdz/2.00_0.00/els.out, byte for byte apart from dates and times."""
+    from tests._fixtures import compare_els_out, golden_els_out
+
+    inp = load_els_input("n2", calc_type="RHF")
+    inp.els_in_text = inp.els_in_text  # echoed verbatim (calc_type line included as shipped)
+    mine = host.run(inp).stdout.splitlines()
+    ref = golden_els_out("n2").splitlines()
+    stop = next(i for i, ln in enumerate(ref) if ln.startswith(" Time taken for restricted Hartree-Fock")) + 1
+    assert compare_els_out("\n".join(mine[:stop]), "\n".join(ref[:stop]), ulps=0.0) == []
