@@ -609,6 +609,8 @@ int afesp_gpu_bench_hbm(afesp_handle hv, const char* what, int o, int v, int rep
       run = [=, &a, &b] { permute(st, 4, dims, perm, 1.0, a.p, acc ? 1.0 : 0.0, b.p); };
     } else if (w == "divide") {
       run = [=, &a, &b, &eo, &ev] { divide_d2(st, b.p, a.p, eo.p, ev.p, o, v); };
+    } else if (w == "divide_probe") {
+      run = [=, &a, &b, &eo, &ev] { divide_d2_probe(st, b.p, a.p, eo.p, ev.p, o, v); };
     } else if (w == "energy") {
       per = 24.0;
       run = [=, &a, &b, &c, &t1, &h] { cc_energy_restricted(h.s.eng, a.p, b.p, t1.p, c.p, o, v, h.s.red_out.p); };

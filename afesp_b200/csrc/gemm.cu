@@ -376,7 +376,7 @@ void launch_by_cfg(int cfg, cudaStream_t st, const Params& p, int nbatch, bool a
   }
 }
 
-int choose_cfg(int M, int N, int nbatch, long long* tiles_out) {
+int choose_cfg(int M, int N, int nbatch, long long* tiles_out, bool tma_ok) {
   int best = 0;
   double best_score = -1.0;
   const double sms = num_sms();
@@ -388,7 +388,9 @@ int choose_cfg(int M, int N, int nbatch, long long* tiles_out) {
     const double slots = sms * t.occ;
     const double waves = std::ceil(tiles / slots);
     const double fill = tiles / (waves * slots);
-    const double score = t.eff * useful * fill;
+    // the 64x64 tile runs through the TMA-staged kernel when the operands are aligned: 92% instead of 87% (profiles/)
+    const double eff = (c == 3 && tma_ok) ? 0.92 : t.eff;
+    const double score = eff * useful * fill;
     if (score > best_score) { best_score = score; best = c; if (tiles_out) *tiles_out = tiles; }
   }
   return best;
@@ -431,7 +433,8 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
 
   // tile selection (see kCfg)
   long long tiles = 0;
-  int cfg = choose_cfg(M, N, nbatch, &tiles);
+  const bool tma_ok = vec2 && (!batch || !(batch->Aptr || batch->Bptr) || (batch->Abase && batch->Bbase));
+  int cfg = choose_cfg(M, N, nbatch, &tiles, tma_ok);
   if (g_force_cfg >= 0 && g_force_cfg < NCFG) {
     cfg = g_force_cfg;
     tiles = (long long)((M + kCfg[cfg].bm - 1) / kCfg[cfg].bm) * ((N + kCfg[cfg].bn - 1) / kCfg[cfg].bn) * nbatch;

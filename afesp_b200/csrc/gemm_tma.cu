@@ -16,6 +16,7 @@
 #include <cuda.h>
 
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -163,46 +164,51 @@ __global__ void __launch_bounds__(NT, 3) gemm_f64_tma(const __grid_constant__ CU
   }
   // fragments of this warp that intersect C (warp-uniform)
   const int mfr = min(4, max(0, (p.M - (m0 + wm0) + 7) >> 3)), nfr = min(4, max(0, (p.N - (n0 + wn0) + 7) >> 3));
-  const bool full_tile = (mfr == 4) && (nfr == 4);
-  for (int kt = 0; kt < nk; ++kt) {
-    const int s = kt % STAGES;
-    mbar_wait(&full[s], (kt / STAGES) & 1);
-    const unsigned char* sa = smem + s * STAGE_BYTES;
-    const unsigned char* sb = sa + TILE_BYTES;
-    if (full_tile) {
+  // Edge tiles: 8-row / 8-column fragments that lie entirely outside C issue no DMMA, which leaves the tensor pipe of
+  // this SM sub-partition to the warps of the co-resident CTAs (M = 360 on 64-row tiles: 6.25% less work).  The loop is
+  // instantiated per row-fragment count so that interior tiles run exactly the unconditional code.
+  auto mainloop = [&](auto mf_tag, auto nedge_tag) {
+    constexpr int MFR = decltype(mf_tag)::value;
+    constexpr bool NEDGE = decltype(nedge_tag)::value;
+    for (int kt = 0; kt < nk; ++kt) {
+      const int s = kt % STAGES;
+      mbar_wait(&full[s], (kt / STAGES) & 1);
+      const unsigned char* sa = smem + s * STAGE_BYTES;
+      const unsigned char* sb = sa + TILE_BYTES;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         double af[4], bf[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) af[i] = *reinterpret_cast<const double*>(sa + aoff[g][i]);
+        for (int i = 0; i < MFR; ++i) af[i] = *reinterpret_cast<const double*>(sa + aoff[g][i]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) bf[j] = *reinterpret_cast<const double*>(sb + boff[g][j]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < MFR; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+          for (int j = 0; j < 4; ++j)
+            if (!NEDGE || j < nfr) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
       }
-    } else {
-      // edge tile: 8-row / 8-column fragments that lie entirely outside C issue no DMMA, which leaves the tensor
-      // pipe of this SM sub-partition to the warps of the co-resident CTAs (M = 360 on 64-row tiles: 6.25% less work)
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        double af[4], bf[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) af[i] = *reinterpret_cast<const double*>(sa + aoff[g][i]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) bf[j] = *reinterpret_cast<const double*>(sb + boff[g][j]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < mfr) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j < nfr) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-          }
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
+  };
+  using std::integral_constant;
+  if (nfr == 4) {
+    switch (mfr) {
+      case 4: mainloop(integral_constant<int, 4>{}, integral_constant<bool, false>{}); break;
+      case 3: mainloop(integral_constant<int, 3>{}, integral_constant<bool, false>{}); break;
+      case 2: mainloop(integral_constant<int, 2>{}, integral_constant<bool, false>{}); break;
+      case 1: mainloop(integral_constant<int, 1>{}, integral_constant<bool, false>{}); break;
+      default: mainloop(integral_constant<int, 0>{}, integral_constant<bool, false>{}); break;
+    }
+  } else {
+    switch (mfr) {
+      case 4: mainloop(integral_constant<int, 4>{}, integral_constant<bool, true>{}); break;
+      case 3: mainloop(integral_constant<int, 3>{}, integral_constant<bool, true>{}); break;
+      case 2: mainloop(integral_constant<int, 2>{}, integral_constant<bool, true>{}); break;
+      case 1: mainloop(integral_constant<int, 1>{}, integral_constant<bool, true>{}); break;
+      default: mainloop(integral_constant<int, 0>{}, integral_constant<bool, true>{}); break;
+    }
   }
 
   // ---------------- epilogue (same fragment ownership as gemm_f64_dmma) ----------------

@@ -12,6 +12,135 @@ inline int grid_for(long long n, int block = 256) {
   return (int)std::max<long long>(1, std::min<long long>(b, 148LL * 16));
 }
 
+// ---- division-free walk over an (o,o,v,v) array --------------------------------------------------------------------
+// These kernels move 16-24 B per element, so the per-element index arithmetic decides whether they run at HBM speed:
+// a 64-bit idx -> (i,j,a,b) decode (four integer divisions) costs several times the memory time.  Instead each block
+// takes chunks of OOVV_CHUNK consecutive (a,b) pairs -- a contiguous run of CHUNK*o^2 doubles -- and keeps in shared
+// memory (i, j) for every ij of the o^2 plane and (a, b) for every pair of the chunk, filled with a handful of divisions
+// per block.  A thread then steps through the run with e += blockDim.x and updates (ij, pair) by compare-and-subtract.
+constexpr int OOVV_T = 256, OOVV_CHUNK = 32;
+constexpr int OOVV_MAX_OO = 3600;   // o <= 60 (tables stay under the 48 KB default dynamic shared memory); larger planes take the generic kernels below
+
+struct OovvTables {
+  unsigned short* i;   // [oo]
+  unsigned short* j;   // [oo]
+  unsigned short* a;   // [CHUNK]
+  unsigned short* b;   // [CHUNK]
+  double* eoo;         // [oo]     eo_i + eo_j   (optional)
+  double* evv;         // [CHUNK]  ev_a + ev_b   (optional)
+};
+
+__host__ __device__ inline size_t oovv_smem_bytes(int oo, bool energies) {
+  return (size_t)(energies ? (oo + OOVV_CHUNK) * sizeof(double) : 0) + (size_t)(2 * oo + 2 * OOVV_CHUNK) * sizeof(unsigned short);
+}
+
+template <bool ENERGIES, int UNROLL, class F>
+__device__ __forceinline__ void oovv_walk(int o, int v, const double* __restrict__ eo, const double* __restrict__ ev,
+                                          F&& f) {
+  extern __shared__ __align__(16) unsigned char oovv_sm[];
+  const int oo = o * o;
+  const long long vv = (long long)v * v;
+  OovvTables t;
+  unsigned char* q = oovv_sm;
+  t.eoo = reinterpret_cast<double*>(q); q += ENERGIES ? oo * sizeof(double) : 0;
+  t.evv = reinterpret_cast<double*>(q); q += ENERGIES ? OOVV_CHUNK * sizeof(double) : 0;
+  t.i = reinterpret_cast<unsigned short*>(q); q += oo * sizeof(unsigned short);
+  t.j = reinterpret_cast<unsigned short*>(q); q += oo * sizeof(unsigned short);
+  t.a = reinterpret_cast<unsigned short*>(q); q += OOVV_CHUNK * sizeof(unsigned short);
+  t.b = reinterpret_cast<unsigned short*>(q);
+  const int tid = threadIdx.x;
+  for (int ij = tid; ij < oo; ij += OOVV_T) {
+    const int jj = ij / o, ii = ij - jj * o;
+    t.i[ij] = (unsigned short)ii; t.j[ij] = (unsigned short)jj;
+    if (ENERGIES) t.eoo[ij] = eo[ii] + eo[jj];
+  }
+  const int ij0 = tid % oo, c0 = tid / oo;   // position of this thread's first element inside a chunk
+  for (long long ab0 = (long long)blockIdx.x * OOVV_CHUNK; ab0 < vv; ab0 += (long long)gridDim.x * OOVV_CHUNK) {
+    const int nab = (int)min((long long)OOVV_CHUNK, vv - ab0);
+    __syncthreads();   // previous chunk fully consumed (and the ij tables written, first time round)
+    if (tid < nab) {
+      const long long ab = ab0 + tid;
+      const int bb = (int)(ab / v), aa = (int)(ab - (long long)bb * v);
+      t.a[tid] = (unsigned short)aa; t.b[tid] = (unsigned short)bb;
+      if (ENERGIES) t.evv[tid] = ev[aa] + ev[bb];
+    }
+    __syncthreads();
+    const long long base = ab0 * oo;
+    const int n = nab * oo;
+    int ij = ij0, c = c0;
+    int e = tid;
+    // four elements per trip: the positions come first so that the four independent loads can be in flight together
+    if (UNROLL > 1) {
+      for (; e + (UNROLL - 1) * OOVV_T < n; e += UNROLL * OOVV_T) {
+        int ijs[UNROLL], cs[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          ijs[u] = ij; cs[u] = c;
+          ij += OOVV_T;
+          while (ij >= oo) { ij -= oo; ++c; }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) f(base + e + u * OOVV_T, ijs[u], cs[u], t);
+      }
+    }
+    for (; e < n; e += OOVV_T) {
+      f(base + e, ij, c, t);
+      ij += OOVV_T;
+      while (ij >= oo) { ij -= oo; ++c; }
+    }
+  }
+}
+
+inline int oovv_grid(int v) {
+  const long long chunks = ((long long)v * v + OOVV_CHUNK - 1) / OOVV_CHUNK;
+  return (int)std::max<long long>(1, std::min<long long>(chunks, 148LL * 8));
+}
+
+// x / d for energy denominators.  The IEEE division sequence (reciprocal seed, Newton steps, residual fix-up and
+// its special-case slow path) costs more issue slots than the two 8-byte streams of the divide kernel take to move
+// (measured: 63% of the copy peak with '/', 93% with a multiplication in its place).  Orbital-energy denominators are
+// O(1) numbers well inside the float range, so: single-precision reciprocal seed (one MUFU), two Newton steps in double
+// (relative error ~2^-90), quotient, one residual correction -- the result is the correctly rounded quotient except for
+// rare last-bit ties.  Anything outside [2^-100, 2^100] takes the ordinary division.
+__device__ __forceinline__ double div_denominator(double x, double d) {
+  const double ad = fabs(d);
+  if (!(ad > 7.9e-31 && ad < 1.2e30)) return x / d;
+  double r = (double)__frcp_rn((float)d);
+  r = fma(fma(-d, r, 1.0), r, r);
+  r = fma(fma(-d, r, 1.0), r, r);
+  const double q = x * r;
+  return fma(fma(-d, q, x), r, q);
+}
+
+__global__ void __launch_bounds__(OOVV_T) k_divide_d2_fast(double* __restrict__ out, const double* __restrict__ x,
+                                                            const double* __restrict__ eo, const double* __restrict__ ev,
+                                                            int o, int v) {
+  oovv_walk<true, 4>(o, v, eo, ev, [&](long long idx, int ij, int c, const OovvTables& t) {
+    out[idx] = div_denominator(x[idx], t.eoo[ij] - t.evv[c]);
+  });
+}
+
+// Diagnostic twin of k_divide_d2_fast (afesp_gpu_bench_hbm "divide_probe"): the same walk and traffic with the FP64
+// division replaced by a multiplication, to separate the cost of the division from the cost of the walk.
+__global__ void __launch_bounds__(OOVV_T) k_divide_d2_probe(double* __restrict__ out, const double* __restrict__ x,
+                                                             const double* __restrict__ eo, const double* __restrict__ ev,
+                                                             int o, int v) {
+  oovv_walk<true, 4>(o, v, eo, ev, [&](long long idx, int ij, int c, const OovvTables& t) {
+    out[idx] = x[idx] * (t.eoo[ij] - t.evv[c]);
+  });
+}
+
+__global__ void __launch_bounds__(OOVV_T) k_t2_plus_t1t1_fast(double* __restrict__ out, const double* __restrict__ t2,
+                                                               const double* __restrict__ t1, int o, int v, double ca,
+                                                               double cb) {
+  oovv_walk<false, 4>(o, v, nullptr, nullptr, [&](long long idx, int ij, int c, const OovvTables& t) {
+    const int i = t.i[ij], j = t.j[ij], a = t.a[c], b = t.b[c];
+    double r = t2[idx] + ca * t1[i + o * a] * t1[j + o * b];
+    if (cb != 0.0) r += cb * t1[i + o * b] * t1[j + o * a];
+    out[idx] = r;
+  });
+}
+
 __global__ void k_divide_d2(double* __restrict__ out, const double* __restrict__ x, const double* __restrict__ eo,
                             const double* __restrict__ ev, int o, int v) {
   const long long oo = (long long)o * o, total = oo * v * v;
@@ -155,6 +284,29 @@ __global__ void __launch_bounds__(RB) k_energy_spinorb(const double* __restrict_
   block_reduce_store<2>(acc, partials);
 }
 
+// Energy + amplitude-change norm in one pass over the (o,o,v,v) arrays, division-free walk (see oovv_walk).
+template <bool SPINORB>
+__global__ void __launch_bounds__(OOVV_T) k_energy_fast(const double* __restrict__ vo, const double* __restrict__ t2,
+                                                         const double* __restrict__ t1, const double* __restrict__ t2_old,
+                                                         int o, int v, double* __restrict__ partials) {
+  double acc[2] = {0.0, 0.0};
+  const long long oo = (long long)o * o;
+  oovv_walk<false, 1>(o, v, nullptr, nullptr, [&](long long idx, int ij, int c, const OovvTables& t) {
+    const int i = t.i[ij], j = t.j[ij], a = t.a[c], b = t.b[c];
+    const double tv = t2[idx];
+    if (SPINORB) {
+      acc[0] += 0.25 * vo[idx] * (tv + 2.0 * t1[i + o * a] * t1[j + o * b]);
+    } else {
+      const double vx = vo[ij + oo * (b + (long long)v * a)];
+      acc[0] += (2.0 * vo[idx] - vx) * (tv + t1[i + o * a] * t1[j + o * b]);
+    }
+    const double d = tv - t2_old[idx];
+    acc[1] += d * d;
+  });
+  __syncthreads();
+  block_reduce_store<2>(acc, partials);
+}
+
 template <int NX>
 __global__ void k_lincomb(long long n, PtrPack xs, double* __restrict__ y) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -168,7 +320,17 @@ __global__ void k_lincomb(long long n, PtrPack xs, double* __restrict__ y) {
 }  // namespace
 
 void divide_d2(cudaStream_t st, double* out, const double* x, const double* eo, const double* ev, int o, int v) {
+  if (o * o <= OOVV_MAX_OO && v < 65536) {
+    k_divide_d2_fast<<<oovv_grid(v), OOVV_T, oovv_smem_bytes(o * o, true), st>>>(out, x, eo, ev, o, v);
+    count_launch();
+    return;
+  }
   k_divide_d2<<<grid_for((long long)o * o * v * v), 256, 0, st>>>(out, x, eo, ev, o, v);
+  count_launch();
+}
+void divide_d2_probe(cudaStream_t st, double* out, const double* x, const double* eo, const double* ev, int o, int v) {
+  AFESP_REQUIRE(o * o <= OOVV_MAX_OO && v < 65536, "divide probe: shape outside the fast path");
+  k_divide_d2_probe<<<oovv_grid(v), OOVV_T, oovv_smem_bytes(o * o, true), st>>>(out, x, eo, ev, o, v);
   count_launch();
 }
 void divide_d1(cudaStream_t st, double* out, const double* x, const double* eo, const double* ev, int o, int v) {
@@ -177,6 +339,11 @@ void divide_d1(cudaStream_t st, double* out, const double* x, const double* eo, 
 }
 void t2_plus_t1t1(cudaStream_t st, double* out, const double* t2, const double* t1, int o, int v, double ca,
                   double cb) {
+  if (o * o <= OOVV_MAX_OO && v < 65536) {
+    k_t2_plus_t1t1_fast<<<oovv_grid(v), OOVV_T, oovv_smem_bytes(o * o, false), st>>>(out, t2, t1, o, v, ca, cb);
+    count_launch();
+    return;
+  }
   k_t2_plus_t1t1<<<grid_for((long long)o * o * v * v), 256, 0, st>>>(out, t2, t1, o, v, ca, cb);
   count_launch();
 }
@@ -225,8 +392,12 @@ void dotn(Engine& e, long long n, int nx, const double* const* xp, const double*
 void cc_energy_restricted(Engine& e, const double* v_oovv, const double* t2, const double* t1, const double* t2_old,
                           int o, int v, double* out) {
   int nb = std::min(grid_for((long long)o * o * v * v, RB), 1024);
+  if (o * o <= OOVV_MAX_OO && v < 65536) nb = oovv_grid(v);
   double* part = reduce_scratch(e, (size_t)nb * 2);
-  k_energy_restricted<<<nb, RB, 0, e.stream>>>(v_oovv, t2, t1, t2_old, o, v, part);
+  if (o * o <= OOVV_MAX_OO && v < 65536)
+    k_energy_fast<false><<<nb, OOVV_T, oovv_smem_bytes(o * o, false), e.stream>>>(v_oovv, t2, t1, t2_old, o, v, part);
+  else
+    k_energy_restricted<<<nb, RB, 0, e.stream>>>(v_oovv, t2, t1, t2_old, o, v, part);
   count_launch();
   finish_partials(e, part, nb, 2, out);
 }
@@ -234,8 +405,12 @@ void cc_energy_restricted(Engine& e, const double* v_oovv, const double* t2, con
 void cc_energy_spinorb(Engine& e, const double* oovv, const double* t2, const double* t1, const double* t2_old, int o,
                        int v, double* out) {
   int nb = std::min(grid_for((long long)o * o * v * v, RB), 1024);
+  if (o * o <= OOVV_MAX_OO && v < 65536) nb = oovv_grid(v);
   double* part = reduce_scratch(e, (size_t)nb * 2);
-  k_energy_spinorb<<<nb, RB, 0, e.stream>>>(oovv, t2, t1, t2_old, o, v, part);
+  if (o * o <= OOVV_MAX_OO && v < 65536)
+    k_energy_fast<true><<<nb, OOVV_T, oovv_smem_bytes(o * o, false), e.stream>>>(oovv, t2, t1, t2_old, o, v, part);
+  else
+    k_energy_spinorb<<<nb, RB, 0, e.stream>>>(oovv, t2, t1, t2_old, o, v, part);
   count_launch();
   finish_partials(e, part, nb, 2, out);
 }

@@ -7,6 +7,7 @@ namespace afesp {
 // out(i,j,a,b) = x(i,j,a,b) / (eo_i + eo_j - ev_a - ev_b); out(i,a) = x(i,a)/(eo_i - ev_a).
 // Denominators come from the orbital energies on the fly (the reference materialises D_ijab, src/ccsd.f90:431-457).
 void divide_d2(cudaStream_t st, double* out, const double* x, const double* eo, const double* ev, int o, int v);
+void divide_d2_probe(cudaStream_t st, double* out, const double* x, const double* eo, const double* ev, int o, int v);  // diagnostic
 void divide_d1(cudaStream_t st, double* out, const double* x, const double* eo, const double* ev, int o, int v);
 
 // out(i,j,a,b) = t2(i,j,a,b) + ca * t1(i,a) t1(j,b) + cb * t1(i,b) t1(j,a)

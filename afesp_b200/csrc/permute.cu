@@ -7,6 +7,8 @@
 //   * axis 0 moved      -> 32x32 shared-memory tile transpose over (input-fastest, output-fastest) axes so that
 //                          both the global read and the global write are coalesced 256-byte rows.
 // Adjacent axes that stay adjacent are merged first, so e.g. (i,j,a,b)->(a,b,i,j) runs as a 2-D transpose.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace afesp {
@@ -90,6 +92,166 @@ __global__ void permute_transpose(const TransParams p, const double* __restrict_
   }
 }
 
+// Axis 0 preserved, row form: a "row" is one run of the (merged) fastest axis, contiguous in both arrays.  Threads
+// walk along the row; the row index is decoded once per row and thread (32-bit arithmetic), not once per element.
+struct RowParams {
+  int n0;                    // row length
+  int nrest;
+  int rdims[MAXR];
+  long long ristr[MAXR], rostr[MAXR];
+  long long rows;
+  double alpha, beta;
+};
+
+template <int RX>   // threads along the row; 256 / RX rows per block pass
+__global__ void __launch_bounds__(256) permute_rows(const RowParams p, const double* __restrict__ in,
+                                                    double* __restrict__ out) {
+  constexpr int RY = 256 / RX;
+  const int tx = threadIdx.x % RX, ty = threadIdx.x / RX;
+  for (long long row = (long long)blockIdx.x * RY + ty; row < p.rows; row += (long long)gridDim.x * RY) {
+    long long ib = 0, ob = 0;
+    if (p.rows < (1LL << 31)) {
+      unsigned rem = (unsigned)row;
+      for (int d = 0; d < p.nrest; ++d) {
+        const unsigned q = rem / (unsigned)p.rdims[d], c = rem - q * (unsigned)p.rdims[d];
+        ib += c * p.ristr[d]; ob += c * p.rostr[d];
+        rem = q;
+      }
+    } else {
+      long long rem = row;
+      for (int d = 0; d < p.nrest; ++d) {
+        const long long q = rem / p.rdims[d], c = rem - q * p.rdims[d];
+        ib += c * p.ristr[d]; ob += c * p.rostr[d];
+        rem = q;
+      }
+    }
+    const double* src = in + ib;
+    double* dst = out + ob;
+    if (p.beta == 0.0) {
+      for (int x = tx; x < p.n0; x += RX) dst[x] = p.alpha * src[x];
+    } else {
+      for (int x = tx; x < p.n0; x += RX) dst[x] = p.alpha * src[x] + p.beta * dst[x];
+    }
+  }
+}
+
+// Leading axes shuffled among themselves, small slab: the first k (merged) axes of the output are a permutation of
+// the first k axes of the input and hold S <= 4096 elements, so every slab is one contiguous run in both arrays
+// (e.g. (i,j,a,b) -> (j,i,a,b) with o <= 64).  A block stages G slabs through shared memory with fully coalesced
+// loads and stores; the in-slab permutation is a table built once per block; slab bases are decoded once per slab.
+struct SlabParams {
+  int k;
+  int sdims[MAXR];     // output extents of the slab axes
+  int sistr[MAXR];     // input stride (inside the slab) of the axis feeding output slab axis d
+  int S, G;
+  int nrest;
+  int rdims[MAXR];
+  long long ristr[MAXR], rostr[MAXR];
+  long long rest_total;
+  double alpha, beta;
+};
+
+__global__ void __launch_bounds__(256) permute_slab(const SlabParams p, const double* __restrict__ in,
+                                                    double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char slab_sm[];
+  double* buf = reinterpret_cast<double*>(slab_sm);                       // [G*S]
+  long long* ibase = reinterpret_cast<long long*>(buf + (size_t)p.G * p.S);  // [G]
+  long long* obase = ibase + p.G;                                         // [G]
+  int* tab = reinterpret_cast<int*>(obase + p.G);                         // [S]
+  const int tid = threadIdx.x, S = p.S;
+  for (int s = tid; s < S; s += 256) {
+    int rem = s, off = 0;
+    for (int d = 0; d < p.k; ++d) {
+      const int q = rem / p.sdims[d], c = rem - q * p.sdims[d];
+      off += c * p.sistr[d];
+      rem = q;
+    }
+    tab[s] = off;
+  }
+  const int s0 = tid % S, g0 = tid / S;
+  for (long long slab0 = (long long)blockIdx.x * p.G; slab0 < p.rest_total; slab0 += (long long)gridDim.x * p.G) {
+    const int ng = (int)min((long long)p.G, p.rest_total - slab0);
+    __syncthreads();
+    for (int t = tid; t < ng; t += 256) {
+      long long rem = slab0 + t, ib = 0, ob = 0;
+      for (int d = 0; d < p.nrest; ++d) {
+        const long long q = rem / p.rdims[d], c = rem - q * p.rdims[d];
+        ib += c * p.ristr[d]; ob += c * p.rostr[d];
+        rem = q;
+      }
+      ibase[t] = ib; obase[t] = ob;
+    }
+    __syncthreads();
+    const int n = ng * S;
+    int s = s0, g = g0;
+    int e = tid;
+    for (; e + 3 * 256 < n; e += 4 * 256) {   // four independent loads in flight per thread
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u] = in[ibase[g] + s];
+        s += 256;
+        while (s >= S) { s -= S; ++g; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) buf[e + u * 256] = v[u];
+    }
+    for (; e < n; e += 256) {
+      buf[e] = in[ibase[g] + s];
+      s += 256;
+      while (s >= S) { s -= S; ++g; }
+    }
+    __syncthreads();
+    s = s0; g = g0;
+    for (int e = tid; e < n; e += 256) {
+      double* o = out + obase[g] + s;
+      double v = p.alpha * buf[g * S + tab[s]];
+      if (p.beta != 0.0) v += p.beta * (*o);
+      *o = v;
+      s += 256;
+      while (s >= S) { s -= S; ++g; }
+    }
+  }
+}
+
+// 64x64 shared-memory tile transpose (512-byte rows on both sides), used when both transposed extents are >= 48.
+__global__ void __launch_bounds__(256) permute_transpose64(const TransParams p, const double* __restrict__ in,
+                                                           double* __restrict__ out) {
+  __shared__ double tile[64][65];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 x 4
+  const int i0 = blockIdx.x * 64;
+  const int tiles_b = (p.nb + 63) / 64;
+  for (int by = blockIdx.y; by < tiles_b; by += gridDim.y)
+  for (long long rest = blockIdx.z; rest < p.rest_total; rest += gridDim.z) {
+    const int b0 = by * 64;
+    long long rem = rest, ibase = 0, obase = 0;
+    for (int d = 0; d < p.nrest; ++d) {
+      long long q = rem / p.rdims[d];
+      long long c = rem - q * p.rdims[d];
+      ibase += c * p.ristr[d];
+      obase += c * p.rostr[d];
+      rem = q;
+    }
+#pragma unroll 4
+    for (int r = ty; r < 64; r += 4) {
+      const int i = i0 + tx, b = b0 + r;
+      if (i < p.n0 && b < p.nb) tile[r][tx] = in[ibase + i + (long long)b * p.istr_b];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = ty; r < 64; r += 4) {
+      const int i = i0 + r, b = b0 + tx;
+      if (i < p.n0 && b < p.nb) {
+        double* o = out + obase + b + (long long)i * p.ostr_0;
+        double v = p.alpha * tile[tx][r];
+        if (p.beta != 0.0) v += p.beta * (*o);
+        *o = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 void permute(cudaStream_t st, int rank, const int* dims, const int* perm, double alpha, const double* in, double beta,
@@ -141,13 +303,67 @@ void permute_strided(cudaStream_t st, int rank, const int* dims, const int* perm
   if (r == 0) { odims[0] = 1; istr[0] = 1; ostr_d[0] = 1; r = 1; }
   AFESP_REQUIRE(ostr_d[0] == 1, "permute: leading output axis must have unit stride");
   if (istr[0] == 1) {
-    PermParams p{};
-    p.rank = r;
-    for (int d = 0; d < r; ++d) { p.odims[d] = odims[d]; p.istr[d] = istr[d]; p.ostr[d] = ostr_d[d]; }
-    p.total = total; p.alpha = alpha; p.beta = beta;
-    int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
-    permute_gather<<<blocks, 256, 0, st>>>(p, in, out);
+    // axis 0 preserved: rows of odims[0] contiguous elements on both sides
+    RowParams p{};
+    p.n0 = odims[0];
+    p.nrest = r - 1;
+    p.rows = 1;
+    for (int d = 1; d < r; ++d) {
+      p.rdims[d - 1] = odims[d]; p.ristr[d - 1] = istr[d]; p.rostr[d - 1] = ostr_d[d];
+      p.rows *= odims[d];
+    }
+    p.alpha = alpha; p.beta = beta;
+    // threads along the row: the width that wastes the fewest lanes in the last pass (ties go to the wider one)
+    int rx = 32;
+    double best = -1.0;
+    for (int w : {256, 128, 64, 32}) {
+      const double eff = (double)p.n0 / ((double)((p.n0 + w - 1) / w) * w);
+      if (eff > best + 1e-9) { best = eff; rx = w; }
+    }
+    const long long passes = (p.rows + (256 / rx) - 1) / (256 / rx);
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(passes, 148LL * 16));
+    switch (rx) {
+      case 256: permute_rows<256><<<blocks, 256, 0, st>>>(p, in, out); break;
+      case 128: permute_rows<128><<<blocks, 256, 0, st>>>(p, in, out); break;
+      case 64: permute_rows<64><<<blocks, 256, 0, st>>>(p, in, out); break;
+      default: permute_rows<32><<<blocks, 256, 0, st>>>(p, in, out); break;
+    }
   } else {
+    // slab form?  smallest k >= 2 whose k leading output axes are exactly the k leading input axes, densely packed
+    int kslab = 0;
+    long long S = 1;
+    for (int k = 2; k <= r && kslab == 0; ++k) {
+      bool dense_out = true;
+      long long acc = 1;
+      for (int d = 0; d < k; ++d) { dense_out = dense_out && (ostr_d[d] == acc); acc *= odims[d]; }
+      if (!dense_out || acc > 4000) break;   // buffer + table + bases must fit the 48 KB default dynamic shared memory
+      // input side: the same axes, sorted by input stride, must tile [0, acc) densely
+      int idx[MAXR];
+      for (int d = 0; d < k; ++d) idx[d] = d;
+      std::sort(idx, idx + k, [&](int a, int b) { return istr[a] < istr[b]; });
+      long long exp = 1;
+      bool dense_in = true;
+      for (int m = 0; m < k; ++m) { dense_in = dense_in && (istr[idx[m]] == exp); exp *= odims[idx[m]]; }
+      if (dense_in) { kslab = k; S = acc; }
+    }
+    if (kslab > 0) {
+      SlabParams p{};
+      p.k = kslab; p.S = (int)S; p.G = (int)std::max<long long>(1, 4000 / S);
+      for (int d = 0; d < kslab; ++d) { p.sdims[d] = odims[d]; p.sistr[d] = (int)istr[d]; }
+      p.nrest = r - kslab; p.rest_total = 1;
+      for (int d = kslab; d < r; ++d) {
+        p.rdims[d - kslab] = odims[d]; p.ristr[d - kslab] = istr[d]; p.rostr[d - kslab] = ostr_d[d];
+        p.rest_total *= odims[d];
+      }
+      p.alpha = alpha; p.beta = beta;
+      const size_t smem = (size_t)p.G * p.S * 8 + (size_t)p.G * 16 + (size_t)p.S * 4;
+      const long long passes = (p.rest_total + p.G - 1) / p.G;
+      const int blocks = (int)std::max<long long>(1, std::min<long long>(passes, 148LL * 8));
+      permute_slab<<<blocks, 256, smem, st>>>(p, in, out);
+      count_launch();
+      AFESP_CUDA_CHECK(cudaGetLastError());
+      return;
+    }
     // find the output axis fed by input axis 0 (input stride 1)
     int d0 = -1;
     for (int d = 1; d < r; ++d) if (istr[d] == 1) d0 = d;
@@ -165,9 +381,15 @@ void permute_strided(cudaStream_t st, int rank, const int* dims, const int* perm
       ++p.nrest;
     }
     p.alpha = alpha; p.beta = beta;
-    dim3 grid((p.n0 + 31) / 32, (unsigned)std::min<long long>((p.nb + 31) / 32, 65535),
-              (unsigned)std::min<long long>(p.rest_total, 65535));
-    permute_transpose<<<grid, dim3(32, 8), 0, st>>>(p, in, out);
+    if (p.n0 >= 48 && p.nb >= 48) {
+      dim3 grid((p.n0 + 63) / 64, (unsigned)std::min<long long>((p.nb + 63) / 64, 65535),
+                (unsigned)std::min<long long>(p.rest_total, 65535));
+      permute_transpose64<<<grid, 256, 0, st>>>(p, in, out);
+    } else {
+      dim3 grid((p.n0 + 31) / 32, (unsigned)std::min<long long>((p.nb + 31) / 32, 65535),
+                (unsigned)std::min<long long>(p.rest_total, 65535));
+      permute_transpose<<<grid, dim3(32, 8), 0, st>>>(p, in, out);
+    }
   }
   count_launch();
   AFESP_CUDA_CHECK(cudaGetLastError());

@@ -40,8 +40,8 @@ double since(Clock::time_point t0) { return std::chrono::duration<double>(Clock:
 
 // ---------------------------------------------------------------------------------------------- error handling
 [[noreturn]] void fail(const std::string& procedure, const std::string& msg) {  // src/error_handling.f90:6-20
-  std::fprintf(stderr, " ERROR.\n Programme stops in procedure: %s.\n Reason: %s.\n EXITING...\n", procedure.c_str(),
-               msg.c_str());
+  std::fprintf(stderr, " ERROR.\n Programme stops in procedure: %s.\n Reason: %s.\n EXITING...\nSTOP 999\n",
+               procedure.c_str(), msg.c_str());
   std::fflush(stdout);
   std::exit(999 & 0xff);
 }

@@ -82,10 +82,11 @@ def _mask(line):
     return m.group(1) if m else line
 
 
-def compare_els_out(mine, ref, ulps=2.0):
+def compare_els_out(mine, ref, ulps=2.0, abs_tol=0.0):
     """Line-by-line comparison of two program outputs: identical text and layout; numeric fields may differ by
-    `ulps` units of their last printed digit (rounding of independently computed doubles).  Returns a list of
-    differences (empty = same)."""
+    `ulps` units of their last printed digit (rounding of independently computed doubles) or by `abs_tol` (the
+    1e-9 Eh energy tolerance of the north star, for the 12-decimal CCSD table), whichever is larger.  Returns a list
+    of differences (empty = same)."""
     a, b = [_mask(x) for x in mine.splitlines()], [_mask(x) for x in ref.splitlines()]
     diffs = []
     if len(a) != len(b):
@@ -103,9 +104,66 @@ def compare_els_out(mine, ref, ulps=2.0):
                     ok = False
                     break
                 dec = len(q.split(".")[1])
-                if abs(float(p) - float(q)) > ulps * 10.0 ** (-dec) * 1.0000001:
+                if abs(float(p) - float(q)) > max(ulps * 10.0 ** (-dec), abs_tol) * 1.0000001:
                     ok = False
                     break
         if not ok:
             diffs.append(f"{n}: {x!r} != {y!r}")
     return diffs
+
+
+
+def write_sample_dir(name, path, calc_type=None):
+    """Write the committed fixture back out as the reference's input files (els.in, s.dat, t.dat, v.dat, eri.dat,
+    geom.dat, guess_in.dat: free-format index/value lines, src/integrals.f90:48-165) so that the C++ host program
+    can be run on it exactly as els.x would be."""
+    z = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
+    text = str(z["els_in"])
+    if calc_type is not None:
+        text = re.sub(r'calc_type\s*=\s*"[^"]*"', f'calc_type="{calc_type}"', text)
+    with open(os.path.join(path, "els.in"), "w") as f:
+        f.write(text)
+    n = z["ovlp"].shape[0]
+    for fname, key in (("s.dat", "ovlp"), ("t.dat", "ke"), ("v.dat", "en")):
+        m = z[key]
+        with open(os.path.join(path, fname), "w") as f:
+            for i in range(n):
+                for j in range(i + 1):
+                    f.write("%d %d %.17g\n" % (i + 1, j + 1, m[i, j]))
+    eri = z["eri"]
+    with open(os.path.join(path, "eri.dat"), "w") as f:
+        pos = 0
+        for i in range(n):
+            for j in range(i + 1):
+                ij = i * (i + 1) // 2 + j
+                for k in range(i + 1):
+                    for l in range(k + 1):
+                        if k * (k + 1) // 2 + l > ij:
+                            break
+                        v = eri[ij * (ij + 1) // 2 + k * (k + 1) // 2 + l]
+                        if v != 0.0:
+                            f.write("%d %d %d %d %.17g\n" % (i + 1, j + 1, k + 1, l + 1, v))
+    geom = z["geom"]
+    with open(os.path.join(path, "geom.dat"), "w") as f:
+        f.write("%d\n" % geom.shape[0])
+        for row in geom:
+            f.write("%.17g %.17g %.17g %.17g\n" % tuple(row))
+    if z["guess"].size:
+        g = z["guess"]
+        with open(os.path.join(path, "guess_in.dat"), "w") as f:
+            for i in range(n):
+                for j in range(n):
+                    f.write("%d %d %.17g\n" % (i + 1, j + 1, g[i, j]))
+    return text
+
+
+def els_host_binary():
+    """Path of the C++ host program, built on demand (host/Makefile; needs the in-tree libafesp_gpu.so)."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "host", "els_host")
+    src = os.path.join(root, "host", "els_host.cpp")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", os.path.join(root, "host")], check=True, capture_output=True)
+    return exe

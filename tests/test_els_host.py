@@ -1,0 +1,48 @@
+"""The C++ host program (host/els_host.cpp, stand-in for the Fortran els.x) on the reference's sample inputs:
+CPU part here (readers, namelist, RHF, guess_out.dat, error behaviour); the full CRCCSD(T) runs are in
+tests/test_gpu_parity.py::test_els_host_*."""
+import os
+import subprocess
+
+import numpy as np
+
+from tests._fixtures import GOLDEN_DIR, compare_els_out, els_host_binary, golden_els_out, write_sample_dir
+
+
+def test_els_host_scf_section_is_byte_identical_to_the_shipped_output(tmp_path):
+    write_sample_dir("n2", str(tmp_path), calc_type="RHF")
+    r = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    mine = r.stdout.splitlines()
+    ref = golden_els_out("n2").replace('calc_type="CRCCSD(T)_spatial"', 'calc_type="RHF"').splitlines()
+    stop = next(i for i, ln in enumerate(ref) if ln.startswith(" Time taken for restricted Hartree-Fock")) + 1
+    assert compare_els_out("\n".join(mine[:stop]), "\n".join(ref[:stop]), ulps=0.0) == []
+    assert " RHF energy:                     -108.3305827541" in mine
+    # guess_out.dat: same text as the file the reference wrote (src/hf.f90:172-191)
+    z = np.load(os.path.join(GOLDEN_DIR, "n2.npz"))
+    lines = (tmp_path / "guess_out.dat").read_text().splitlines()
+    for mine_ln, ref_ln in zip(lines, str(z["guess_out_head"]).splitlines()):
+        assert len(mine_ln) == len(ref_ln) and mine_ln.split()[:2] == ref_ln.split()[:2]
+        if abs(float(ref_ln.split()[2])) > 1e-6:      # entries that are numerical noise (1e-12) differ in every run
+            assert mine_ln == ref_ln
+    got = np.array([float(x.split()[2]) for x in lines]).reshape(z["guess_out"].shape)
+    assert np.max(np.abs(got - z["guess_out"])) < 5e-9
+
+
+def test_els_host_f2_scf_table(tmp_path):
+    write_sample_dir("f2", str(tmp_path), calc_type="RHF")
+    r = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    ref = golden_els_out("f2").replace('calc_type="CRCCSD(T)_spatial"', 'calc_type="RHF"').splitlines()
+    stop = next(i for i, ln in enumerate(ref) if ln.startswith(" Time taken for restricted Hartree-Fock")) + 1
+    assert compare_els_out("\n".join(r.stdout.splitlines()[:stop]), "\n".join(ref[:stop]), ulps=1.0) == []
+
+
+def test_els_host_error_behaviour(tmp_path):
+    """src/error_handling.f90:6-20: error block on stderr, non-zero stop."""
+    r = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0
+    assert " ERROR." in r.stderr and "system::read_system_in" in r.stderr and "els.in does not exist" in r.stderr
+    write_sample_dir("n2", str(tmp_path), calc_type="CCSD(Q)_spatial")
+    r = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "Unrecognised calculation type!" in r.stderr

@@ -10,6 +10,7 @@ import torch
 from afesp_b200 import AfespGpu, synthetic
 
 n, o = int(os.environ.get("NBF", 200)), int(os.environ.get("NOCC", 20))
+v = n - o
 what = os.environ.get("PROFILE", "T")
 rt = torch.cuda.cudart()
 g = AfespGpu(0)
@@ -20,10 +21,14 @@ g.ccsd_init(o, True, eps, 8)
 g.ccsd_iterate()
 g.ccsd_diis()
 if what == "CCSD":
+    # the two GEMM shapes that carry the CCSD iteration, as the iteration issues them: the (+)-packed ladder
+    # S(o^2 x P+) . V+(P+ x P+) and an o^3 v^3 ring (ov x ov x ov); one launch each inside the profiled range
+    Pp = v * (v + 1) // 2
+    g.bench_dgemm("N", "N", o * o, Pp, Pp, reps=1, beta=0.0)   # warm-up inside bench_dgemm is outside the range below
     rt.cudaProfilerStart()
-    g.ccsd_iterate()
+    print("ladder ms", g.bench_dgemm("N", "N", o * o, Pp, Pp, reps=1, beta=0.0))
+    print("ring ms", g.bench_dgemm("N", "N", o * v, o * v, o * v, reps=1, beta=1.0))
     rt.cudaProfilerStop()
-    print("ccsd iter ms", g.last_stage_ms())
 g.ccsd_finalize()
 if what == "T":
     g.set_option("triples_batch_bytes", float(6 << 30))

@@ -21,6 +21,12 @@ def main(path, out=None):
         if m:
             short = "gemm_f64_dmma<BM%s,BN%s,BK%s,akmajor%s,bkmajor%s,vec%s>" % (m.group(1), m.group(2), m.group(3), m.group(7), m.group(8), m.group(9))
         else:
+            m3 = re.search(r"gemm_f64_tma<\(bool\)(\d), \(bool\)(\d)>", name)
+            if m3:
+                short = "gemm_f64_tma<akmajor%s,bkmajor%s>" % (m3.group(1), m3.group(2))
+                agg[short][0] += 1
+                agg[short][1] += t
+                continue
             m2 = re.search(r"(k_\w+|permute_\w+|splitk_reduce|scale_c|fused_\w+|triples_\w+)", name)
             short = m2.group(1) if m2 else name[:70]
         agg[short][0] += 1
