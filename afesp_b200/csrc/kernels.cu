@@ -96,27 +96,15 @@ inline int oovv_grid(int v) {
   return (int)std::max<long long>(1, std::min<long long>(chunks, 148LL * 8));
 }
 
-// x / d for energy denominators.  The IEEE division sequence (reciprocal seed, Newton steps, residual fix-up and
-// its special-case slow path) costs more issue slots than the two 8-byte streams of the divide kernel take to move
-// (measured: 63% of the copy peak with '/', 93% with a multiplication in its place).  Orbital-energy denominators are
-// O(1) numbers well inside the float range, so: single-precision reciprocal seed (one MUFU), two Newton steps in double
-// (relative error ~2^-90), quotient, one residual correction -- the result is the correctly rounded quotient except for
-// rare last-bit ties.  Anything outside [2^-100, 2^100] takes the ordinary division.
-__device__ __forceinline__ double div_denominator(double x, double d) {
-  const double ad = fabs(d);
-  if (!(ad > 7.9e-31 && ad < 1.2e30)) return x / d;
-  double r = (double)__frcp_rn((float)d);
-  r = fma(fma(-d, r, 1.0), r, r);
-  r = fma(fma(-d, r, 1.0), r, r);
-  const double q = x * r;
-  return fma(fma(-d, q, x), r, q);
-}
-
+// Note on the division: measured on B200 the divide kernel reaches 63% of the copy peak with the IEEE '/', 93% with a
+// multiplication in its place (k_divide_d2_probe) and 58% with a float-seeded Newton reciprocal -- the quarter-rate
+// MUFU / conversion slots, not the DFMA count, are what the division costs, so the plain correctly-rounded division
+// stays (bit-identical to the reference's T = X / D).
 __global__ void __launch_bounds__(OOVV_T) k_divide_d2_fast(double* __restrict__ out, const double* __restrict__ x,
                                                             const double* __restrict__ eo, const double* __restrict__ ev,
                                                             int o, int v) {
   oovv_walk<true, 4>(o, v, eo, ev, [&](long long idx, int ij, int c, const OovvTables& t) {
-    out[idx] = div_denominator(x[idx], t.eoo[ij] - t.evv[c]);
+    out[idx] = x[idx] / (t.eoo[ij] - t.evv[c]);
   });
 }
 

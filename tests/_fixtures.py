@@ -73,7 +73,9 @@ _NUM = re.compile(r"^[-+]?\d+\.\d+(E[-+]\d+)?$")
 
 
 def _mask(line):
-    """Drop what legitimately differs between two runs of the same program: dates and wall-clock times."""
+    """Drop what legitimately differs between two runs of the same program: dates and wall-clock times (and trailing
+    blanks: a list-directed empty `write(iunit, *)` prints '' or ' ' depending on the compiler's runtime)."""
+    line = line.rstrip()
     if re.match(r"^ (Started|Finished) running on ", line):
         return line.split(" on ")[0] + " on <date>"
     if line.startswith(" Time taken"):

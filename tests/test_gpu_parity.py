@@ -195,12 +195,13 @@ def test_els_host_whole_program_matches_shipped_els_out(name, tmp_path):
 
     from tests._fixtures import compare_els_out, els_host_binary, golden_els_out, write_sample_dir
 
-    write_sample_dir(name, str(tmp_path))
+    text = write_sample_dir(name, str(tmp_path))
     r = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     diffs = compare_els_out(r.stdout, golden_els_out(name), ulps=2.0, abs_tol=E_TOL)
     assert diffs == [], "\n".join(diffs[:20])
-    assert (tmp_path / "guess_out.dat").exists()
+    wants_guess = "scf_write_guess = .true." in text or "scf_write_guess=.true." in text
+    assert (tmp_path / "guess_out.dat").exists() == wants_guess
 
 
 def test_els_host_writes_fcidump_and_spinorb_path(tmp_path):
