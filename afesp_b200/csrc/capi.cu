@@ -216,7 +216,7 @@ int afesp_gpu_set_option(afesp_handle hv, const char* key, double value) {
     else if (k == "finalize_keep_ccsd") o.finalize_keep_ccsd = value != 0.0;
     else if (k == "gemm_timing") gemm_timing_enable(value != 0.0);
     else if (k == "gemm_force_config") gemm_force_config((int)value);
-    else if (k == "gemm_use_tma") gemm_tma_enable(value != 0.0);
+    else if (k == "gemm_use_tma") gemm_tma_scope((int)value);   // 0 off, 1 (T) batches only (default), 2 all aligned GEMMs
     else if (k == "dist_min_flops") h.s.eng.dist.min_flops = value;   // GEMMs below this stay replicated
     else if (k == "dist_ccsd") h.s.eng.dist.enabled = value != 0.0;       // 0: replicate CCSD / AO->MO, shard only (T)
     else throw Error(1, "set_option: unknown key " + k);

@@ -95,7 +95,10 @@ extern double g_gemm_flops;
 // the live roofline figure.  gemm_timing_collect() synchronises and returns the accumulated milliseconds.
 void gemm_timing_enable(bool on);
 void gemm_force_config(int cfg);  // tuning aid: -1 = automatic tile selection
-void gemm_tma_enable(bool on);     // TMA-staged operand path for aligned problems (default on)
+// TMA-staged operand path: scope 0 = off, 1 = gathered batches only (the (T) contraction; default), 2 = every aligned
+// problem the 64x64 tile is chosen for.  See DESIGN.md section 4.1 for why the default is 1.
+void gemm_tma_scope(int scope);
+int gemm_tma_scope_get();
 bool dgemm_tma(cudaStream_t st, bool ak, bool bk, int M, int N, int K, double alpha, const double* A, long long lda,
                const double* B, long long ldb, double beta, double* C, long long ldc, const GemmBatch* batch, int cvec);
 double gemm_timing_collect(double* flops_out, long long* launches_out = nullptr);

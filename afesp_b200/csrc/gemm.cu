@@ -18,6 +18,9 @@
 // reduced by a second kernel, deterministically (no atomics).
 #include <cmath>
 
+#include <cmath>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace afesp {
@@ -433,7 +436,9 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
 
   // tile selection (see kCfg)
   long long tiles = 0;
-  const bool tma_ok = vec2 && (!batch || !(batch->Aptr || batch->Bptr) || (batch->Abase && batch->Bbase));
+  const bool gathered = batch && batch->Abase && batch->Bbase;
+  const bool tma_ok = vec2 && (gemm_tma_scope_get() == 2 ? (!batch || !(batch->Aptr || batch->Bptr) || gathered)
+                                                         : (gemm_tma_scope_get() == 1 && gathered));
   int cfg = choose_cfg(M, N, nbatch, &tiles, tma_ok);
   if (g_force_cfg >= 0 && g_force_cfg < NCFG) {
     cfg = g_force_cfg;
@@ -461,9 +466,55 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
   if (evs) { cudaEventRecord(evs->first, st); g_timed_flops += 2.0 * M * N * (double)K * nbatch; g_timed_launches += 1; }
   // aligned problems on the 64x64 tile go through the TMA-staged kernel (gemm_tma.cu); everything else through cp.async
   bool used_tma = false;
+  // Developer check (AFESP_GEMM_VERIFY=1, unbatched problems): run the cp.async kernel on a copy of C as well and report
+  // any TMA result that differs from it by more than rounding.
+  static const bool verify = std::getenv("AFESP_GEMM_VERIFY") != nullptr;
+  double* vcopy = nullptr;
+  const bool do_verify = verify && cfg == 3 && p.splitk == 1 && vec2 && nbatch == 1 && ldc == M;
+  if (do_verify) {
+    vcopy = device_alloc((size_t)M * N);
+    AFESP_CUDA_CHECK(cudaMemcpyAsync(vcopy, C, (size_t)M * N * 8, cudaMemcpyDeviceToDevice, st));
+  }
   if (cfg == 3 && p.splitk == 1 && vec2)
     used_tma = dgemm_tma(st, ak, bk, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, batch, p.cvec);
   if (!used_tma) launch_by_cfg(cfg, st, p, nbatch, ak, bk, vec2);
+  if (do_verify) {
+    if (used_tma) {
+      Params q = p;
+      q.C = vcopy;
+      launch_by_cfg(cfg, st, q, nbatch, ak, bk, vec2);
+      std::vector<double> a((size_t)M * N), b((size_t)M * N);
+      AFESP_CUDA_CHECK(cudaMemcpyAsync(a.data(), C, a.size() * 8, cudaMemcpyDeviceToHost, st));
+      AFESP_CUDA_CHECK(cudaMemcpyAsync(b.data(), vcopy, b.size() * 8, cudaMemcpyDeviceToHost, st));
+      AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
+      double md = 0.0, mr = 0.0;
+      long long where = -1, nbad = 0;
+      for (size_t i = 0; i < a.size(); ++i) {
+        const double d = std::fabs(a[i] - b[i]);
+        if (d > md) { md = d; where = (long long)i; }
+        mr = std::max(mr, std::fabs(b[i]));
+      }
+      for (size_t i = 0; i < a.size(); ++i) if (std::fabs(a[i] - b[i]) > 1e-11 * mr) ++nbad;
+      static int nreport = 0;
+      if (md > 1e-11 * mr && nreport < 3) {
+        int shown = 0;
+        for (size_t i = 0; i < a.size() && shown < 40; ++i)
+          if (std::fabs(a[i] - b[i]) > 1e-11 * mr) {
+            std::fprintf(stderr, "   bad (m=%lld [tile %lld +%lld], n=%lld [tile %lld +%lld]) tma=%.6e ref=%.6e diff=%.3e\n",
+                         (long long)(i % M), (long long)((i % M) / 64), (long long)((i % M) % 64), (long long)(i / M),
+                         (long long)((i / M) / 64), (long long)((i / M) % 64), a[i], b[i], a[i] - b[i]);
+            ++shown;
+          }
+      }
+      if (md > 1e-11 * mr && nreport++ < 40)
+        std::fprintf(stderr, "[afesp gemm verify] TMA != cp.async: M=%d N=%d K=%d ak=%d bk=%d lda=%lld ldb=%lld alpha=%g beta=%g "
+                             "maxdiff=%.3e maxref=%.3e at (m=%lld,n=%lld) nbad=%lld A%%128=%d B%%128=%d\n",
+                     M, N, K, (int)ak, (int)bk, lda, ldb, alpha, beta, md, mr, where % M, where / M, nbad,
+                     (int)(reinterpret_cast<uintptr_t>(A) & 127), (int)(reinterpret_cast<uintptr_t>(B) & 127));
+    }
+    AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
+    device_free(vcopy);
+  }
   if (p.splitk > 1) {
     long long MN = (long long)M * N;
     splitk_reduce<<<(int)std::min<long long>((MN + 255) / 256, 2048), 256, 0, st>>>(p.ws, p.splitk, M, N, alpha,

@@ -15,6 +15,7 @@
 // dimensions and batch strides.  Out-of-range k is zero-filled by TMA; out-of-range m/n only ever feeds masked outputs.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <type_traits>
 
@@ -162,53 +163,28 @@ __global__ void __launch_bounds__(NT, 3) gemm_f64_tma(const __grid_constant__ CU
       boff[s][i] = tile_off<BKM>(wn0 + 8 * i + gid, k);
     }
   }
-  // fragments of this warp that intersect C (warp-uniform)
-  const int mfr = min(4, max(0, (p.M - (m0 + wm0) + 7) >> 3)), nfr = min(4, max(0, (p.N - (n0 + wn0) + 7) >> 3));
-  // Edge tiles: 8-row / 8-column fragments that lie entirely outside C issue no DMMA, which leaves the tensor pipe of
-  // this SM sub-partition to the warps of the co-resident CTAs (M = 360 on 64-row tiles: 6.25% less work).  The loop is
-  // instantiated per row-fragment count so that interior tiles run exactly the unconditional code.
-  auto mainloop = [&](auto mf_tag, auto nedge_tag) {
-    constexpr int MFR = decltype(mf_tag)::value;
-    constexpr bool NEDGE = decltype(nedge_tag)::value;
-    for (int kt = 0; kt < nk; ++kt) {
-      const int s = kt % STAGES;
-      mbar_wait(&full[s], (kt / STAGES) & 1);
-      const unsigned char* sa = smem + s * STAGE_BYTES;
-      const unsigned char* sb = sa + TILE_BYTES;
+  // Every warp issues the full 4x4 fragment grid, also in edge tiles.  (Skipping the fragments that lie outside C
+  // was tried: it gains ~1.5% on M = 360 but made edge-tile results irreproducible when the epilogue also reads C,
+  // beta != 0 -- tools/tma_edge_probe.py -- so it is not used.)
+  for (int kt = 0; kt < nk; ++kt) {
+    const int s = kt % STAGES;
+    mbar_wait(&full[s], (kt / STAGES) & 1);
+    const unsigned char* sa = smem + s * STAGE_BYTES;
+    const unsigned char* sb = sa + TILE_BYTES;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        double af[4], bf[4];
+    for (int g = 0; g < 4; ++g) {
+      double af[4], bf[4];
 #pragma unroll
-        for (int i = 0; i < MFR; ++i) af[i] = *reinterpret_cast<const double*>(sa + aoff[g][i]);
+      for (int i = 0; i < 4; ++i) af[i] = *reinterpret_cast<const double*>(sa + aoff[g][i]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bf[j] = *reinterpret_cast<const double*>(sb + boff[g][j]);
+      for (int j = 0; j < 4; ++j) bf[j] = *reinterpret_cast<const double*>(sb + boff[g][j]);
 #pragma unroll
-        for (int i = 0; i < MFR; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (!NEDGE || j < nfr) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
-  };
-  using std::integral_constant;
-  if (nfr == 4) {
-    switch (mfr) {
-      case 4: mainloop(integral_constant<int, 4>{}, integral_constant<bool, false>{}); break;
-      case 3: mainloop(integral_constant<int, 3>{}, integral_constant<bool, false>{}); break;
-      case 2: mainloop(integral_constant<int, 2>{}, integral_constant<bool, false>{}); break;
-      case 1: mainloop(integral_constant<int, 1>{}, integral_constant<bool, false>{}); break;
-      default: mainloop(integral_constant<int, 0>{}, integral_constant<bool, false>{}); break;
-    }
-  } else {
-    switch (mfr) {
-      case 4: mainloop(integral_constant<int, 4>{}, integral_constant<bool, true>{}); break;
-      case 3: mainloop(integral_constant<int, 3>{}, integral_constant<bool, true>{}); break;
-      case 2: mainloop(integral_constant<int, 2>{}, integral_constant<bool, true>{}); break;
-      case 1: mainloop(integral_constant<int, 1>{}, integral_constant<bool, true>{}); break;
-      default: mainloop(integral_constant<int, 0>{}, integral_constant<bool, true>{}); break;
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
   }
 
   // ---------------- epilogue (same fragment ownership as gemm_f64_dmma) ----------------
@@ -317,16 +293,19 @@ bool make_map(CUtensorMap* map, bool kmajor, const double* base, long long MN, l
   return r == CUDA_SUCCESS;
 }
 
-bool g_use_tma = true;
+int g_tma_scope = 1;   // 0 = off, 1 = gathered batches only (the (T) contraction), 2 = every aligned 64x64-tile problem
 
 }  // namespace
 
-void gemm_tma_enable(bool on) { g_use_tma = on; }
+void gemm_tma_scope(int scope) { g_tma_scope = scope; }
+int gemm_tma_scope_get() { return g_tma_scope; }
 
 // Returns false when the TMA path does not apply (the caller then runs the cp.async kernel).
 bool dgemm_tma(cudaStream_t st, bool ak, bool bk, int M, int N, int K, double alpha, const double* A, long long lda,
                const double* B, long long ldb, double beta, double* C, long long ldc, const GemmBatch* batch, int cvec) {
-  if (!g_use_tma || K < 1) return false;
+  if (g_tma_scope == 0 || K < 1) return false;
+  const bool gathered = batch && batch->Abase && batch->Bbase && batch->Aidx && batch->Bidx;
+  if (g_tma_scope == 1 && !gathered) return false;
   const int nbatch = batch ? batch->count : 1;
   const double* Abase = A;
   const double* Bbase = B;

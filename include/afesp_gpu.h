@@ -42,7 +42,12 @@ const char* afesp_gpu_last_error(afesp_handle h); /* h may be NULL: error of the
  *   "triples_batch_bytes"      work-buffer budget of the (T) batches, bytes
  * Measurement switches (default 0):
  *   "finalize_keep_ccsd"       afesp_gpu_ccsd_finalize keeps the DIIS history and intermediates (benchmark loops)
- *   "gemm_timing"              bracket every DMMA GEMM launch with CUDA events (see afesp_gpu_gemm_time) */
+ *   "gemm_timing"              bracket every DMMA GEMM launch with CUDA events (see afesp_gpu_gemm_time)
+ * Kernel selection:
+ *   "gemm_use_tma"             0 = cp.async kernels only; 1 (default) = the TMA-staged kernel for the gathered (T)
+ *                              batches; 2 = also for every other aligned GEMM the 64x64 tile is chosen for
+ *   "gemm_force_config"        tile menu entry (tuning aid), -1 = automatic
+ *   "dist_ccsd", "dist_min_flops"   see the multi-GPU section below */
 int afesp_gpu_set_option(afesp_handle h, const char* key, double value);
 /* Kernel launches and executed DMMA flop (2*M*N*K per GEMM) since the handle was opened. */
 int afesp_gpu_counters(afesp_handle h, long long* launches, double* gemm_flops);

@@ -17,7 +17,7 @@ for (M, N, K) in [(64, 64, 16), (64, 64, 64), (128, 192, 80), (70, 66, 34), (130
             Bf = (B if tb == "N" else B.T).ravel(order="F")
             ref = 0.7 * A @ B + 0.3 * C0
             for tma in (0, 1):
-                g.set_option("gemm_use_tma", tma)
+                g.set_option("gemm_use_tma", 2 * tma)
                 out = g.dgemm_wrapper(ta, tb, M, N, K, Af, Bf, C0.ravel(order="F"), alpha=0.7, beta=0.3).reshape((M, N), order="F")
                 err = np.abs(out - ref).max() / max(1.0, np.abs(ref).max())
                 if err > 1e-13:
@@ -38,7 +38,7 @@ shapes = [
 for name, ta, tb, M, N, K, beta in shapes:
     row = {"shape": name, "M": M, "N": N, "K": K}
     for tma in (0, 1):
-        g.set_option("gemm_use_tma", tma)
+        g.set_option("gemm_use_tma", 2 * tma)
         ms = g.bench_dgemm(ta, tb, M, N, K, reps=3, beta=beta)
         tf = 2.0 * M * N * K / ms / 1e9
         row["tma" if tma else "cpasync"] = {"ms": ms, "tflops": tf}
