@@ -350,6 +350,20 @@ static_assert(sizeof(double) == sizeof(void*), "pointer arrays are carried in do
 
 }  // namespace
 
+namespace {
+// Developer check (AFESP_T_VERIFY=1): count elements of two X buffers that differ by more than rounding.
+__global__ void k_count_mismatch(const double* __restrict__ a, const double* __restrict__ b, long long n, double tol,
+                                 unsigned long long* __restrict__ out) {
+  unsigned long long bad = 0;
+  double worst = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double d = fabs(a[i] - b[i]);
+    if (d > tol * fmax(fabs(b[i]), 1e-6)) { ++bad; worst = fmax(worst, d); }
+  }
+  if (bad) { atomicAdd(out, bad); atomicMax(out + 1, (unsigned long long)__double_as_longlong(worst)); }
+}
+}  // namespace
+
 void triples_partition_counts(int o, bool symmetric, bool strict, int nranks, long long* counts) {
   for (int r = 0; r < nranks; ++r) counts[r] = (long long)my_triples(o, symmetric, strict, r, nranks).size();
 }
@@ -446,6 +460,15 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
   const bool al16 = (v % 2 == 0) && (o % 2 == 0);
   const int perm6[6][3] = {{0, 1, 2}, {1, 0, 2}, {2, 1, 0}, {0, 2, 1}, {1, 2, 0}, {2, 0, 1}};
 
+  static const bool verify_env = std::getenv("AFESP_T_VERIFY") != nullptr;
+  const bool verify_t = verify_env && gemm_tma_scope_get() != 0;
+  std::unique_ptr<Scratch> verify_buf, verify_cnt;
+  double verify_elems = 0.0;
+  if (verify_t) {
+    verify_buf.reset(new Scratch(e.pool, (size_t)nb * 6 * v3));
+    verify_cnt.reset(new Scratch(e.pool, 2));
+    AFESP_CUDA_CHECK(cudaMemsetAsync(verify_cnt->p, 0, 16, st));
+  }
   tr.lap(1);
   for (size_t bi = 0; bi < nbatches; ++bi) {
     const size_t t0 = bi * nb;
@@ -489,6 +512,16 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
       tr.lap(4);
     };
     run_gemms(sAcat.p, sBcat.p, X.p);
+    if (verify_t) {
+      // the same batch once more through the cp.async kernel, element-wise comparison on the device
+      const int scope = gemm_tma_scope_get();
+      gemm_tma_scope(0);
+      run_gemms(sAcat.p, sBcat.p, verify_buf->p);
+      gemm_tma_scope(scope);
+      k_count_mismatch<<<148 * 8, 256, 0, st>>>(X.p, verify_buf->p, (long long)ng * v3, 1e-11,
+                                                reinterpret_cast<unsigned long long*>(verify_cnt->p));
+      verify_elems += (double)ng * v3;
+    }
     if (do_m) run_gemms(sAcatM->p, sBcatM->p, XM->p);
     FusedArgs fa{};
     fa.X = X.p; fa.XM = do_m ? XM->p : nullptr; fa.t1 = s.t1.p(); fa.t2 = s.t2.p(); fa.vo = s.get("v_oovv").p();
@@ -529,6 +562,14 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
   std::vector<double> h(nbatches * 6);
   AFESP_CUDA_CHECK(cudaMemcpyAsync(h.data(), batch_sums.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
   AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (verify_t) {
+    unsigned long long cnt[2] = {0, 0};
+    AFESP_CUDA_CHECK(cudaMemcpy(cnt, verify_cnt->p, 16, cudaMemcpyDeviceToHost));
+    double worst;
+    std::memcpy(&worst, &cnt[1], 8);
+    std::fprintf(stderr, "[afesp T verify] TMA vs cp.async over %.3e X elements: %llu mismatches (worst |diff| %.3e)\n",
+                 verify_elems, cnt[0], cnt[0] ? worst : 0.0);
+  }
   for (size_t bi = 0; bi < nbatches; ++bi)
     for (int k = 0; k < 6; ++k) sums[k] += h[bi * 6 + k];
   if (!paren) { sums[1] = 0.0; sums[3] = 0.0; sums[5] = 0.0; }
