@@ -11,7 +11,8 @@ Also checks that all ranks hold bit-identical amplitudes after the sharded run. 
 The compared iterations run WITHOUT the DIIS extrapolation (plain fixed-point steps, which contract differences).
 With DIIS the comparison would measure the conditioning of the DIIS linear system rather than the sharding: on a
 single GPU, two runs that differ only in the summation order inside a k-tile (TMA kernel vs cp.async kernel) drift
-apart by 1e-9 Eh / 7e-8 in T2 within 6 extrapolated iterations of these fast-converging synthetic systems
+apart by up to 2e-10 Eh within 6 extrapolated iterations of these fast-converging synthetic systems and meet
+again at convergence
 (tools/rounding_sensitivity.py, profiles/r01_rounding_sensitivity.json) -- and slab-width GEMMs select other tile
 shapes than full-width ones.  `--diis` switches the extrapolation back on."""
 import argparse
