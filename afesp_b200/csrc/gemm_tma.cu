@@ -100,6 +100,7 @@ struct TmaParams {
   const int* Aidx;   // per-batch block index into the A map's outermost dimension (null: batch index)
   const int* Bidx;
   int M, N, K, tiles_m;
+  int nbatch;        // > 0: batch-fastest rasterisation on a 1-D grid (see the kernel); 0: batch = blockIdx.z
   double alpha, beta;
   int cvec;
 };
@@ -114,8 +115,20 @@ __global__ void __launch_bounds__(NT, 3) gemm_f64_tma(const __grid_constant__ CU
   unsigned long long* empty = full + STAGES;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = (blockIdx.x % p.tiles_m) * BM, n0 = (blockIdx.x / p.tiles_m) * BN;
-  const int batch = blockIdx.z;
+  // Rasterisation.  Batched launches walk (m-tile, batch) fastest and the n-tile slowest: the batch entries are sorted
+  // by their B block (triples.cu), so the CTAs that share one K x 64 tile of B run back to back and B is fetched from
+  // DRAM once per distinct block instead of once per batch entry; the A blocks (M x K each) stay L2-resident.
+  int m0, n0, batch;
+  if (p.nbatch > 0) {
+    const unsigned per_n = (unsigned)p.tiles_m * (unsigned)p.nbatch;
+    const unsigned nt = blockIdx.x / per_n, rem = blockIdx.x - nt * per_n;
+    batch = (int)(rem / (unsigned)p.tiles_m);
+    m0 = (int)(rem - (unsigned)batch * p.tiles_m) * BM;
+    n0 = (int)nt * BN;
+  } else {
+    m0 = (blockIdx.x % p.tiles_m) * BM; n0 = (blockIdx.x / p.tiles_m) * BN;
+    batch = blockIdx.z;
+  }
   const int nk = (p.K + BK - 1) / BK;
 
   if (tid == 0) {
@@ -337,6 +350,11 @@ bool dgemm_tma(cudaStream_t st, bool ak, bool bk, int M, int N, int K, double al
   if (tiles >= (1LL << 31) || nbatch > 65535) return false;
   constexpr size_t SMEM = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;
   dim3 grid((unsigned)tiles, 1, nbatch);
+  p.nbatch = 0;
+  if (nbatch > 1 && tiles * nbatch < (1LL << 31)) {
+    p.nbatch = nbatch;
+    grid = dim3((unsigned)(tiles * nbatch), 1, 1);
+  }
   // all four instantiations share one function-pointer type: raise their dynamic shared-memory limit together, once
   static std::once_flag once;
   std::call_once(once, [&] {
