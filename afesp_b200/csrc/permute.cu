@@ -316,7 +316,7 @@ void permute_strided(cudaStream_t st, int rank, const int* dims, const int* perm
     // threads along the row: the width that wastes the fewest lanes in the last pass (ties go to the wider one)
     int rx = 32;
     double best = -1.0;
-    for (int w : {256, 128, 64, 32}) {
+    for (int w : {256, 128, 64, 32, 16, 8}) {
       const double eff = (double)p.n0 / ((double)((p.n0 + w - 1) / w) * w);
       if (eff > best + 1e-9) { best = eff; rx = w; }
     }
@@ -326,7 +326,9 @@ void permute_strided(cudaStream_t st, int rank, const int* dims, const int* perm
       case 256: permute_rows<256><<<blocks, 256, 0, st>>>(p, in, out); break;
       case 128: permute_rows<128><<<blocks, 256, 0, st>>>(p, in, out); break;
       case 64: permute_rows<64><<<blocks, 256, 0, st>>>(p, in, out); break;
-      default: permute_rows<32><<<blocks, 256, 0, st>>>(p, in, out); break;
+      case 32: permute_rows<32><<<blocks, 256, 0, st>>>(p, in, out); break;
+      case 16: permute_rows<16><<<blocks, 256, 0, st>>>(p, in, out); break;   // short rows (e.g. o = 40): sub-warp groups
+      default: permute_rows<8><<<blocks, 256, 0, st>>>(p, in, out); break;
     }
   } else {
     // slab form?  smallest k >= 2 whose k leading output axes are exactly the k leading input axes, densely packed
