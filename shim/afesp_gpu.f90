@@ -15,6 +15,7 @@ module afesp_gpu
    implicit none
    private
    public :: gpu_open, gpu_close, gpu_mp2, gpu_ccsd, gpu_ccsd_t_spatial, gpu_ccsd_t_spinorb, gpu_handle
+   public :: gpu_comm_id, gpu_comm_attach
 
    type(c_ptr), save :: gpu_handle = c_null_ptr
 
@@ -89,6 +90,19 @@ module afesp_gpu
          type(c_ptr), value :: h
          real(c_double), intent(out) :: e_T
       end function
+      ! Multi-GPU (one process per GPU, e.g. one MPI rank each): rank 0 obtains the 128-byte id, the host program
+      ! broadcasts it with its own transport (MPI_Bcast), every rank attaches.  Afterwards the stage calls above are
+      ! collective: AO->MO, the heavy CCSD GEMMs with the ladder integrals and the (T) triples are sharded over the ranks.
+      integer(c_int) function afesp_gpu_comm_unique_id(id) bind(C, name='afesp_gpu_comm_unique_id')
+         import :: c_int, c_char
+         character(kind=c_char), dimension(128), intent(out) :: id
+      end function
+      integer(c_int) function afesp_gpu_comm_init(h, rank, nranks, id) bind(C, name='afesp_gpu_comm_init')
+         import :: c_int, c_ptr, c_char
+         type(c_ptr), value :: h
+         integer(c_int), value :: rank, nranks
+         character(kind=c_char), dimension(128), intent(in) :: id
+      end function
    end interface
 
 contains
@@ -114,6 +128,18 @@ contains
       integer, intent(in) :: device
       call check(afesp_gpu_open(int(device, c_int), gpu_handle), 'open')
    end subroutine gpu_open
+
+   subroutine gpu_comm_id(id)
+      ! rank 0 only; broadcast `id` to the other ranks before gpu_comm_attach
+      character(kind=c_char), dimension(128), intent(out) :: id
+      call check(afesp_gpu_comm_unique_id(id), 'comm_unique_id')
+   end subroutine gpu_comm_id
+
+   subroutine gpu_comm_attach(rank, nranks, id)
+      integer, intent(in) :: rank, nranks
+      character(kind=c_char), dimension(128), intent(in) :: id
+      call check(afesp_gpu_comm_init(gpu_handle, int(rank, c_int), int(nranks, c_int), id), 'comm_init')
+   end subroutine gpu_comm_attach
 
    subroutine gpu_close()
       call check(afesp_gpu_close(gpu_handle), 'close')
