@@ -41,6 +41,7 @@ SIGNATURES = {
     "afesp_gpu_dmma_peak": [_H, _dp],
     "afesp_gpu_last_stage_ms": [_H, _dp],
     "afesp_gpu_timer": [_H, C.c_int, _dp],
+    "afesp_gpu_tma_status": [_H, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "afesp_gpu_bench_hbm": [_H, C.c_char_p, C.c_int, C.c_int, C.c_int, _dp, _dp],
     "afesp_gpu_gemm_time": [_H, _dp, _dp],
     "afesp_gpu_gemm_stats": [_H, _dp, _dp, C.POINTER(C.c_longlong)],
@@ -311,6 +312,12 @@ class AfespGpu:
         self._check("bench_hbm", self.lib.afesp_gpu_bench_hbm(self.h, what.encode(), int(nocc), int(nvirt), int(reps),
                                                               C.byref(ms), C.byref(by)))
         return ms.value, by.value
+
+    def tma_status(self):
+        """(scope in force, self-test state): see afesp_gpu_tma_status."""
+        a, b = C.c_int(0), C.c_int(0)
+        self._check("tma_status", self.lib.afesp_gpu_tma_status(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def timer_start(self):
         self._check("timer", self.lib.afesp_gpu_timer(self.h, 0, None))

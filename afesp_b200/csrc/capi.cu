@@ -175,10 +175,25 @@ int afesp_gpu_open(int device, afesp_handle* out) {
     delete h;
     return 2;
   }
+  try {
+    gemm_tma_selftest(h->s.eng.stream);   // once per process; a mismatch switches the TMA path off (see gemm_tma.cu)
+  } catch (const std::exception& e) {
+    g_open_error = std::string("afesp_gpu_open: TMA self-test could not run: ") + e.what();
+    cudaStreamDestroy(h->s.eng.stream);
+    delete h;
+    return 2;
+  }
   h->launches0 = g_launch_count;
   h->flops0 = g_gemm_flops;
   *out = h;
   return 0;
+}
+
+int afesp_gpu_tma_status(afesp_handle hv, int* scope, int* selftest) {
+  return guarded(hv, [&](Handle&) {
+    if (scope) *scope = gemm_tma_scope_get();
+    if (selftest) *selftest = gemm_tma_selftest_state();
+  });
 }
 
 int afesp_gpu_close(afesp_handle hv) {

@@ -99,6 +99,10 @@ void gemm_force_config(int cfg);  // tuning aid: -1 = automatic tile selection
 // problem the 64x64 tile is chosen for.  See DESIGN.md section 4.1 for why the default is 1.
 void gemm_tma_scope(int scope);
 int gemm_tma_scope_get();
+// One-off consistency check of the TMA kernel against the cp.async kernel on the current device (gemm_tma.cu); a
+// failure switches the TMA path off for the process.  State: 0 not run, 1 passed, -1 failed.
+bool gemm_tma_selftest(cudaStream_t st);
+int gemm_tma_selftest_state();
 bool dgemm_tma(cudaStream_t st, bool ak, bool bk, int M, int N, int K, double alpha, const double* A, long long lda,
                const double* B, long long ldb, double beta, double* C, long long ldc, const GemmBatch* batch, int cvec);
 double gemm_timing_collect(double* flops_out, long long* launches_out = nullptr);

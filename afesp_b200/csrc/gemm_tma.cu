@@ -310,7 +310,80 @@ int g_tma_scope = 1;   // 0 = off, 1 = gathered batches only (the (T) contractio
 
 }  // namespace
 
-void gemm_tma_scope(int scope) { g_tma_scope = scope; }
+namespace {
+// ---- start-up self-test ------------------------------------------------------------------------------------------
+// During this round the TMA-staged kernel produced sporadic wrong sectors on one physical B200 of the test pool
+// (serial 1651326046738: the (T)-shaped batch M=64 N=4096 K=72 failed in every run there) and never on the others,
+// while the cp.async kernel was consistent everywhere.  Whether that is a marginal part or a timing-dependent race in
+// this kernel is not settled, so the library checks the device it runs on: the shapes that
+// failed there are run through both kernels on pseudo-random data and compared on the device; any mismatch switches
+// the TMA path off for the process (the cp.async kernel then carries everything, ~5-8% slower (T)).
+__global__ void k_selftest_fill(double* x, long long n, unsigned seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned h = (unsigned)(i * 2654435761u) ^ seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    x[i] = ((double)h / 4294967296.0 - 0.5) * 2e-2;
+  }
+}
+__global__ void k_selftest_cmp(const double* a, const double* b, long long n, double tol, unsigned long long* bad) {
+  unsigned long long c = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (fabs(a[i] - b[i]) > tol) ++c;
+  if (c) atomicAdd(bad, c);
+}
+int g_selftest_state = 0;   // 0 not run, 1 passed, -1 failed (TMA switched off)
+}  // namespace
+
+int gemm_tma_selftest_state() { return g_selftest_state; }
+
+// Runs once per process (first handle).  Returns true when the TMA kernel reproduced the cp.async kernel on every case.
+bool gemm_tma_selftest(cudaStream_t st) {
+  if (g_selftest_state != 0) return g_selftest_state > 0;
+  if (std::getenv("AFESP_TMA_SELFTEST") && std::atoi(std::getenv("AFESP_TMA_SELFTEST")) == 0) { g_selftest_state = 1; return true; }
+  struct Case { int M, N, K, batch, reps; double beta; };
+  const Case cases[] = {{64, 4096, 72, 48, 12, 0.0},      // (T)-shaped batch at v = 64, nbf = 72: K tail, 5 k-tiles
+                        {144, 13456, 144, 1, 4, 1.0},     // I_oooo . c with accumulate, edge M tile
+                        {180, 32400, 200, 4, 2, 0.0}};    // (T)-shaped batch of the default bench shape
+  const int scope0 = g_tma_scope;
+  unsigned long long total_bad = 0;
+  try {
+    DBuf cnt(1);
+    AFESP_CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, 8, st));
+    for (const Case& c : cases) {
+      const size_t na = (size_t)c.M * c.K * c.batch, nb = (size_t)c.K * c.N * c.batch, nc = (size_t)c.M * c.N * c.batch;
+      DBuf A(na + 16), B(nb + 16), C0(nc), C1(nc), C2(nc);
+      k_selftest_fill<<<592, 256, 0, st>>>(A.p, (long long)na + 16, 17u);
+      k_selftest_fill<<<592, 256, 0, st>>>(B.p, (long long)nb + 16, 91u);
+      k_selftest_fill<<<592, 256, 0, st>>>(C0.p, (long long)nc, 5u);
+      GemmBatch bt;
+      bt.count = c.batch; bt.strideA = (long long)c.M * c.K; bt.strideB = (long long)c.K * c.N; bt.strideC = (long long)c.M * c.N;
+      gemm_force_config(3);
+      g_tma_scope = 0;
+      AFESP_CUDA_CHECK(cudaMemcpyAsync(C1.p, C0.p, nc * 8, cudaMemcpyDeviceToDevice, st));
+      dgemm(st, 'N', 'N', c.M, c.N, c.K, 0.5, A.p, c.M, B.p, c.K, c.beta, C1.p, c.M, c.batch > 1 ? &bt : nullptr);
+      g_tma_scope = 2;
+      for (int r = 0; r < c.reps; ++r) {
+        AFESP_CUDA_CHECK(cudaMemcpyAsync(C2.p, C0.p, nc * 8, cudaMemcpyDeviceToDevice, st));
+        dgemm(st, 'N', 'N', c.M, c.N, c.K, 0.5, A.p, c.M, B.p, c.K, c.beta, C2.p, c.M, c.batch > 1 ? &bt : nullptr);
+        k_selftest_cmp<<<592, 256, 0, st>>>(C1.p, C2.p, (long long)nc, 1e-12,
+                                            reinterpret_cast<unsigned long long*>(cnt.p));
+      }
+      AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    AFESP_CUDA_CHECK(cudaMemcpy(&total_bad, cnt.p, 8, cudaMemcpyDeviceToHost));
+  } catch (...) {
+    gemm_force_config(-1);
+    g_tma_scope = scope0;
+    throw;
+  }
+  gemm_force_config(-1);
+  g_tma_scope = scope0;
+  g_selftest_state = total_bad == 0 ? 1 : -1;
+  if (total_bad != 0) g_tma_scope = 0;
+  return total_bad == 0;
+}
+
+void gemm_tma_scope(int scope) { g_tma_scope = (g_selftest_state < 0) ? 0 : scope; }
 int gemm_tma_scope_get() { return g_tma_scope; }
 
 // Returns false when the TMA path does not apply (the caller then runs the cp.async kernel).

@@ -460,8 +460,12 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
   const bool al16 = (v % 2 == 0) && (o % 2 == 0);
   const int perm6[6][3] = {{0, 1, 2}, {1, 0, 2}, {2, 1, 0}, {0, 2, 1}, {1, 2, 0}, {2, 0, 1}};
 
-  static const bool verify_env = std::getenv("AFESP_T_VERIFY") != nullptr;
-  const bool verify_t = verify_env && gemm_tma_scope_get() != 0;
+  // AFESP_T_VERIFY=1: every batch also through the cp.async kernel, compared on the device; =2: control experiment,
+  // the cp.async kernel against itself (both passes with the TMA path switched off)
+  static const int verify_mode = std::getenv("AFESP_T_VERIFY") ? std::atoi(std::getenv("AFESP_T_VERIFY")) : 0;
+  const int scope_at_entry = gemm_tma_scope_get();
+  if (verify_mode == 2) gemm_tma_scope(0);
+  const bool verify_t = verify_mode == 2 || (verify_mode == 1 && gemm_tma_scope_get() != 0);
   std::unique_ptr<Scratch> verify_buf, verify_cnt;
   double verify_elems = 0.0;
   if (verify_t) {
@@ -571,7 +575,9 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
     AFESP_CUDA_CHECK(cudaMemcpy(cnt, verify_cnt->p, 16, cudaMemcpyDeviceToHost));
     double worst;
     std::memcpy(&worst, &cnt[1], 8);
-    std::fprintf(stderr, "[afesp T verify] TMA vs cp.async over %.3e X elements: %llu mismatches (worst |diff| %.3e)\n",
+    if (verify_mode == 2) gemm_tma_scope(scope_at_entry);
+    std::fprintf(stderr, verify_mode == 2 ? "[afesp T verify] CONTROL cp.async vs cp.async over %.3e X elements: %llu mismatches (worst |diff| %.3e)\n" :
+                         "[afesp T verify] TMA vs cp.async over %.3e X elements: %llu mismatches (worst |diff| %.3e)\n",
                  verify_elems, cnt[0], cnt[0] ? worst : 0.0);
   }
   for (size_t bi = 0; bi < nbatches; ++bi)

@@ -379,6 +379,7 @@ def run_ours(args, rank, world, local):
                     "breakdown_s": {k: x / ksteps for k, x in parts.items()}},
             "gpu_launches": int(l1 - l0),
             "clocks": clocks,
+            "tma": dict(zip(("scope", "selftest"), gpu.tma_status())),
             "hbm_kernels": hbm,
         }
         if world > 1:
