@@ -175,14 +175,6 @@ int afesp_gpu_open(int device, afesp_handle* out) {
     delete h;
     return 2;
   }
-  try {
-    gemm_tma_selftest(h->s.eng.stream);   // once per process; a mismatch switches the TMA path off (see gemm_tma.cu)
-  } catch (const std::exception& e) {
-    g_open_error = std::string("afesp_gpu_open: TMA self-test could not run: ") + e.what();
-    cudaStreamDestroy(h->s.eng.stream);
-    delete h;
-    return 2;
-  }
   h->launches0 = g_launch_count;
   h->flops0 = g_gemm_flops;
   *out = h;
@@ -231,7 +223,12 @@ int afesp_gpu_set_option(afesp_handle hv, const char* key, double value) {
     else if (k == "finalize_keep_ccsd") o.finalize_keep_ccsd = value != 0.0;
     else if (k == "gemm_timing") gemm_timing_enable(value != 0.0);
     else if (k == "gemm_force_config") gemm_force_config((int)value);
-    else if (k == "gemm_use_tma") gemm_tma_scope((int)value);   // 0 off, 1 (T) batches only (default), 2 all aligned GEMMs
+    else if (k == "gemm_use_tma") {
+      // 0 off (default), 1 the gathered (T) batches, 2 every aligned GEMM.  Switching it on runs the consistency check
+      // against the cp.async kernel first (once per process); if that fails the path stays off (afesp_gpu_tma_status).
+      if ((int)value > 0) gemm_tma_selftest(h.s.eng.stream);
+      gemm_tma_scope((int)value);
+    }
     else if (k == "dist_min_flops") h.s.eng.dist.min_flops = value;   // GEMMs below this stay replicated
     else if (k == "dist_ccsd") h.s.eng.dist.enabled = value != 0.0;       // 0: replicate CCSD / AO->MO, shard only (T)
     else throw Error(1, "set_option: unknown key " + k);

@@ -101,6 +101,7 @@ struct Params {
   const double* const* Ap;
   const double* const* Bp;
   double* const* Cp;
+  int zfast;             // > 0: batch-fastest rasterisation on a 1-D grid (value = batch count), see the kernel
   int splitk;            // >1: write raw partials to ws[split][M*N]
   int kchunk;            // K extent per split (multiple of BK)
   double* ws;
@@ -121,10 +122,21 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) gemm_f64_dmm
   const int gid = lane >> 2, tig = lane & 3;
   const int wm0 = (warp % (BM / WM)) * WM;
   const int wn0 = (warp / (BM / WM)) * WN;
-  const int m0 = (blockIdx.x % p.tiles_m) * BM, n0 = (blockIdx.x / p.tiles_m) * BN;
-
-  int batch = blockIdx.z, split = 0;
-  if (p.splitk > 1) { split = blockIdx.z % p.splitk; batch = blockIdx.z / p.splitk; }
+  // Rasterisation.  Pointer-array batches (the (T) driver sorts them by their B block) walk (m-tile, batch entry)
+  // fastest and the n-tile slowest on a 1-D grid, so the CTAs sharing one K x BN tile of B run back to back and B comes
+  // from DRAM once per distinct block; everything else uses (tile, batch/split) on grid.x / grid.z.
+  int m0, n0, batch, split = 0;
+  if (p.zfast > 0) {
+    const unsigned per_n = (unsigned)p.tiles_m * (unsigned)p.zfast;
+    const unsigned nt = blockIdx.x / per_n, rem = blockIdx.x - nt * per_n;
+    batch = (int)(rem / (unsigned)p.tiles_m);
+    m0 = (int)(rem - (unsigned)batch * p.tiles_m) * BM;
+    n0 = (int)nt * BN;
+  } else {
+    m0 = (blockIdx.x % p.tiles_m) * BM; n0 = (blockIdx.x / p.tiles_m) * BN;
+    batch = blockIdx.z;
+    if (p.splitk > 1) { split = blockIdx.z % p.splitk; batch = blockIdx.z / p.splitk; }
+  }
   const double* A = p.Ap ? p.Ap[batch] : p.A + batch * p.sA;
   const double* B = p.Bp ? p.Bp[batch] : p.B + batch * p.sB;
   double* C = p.Cp ? p.Cp[batch] : p.C + batch * p.sC;
@@ -330,6 +342,11 @@ void launch_cfg(cudaStream_t st, const Params& p, int nbatch) {
   const long long tiles = (long long)q.tiles_m * ((p.N + BN - 1) / BN);
   AFESP_REQUIRE(tiles < (1LL << 31), "gemm: too many tiles");
   dim3 grid((unsigned)tiles, 1, nbatch * (p.splitk > 1 ? p.splitk : 1));
+  q.zfast = 0;
+  if (nbatch > 1 && p.splitk <= 1 && p.Bp != nullptr && tiles * nbatch < (1LL << 31)) {
+    q.zfast = nbatch;
+    grid = dim3((unsigned)(tiles * nbatch), 1, 1);
+  }
   AFESP_REQUIRE(grid.z <= 65535, "gemm: batch too large");
   kern<<<grid, NT, SMEM, st>>>(q);
   count_launch();

@@ -196,6 +196,9 @@ def run_ours(args, rank, world, local):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.tma:
+        gpu.set_option("gemm_use_tma", args.tma)
+    tma_scope, tma_selftest = gpu.tma_status()
     peak = max(gpu.dmma_peak(), gpu.dmma_peak())
     # ---- device-resident leg
     npair = n * (n + 1) // 2
@@ -329,7 +332,7 @@ def run_ours(args, rank, world, local):
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_gemm_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and tma_scope >= 1:   # the committed capture is of the TMA kernel
             try:
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch", {}).get(f"nbf{n}")
             except Exception:
@@ -361,9 +364,8 @@ def run_ours(args, rank, world, local):
                                      "gemm_share_of_step": tot_ms * 1e-3 / elapsed if elapsed > 0 else None},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "kernel": "gemm_f64_tma<N,N> batched over (ijk-permutations): (T) contraction "
-                                   f"M={v} N={v * v} K={n} per block (the cp.async twin gemm_f64_dmma runs when v or "
-                                   "nbf is odd)",
+                         "kernel": ("gemm_f64_tma<N,N>" if tma_scope >= 1 else "gemm_f64_dmma<64,64,16> (cp.async ring)") +
+                                   f" batched over (ijk-permutations): (T) contraction M={v} N={v * v} K={n} per block",
                          "launches": t_nl, "flops_per_launch": (t_fl / t_nl) if t_nl else None,
                          "ms_per_launch": (t_ms / t_nl) if t_nl else None,
                          "share_of_step": t_ms * 1e-3 / elapsed if elapsed > 0 else None,
@@ -399,6 +401,8 @@ def main():
     ap.add_argument("--nbf", type=int, default=200)
     ap.add_argument("--nocc", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--tma", type=int, default=0, help="gemm_use_tma: 0 cp.async kernels (default), 1 TMA for the (T) "
+                                                       "batches, 2 TMA for every aligned GEMM (see DESIGN.md 4.1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

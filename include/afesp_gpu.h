@@ -44,14 +44,15 @@ const char* afesp_gpu_last_error(afesp_handle h); /* h may be NULL: error of the
  *   "finalize_keep_ccsd"       afesp_gpu_ccsd_finalize keeps the DIIS history and intermediates (benchmark loops)
  *   "gemm_timing"              bracket every DMMA GEMM launch with CUDA events (see afesp_gpu_gemm_time)
  * Kernel selection:
- *   "gemm_use_tma"             0 = cp.async kernels only; 1 (default) = the TMA-staged kernel for the gathered (T)
- *                              batches; 2 = also for every other aligned GEMM the 64x64 tile is chosen for
+ *   "gemm_use_tma"             0 (default) = cp.async kernels only; 1 = the TMA-staged kernel for the gathered (T)
+ *                              batches; 2 = also for every other aligned GEMM the 64x64 tile is chosen for.  Values
+ *                              > 0 first run a consistency check against the cp.async kernel (afesp_gpu_tma_status)
  *   "gemm_force_config"        tile menu entry (tuning aid), -1 = automatic
  *   "dist_ccsd", "dist_min_flops"   see the multi-GPU section below */
 int afesp_gpu_set_option(afesp_handle h, const char* key, double value);
 /* State of the TMA-staged GEMM path: *scope = value of "gemm_use_tma" in force; *selftest = 1 when the start-up
  * consistency check against the cp.async kernel passed on this device, -1 when it failed (the TMA path is then off for
- * the process and cannot be switched on), 0 when it was skipped (environment AFESP_TMA_SELFTEST=0). */
+ * the process and cannot be switched on), 0 when it has not run (TMA never requested). */
 int afesp_gpu_tma_status(afesp_handle h, int* scope, int* selftest);
 /* Kernel launches and executed DMMA flop (2*M*N*K per GEMM) since the handle was opened. */
 int afesp_gpu_counters(afesp_handle h, long long* launches, double* gemm_flops);

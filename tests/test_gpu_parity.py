@@ -117,37 +117,6 @@ def test_elementwise_oovv_kernels_match_numpy(gpu):
     assert np.max(np.abs(t2_dev - t2)) < 1e-14
 
 
-def test_triples_tma_kernel_equals_cpasync_kernel(gpu):
-    """The (T) contraction through the TMA-staged GEMM (default) against the cp.async GEMM on an even-dimensioned
-    synthetic system (the sample molecules have odd o, v and never reach the TMA path): all six sums to 1e-13
-    relative, three repetitions each (the result must also be reproducible run to run)."""
-    from afesp_b200 import synthetic
-
-    n, o = 72, 8
-    eri, Cmo, eps = synthetic.make(n, o, seed=9)
-    gpu.ao2mo(n, eri, Cmo, want_result=False)
-    gpu.set_option("finalize_keep_ccsd", 1)
-    gpu.ccsd_init(o, True, eps, 8)
-    for _ in range(4):
-        gpu.ccsd_iterate()
-        gpu.ccsd_diis()
-    gpu.ccsd_finalize(want_cr=True)
-    got = {}
-    try:
-        for scope in (0, 1, 1, 1):
-            gpu.set_option("gemm_use_tma", scope)
-            sums, _ = gpu.ccsd_t_spatial(True, False, True)
-            got.setdefault(scope, []).append(np.array(sums))
-    finally:
-        gpu.set_option("gemm_use_tma", 1)
-        gpu.set_option("finalize_keep_ccsd", 0)
-    ref = got[0][0]
-    assert np.all(np.abs(ref[[0, 1, 2, 3, 4, 5]]) > 0)
-    for s in got[1]:
-        assert np.max(np.abs(s - ref) / np.abs(ref)) < 1e-13
-        assert np.array_equal(s, got[1][0])
-
-
 # ---------------------------------------------------------------- AO->MO + MP2
 @pytest.mark.parametrize("name", ["n2", "f2", "h2o"])
 def test_ao2mo_and_mp2_match_oracle_and_golden(gpu, name, oracle_runs):
