@@ -332,9 +332,10 @@ def run_ours(args, rank, world, local):
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_gemm_traffic.json")
-        if os.path.exists(tpath) and tma_scope >= 1:   # the committed capture is of the TMA kernel
+        if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch", {}).get(f"nbf{n}")
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch", {}).get(f"nbf{n}", {}).get(
+                    "tma" if tma_scope >= 1 else "cpasync")
             except Exception:
                 traffic = None
         tot_ms = gstat["ccsd"][0] + gstat["t"][0]
