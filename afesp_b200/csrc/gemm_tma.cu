@@ -71,6 +71,12 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
@@ -132,7 +138,7 @@ __global__ void __launch_bounds__(NT, 3) gemm_f64_tma(const __grid_constant__ CU
   const int nk = (p.K + BK - 1) / BK;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS * 32); /* every consumer lane arrives */ }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -176,29 +182,36 @@ __global__ void __launch_bounds__(NT, 3) gemm_f64_tma(const __grid_constant__ CU
       boff[s][i] = tile_off<BKM>(wn0 + 8 * i + gid, k);
     }
   }
-  // Every warp issues the full 4x4 fragment grid, also in edge tiles.  (Skipping the fragments that lie outside C
-  // was tried: it gains ~1.5% on M = 360 but made edge-tile results irreproducible when the epilogue also reads C,
-  // beta != 0 -- tools/tma_edge_probe.py -- so it is not used.)
+  // Every warp issues the full 4x4 fragment grid, also in edge tiles.
+  //
+  // Slot release.  The first version released slot s right after the DMMAs of its k-tile: `__syncwarp(); if (lane == 0)
+  // arrive(empty[s])`.  The SASS showed why that produced sporadic wrong 32-byte sectors: the fragment loads were
+  // generic LD.E (the shared address space was lost in the pointer round-up), the WARPSYNC had been hoisted above most
+  // of them, and the SYNCS.ARRIVE was scheduled right behind the last loads and *ahead of* the DMMAs that consume them --
+  // so a slot could be handed back to the producer while fragment loads of some lanes were still in flight, and the
+  // next TMA write raced them.  Now (i) fragments are read with explicit ld.shared, (ii) every lane arrives for itself
+  // (barrier count NCONS*32), and (iii) the release of k-tile kt-1 is issued only after the wait for k-tile kt: by then
+  // the DMMAs of kt-1 have been issued, which requires all of this lane's fragment loads of kt-1 to have returned.
+  const unsigned smem_s = smem_u32(smem);
   for (int kt = 0; kt < nk; ++kt) {
     const int s = kt % STAGES;
     mbar_wait(&full[s], (kt / STAGES) & 1);
-    const unsigned char* sa = smem + s * STAGE_BYTES;
-    const unsigned char* sb = sa + TILE_BYTES;
+    if (kt > 0) mbar_arrive(&empty[(kt - 1) % STAGES]);
+    const unsigned sa = smem_s + s * STAGE_BYTES, sb = sa + TILE_BYTES;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       double af[4], bf[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) af[i] = *reinterpret_cast<const double*>(sa + aoff[g][i]);
+      for (int i = 0; i < 4; ++i) af[i] = lds_f64(sa + aoff[g][i]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = *reinterpret_cast<const double*>(sb + boff[g][j]);
+      for (int j = 0; j < 4; ++j) bf[j] = lds_f64(sb + boff[g][j]);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
   }
+  // (the last k-tile's slot needs no release: nothing is loaded after it)
 
   // ---------------- epilogue (same fragment ownership as gemm_f64_dmma) ----------------
   double* C = p.Cp ? p.Cp[batch] : p.C + batch * p.sC;

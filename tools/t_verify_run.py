@@ -4,6 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from afesp_b200 import AfespGpu, synthetic
 n, o = int(os.environ.get("NBF", 200)), int(os.environ.get("NOCC", 20))
 g = AfespGpu(0)
+g.set_option("gemm_use_tma", int(os.environ.get("TMA", 1)))   # the TMA path is opt-in; this tool exists to check it
+print("tma status (scope, selftest):", g.tma_status(), flush=True)
 if n > 240:
     Bfac, Cmo, eps = synthetic.make_factors(n, o)
     g.synth_eri_ao(n, Bfac, Cmo)
