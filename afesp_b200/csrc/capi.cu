@@ -175,6 +175,17 @@ int afesp_gpu_open(int device, afesp_handle* out) {
     delete h;
     return 2;
   }
+  if (gemm_tma_scope_get() > 0) {
+    // once per process: the TMA-staged kernel must reproduce the cp.async kernel on this device, else it is switched off
+    try {
+      gemm_tma_selftest(h->s.eng.stream);
+    } catch (const std::exception& e) {
+      g_open_error = std::string("afesp_gpu_open: TMA self-test could not run: ") + e.what();
+      cudaStreamDestroy(h->s.eng.stream);
+      delete h;
+      return 2;
+    }
+  }
   h->launches0 = g_launch_count;
   h->flops0 = g_gemm_flops;
   *out = h;

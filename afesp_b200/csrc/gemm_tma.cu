@@ -319,7 +319,7 @@ bool make_map(CUtensorMap* map, bool kmajor, const double* base, long long MN, l
   return r == CUDA_SUCCESS;
 }
 
-int g_tma_scope = 0;   // 0 = off (default), 1 = gathered (T) batches, 2 = every aligned 64x64-tile problem
+int g_tma_scope = 1;   // 0 = off, 1 = gathered (T) batches (default), 2 = every aligned 64x64-tile problem
 
 }  // namespace
 

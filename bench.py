@@ -196,7 +196,7 @@ def run_ours(args, rank, world, local):
             dist.barrier()
         torch.cuda.synchronize()
 
-    if args.tma:
+    if args.tma >= 0:
         gpu.set_option("gemm_use_tma", args.tma)
     tma_scope, tma_selftest = gpu.tma_status()
     peak = max(gpu.dmma_peak(), gpu.dmma_peak())
@@ -402,8 +402,8 @@ def main():
     ap.add_argument("--nbf", type=int, default=200)
     ap.add_argument("--nocc", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--tma", type=int, default=0, help="gemm_use_tma: 0 cp.async kernels (default), 1 TMA for the (T) "
-                                                       "batches, 2 TMA for every aligned GEMM (see DESIGN.md 4.1)")
+    ap.add_argument("--tma", type=int, default=-1, help="gemm_use_tma: -1 library default (1: TMA-staged kernel for the "
+                                                        "(T) batches), 0 cp.async kernels only, 2 TMA for every aligned GEMM")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -44,9 +44,10 @@ const char* afesp_gpu_last_error(afesp_handle h); /* h may be NULL: error of the
  *   "finalize_keep_ccsd"       afesp_gpu_ccsd_finalize keeps the DIIS history and intermediates (benchmark loops)
  *   "gemm_timing"              bracket every DMMA GEMM launch with CUDA events (see afesp_gpu_gemm_time)
  * Kernel selection:
- *   "gemm_use_tma"             0 (default) = cp.async kernels only; 1 = the TMA-staged kernel for the gathered (T)
- *                              batches; 2 = also for every other aligned GEMM the 64x64 tile is chosen for.  Values
- *                              > 0 first run a consistency check against the cp.async kernel (afesp_gpu_tma_status)
+ *   "gemm_use_tma"             0 = cp.async kernels only; 1 (default) = the TMA-staged kernel for the gathered (T)
+ *                              batches; 2 = also for every other aligned GEMM the 64x64 tile is chosen for.  With a
+ *                              value > 0 a consistency check against the cp.async kernel runs once per process
+ *                              (at afesp_gpu_open / when switched on); if it fails the path is off (afesp_gpu_tma_status)
  *   "gemm_force_config"        tile menu entry (tuning aid), -1 = automatic
  *   "dist_ccsd", "dist_min_flops"   see the multi-GPU section below */
 int afesp_gpu_set_option(afesp_handle h, const char* key, double value);
