@@ -2,11 +2,13 @@
 //
 // Replaces the reference's omp_reshape (24 fypp-generated 4-index permutations with optional beta,
 // src/linalg.fpp:99-156) and the intrinsic reshape(..., order=) call sites in src/ccsd.f90.
-// HBM-bound: 16 B moved per element (+8 B when beta != 0).  Two kernels:
-//   * axis 0 preserved  -> straight coalesced gather (reads and writes both run along the fastest axis);
-//   * axis 0 moved      -> 32x32 shared-memory tile transpose over (input-fastest, output-fastest) axes so that
-//                          both the global read and the global write are coalesced 256-byte rows.
-// Adjacent axes that stay adjacent are merged first, so e.g. (i,j,a,b)->(a,b,i,j) runs as a 2-D transpose.
+// HBM-bound: 16 B moved per element (+8 B when beta != 0).  Adjacent axes that stay adjacent are merged first
+// (e.g. (i,j,a,b)->(a,b,i,j) runs as a 2-D transpose); then one of four kernels:
+//   * permute_rows          axis 0 preserved: threads walk contiguous rows, the row index is decoded once per row;
+//   * permute_slab          leading axes shuffled among themselves, <= 4000 elements: contiguous slabs staged through
+//                           shared memory, the in-slab permutation comes from a table built once per block;
+//   * permute_transpose64   axis 0 moved, both transposed extents >= 48: 64x64 shared-memory tile, 512-byte rows;
+//   * permute_transpose     axis 0 moved, small extents: 32x32 shared-memory tile.
 #include <algorithm>
 
 #include "common.cuh"
@@ -15,35 +17,6 @@ namespace afesp {
 namespace {
 
 constexpr int MAXR = 6;
-
-struct PermParams {
-  int rank;
-  int odims[MAXR];          // output extents
-  long long istr[MAXR];     // input stride of the input axis feeding output axis d
-  long long ostr[MAXR];     // output stride of output axis d (ostr[0] == 1)
-  long long total;
-  double alpha, beta;
-};
-
-__global__ void permute_gather(const PermParams p, const double* __restrict__ in, double* __restrict__ out) {
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < p.total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    long long rem = idx, off = 0, oo = 0;
-#pragma unroll
-    for (int d = 0; d < MAXR; ++d) {
-      if (d < p.rank) {
-        long long q = rem / p.odims[d];
-        long long c = rem - q * p.odims[d];
-        off += c * p.istr[d];
-        oo += c * p.ostr[d];
-        rem = q;
-      }
-    }
-    double v = p.alpha * in[off];
-    if (p.beta != 0.0) v += p.beta * out[oo];
-    out[oo] = v;
-  }
-}
 
 struct TransParams {
   int n0, nb;                 // extents of input axis 0 and of the input axis that becomes output axis 0

