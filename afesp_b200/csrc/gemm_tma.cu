@@ -8,7 +8,7 @@
 //   * tiles land in the 128-byte-swizzled layout TMA produces.  Bank conflicts are avoided by choosing WHICH four
 //     k-indices feed each DMMA: the 16 k's of a tile are split into the sets {0,3,12,15} {1,2,13,14} {4,7,8,11}
 //     {5,6,9,10}; with that assignment every fragment load of a half-warp touches 16 distinct 8-byte banks for both
-//     the MN-major box layout [mn/16][k][16] and the K-major layout [mn][16 k] (derivation in DESIGN.md §4.1).
+//     the MN-major box layout [mn/16][k][16] and the K-major layout [mn][16 k] (enumerated in tests/test_tma_layout.py).
 // Operands may be batched three ways: plain, strided, or gathered through per-batch block indices (the (T) driver
 // gathers A by occupied pair and B by occupied index); tensor maps carry the batch as the outermost dimension.
 // Requirements (checked by the caller, otherwise the cp.async kernel runs): 16-byte aligned bases, even leading
