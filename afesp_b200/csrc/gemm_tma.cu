@@ -3,8 +3,10 @@
 // Same math and epilogue as gemm_f64_dmma (gemm.cu); what changes is how operand tiles reach shared memory:
 //   * one producer warp: an elected lane arms an mbarrier with the stage's byte count and issues two
 //     cp.async.bulk.tensor (TMA) copies per k-tile -- no per-thread address arithmetic, no cp.async groups;
-//   * four consumer warps (32x32 DMMA sub-tiles of a 64x64 CTA tile) wait on the stage's "full" mbarrier, issue the
-//     DMMAs and release the slot through its "empty" mbarrier: the main loop has no CTA-wide barrier at all;
+//   * four consumer warps (32x32 DMMA sub-tiles of a 64x64 CTA tile) wait on the stage's "full" mbarrier, read their
+//     fragments with ld.shared, issue the DMMAs and release the slot through its "empty" mbarrier -- every lane arrives
+//     for itself, one k-tile late (after the wait for the next tile), so that no fragment load can still be in flight
+//     when the producer refills the slot (see the comment at the main loop); there is no CTA-wide barrier in the loop;
 //   * tiles land in the 128-byte-swizzled layout TMA produces.  Bank conflicts are avoided by choosing WHICH four
 //     k-indices feed each DMMA: the 16 k's of a tile are split into the sets {0,3,12,15} {1,2,13,14} {4,7,8,11}
 //     {5,6,9,10}; with that assignment every fragment load of a half-warp touches 16 distinct 8-byte banks for both
