@@ -133,12 +133,19 @@ def read_inputs(dirpath) -> ElsInput:
     inp.ovlp = _sym_from_triples(s, n)
     inp.core_hamil = _sym_from_triples(np.loadtxt(os.path.join(dirpath, "t.dat"), ndmin=2), n) + \
         _sym_from_triples(np.loadtxt(os.path.join(dirpath, "v.dat"), ndmin=2), n)
-    d = np.loadtxt(os.path.join(dirpath, "eri.dat"), ndmin=2)
-    idx = d[:, :4].astype(np.int64) - 1
     npair = n * (n + 1) // 2
-    eri = np.zeros(npair * (npair + 1) // 2)
-    eri[pair_index(pair_index(idx[:, 0], idx[:, 1]), pair_index(idx[:, 2], idx[:, 3]))] = d[:, 4]
-    inp.eri = eri
+    bin_path = os.path.join(dirpath, "eri.bin")
+    if os.path.exists(bin_path):
+        # extension for large basis sets: the packed array itself, little-endian float64
+        inp.eri = np.fromfile(bin_path, dtype="<f8")
+        if inp.eri.size != npair * (npair + 1) // 2:
+            raise ValueError("integrals::read_integrals_in: eri.bin does not hold npair(npair+1)/2 doubles for this basis")
+    else:
+        d = np.loadtxt(os.path.join(dirpath, "eri.dat"), ndmin=2)
+        idx = d[:, :4].astype(np.int64) - 1
+        eri = np.zeros(npair * (npair + 1) // 2)
+        eri[pair_index(pair_index(idx[:, 0], idx[:, 1]), pair_index(idx[:, 2], idx[:, 3]))] = d[:, 4]
+        inp.eri = eri
     with open(os.path.join(dirpath, "geom.dat")) as f:
         toks = f.read().split()
     nat = int(toks[0])

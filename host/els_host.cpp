@@ -179,6 +179,19 @@ void read_integrals_in(Sys& s) {
   for (size_t k = 0; k < s.hcore.size(); ++k) s.hcore[k] = ke[k] + en[k];
   const long long npair = (long long)n * (n + 1) / 2;
   s.eri.assign((size_t)(npair * (npair + 1) / 2), 0.0);
+  {
+    // Extension for large basis sets: a text eri.dat at nbf = 400 would be ~3e9 lines and the
+    // reference's default-integer pair index overflows there.  If `eri.bin` is present it is taken instead: the packed
+    // 8-fold-unique array itself (npair(npair+1)/2 little-endian doubles, canonical order of src/integrals.f90:196-210,
+    // 64-bit indices).
+    std::ifstream fb("eri.bin", std::ios::binary);
+    if (fb) {
+      fb.read(reinterpret_cast<char*>(s.eri.data()), (std::streamsize)(s.eri.size() * sizeof(double)));
+      if ((size_t)fb.gcount() != s.eri.size() * sizeof(double) || fb.peek() != EOF)
+        fail("integrals::read_integrals_in", "eri.bin does not hold npair(npair+1)/2 doubles for this basis");
+      return;
+    }
+  }
   std::ifstream f("eri.dat");
   if (!f) fail("integrals::read_integrals_in", "cannot open eri.dat");
   long long i, j, k, l;

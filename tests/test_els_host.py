@@ -46,3 +46,24 @@ def test_els_host_error_behaviour(tmp_path):
     write_sample_dir("n2", str(tmp_path), calc_type="CCSD(Q)_spatial")
     r = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0 and "Unrecognised calculation type!" in r.stderr
+
+
+def test_binary_packed_integrals_are_read_by_both_hosts(tmp_path):
+    """eri.bin (the packed array as little-endian doubles, for basis sets whose text eri.dat
+    would be billions of lines) gives the same SCF as eri.dat, in the C++ host and in the Python host."""
+    from afesp_b200 import host
+
+    write_sample_dir("f2", str(tmp_path), calc_type="RHF")
+    r1 = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=300)
+    z = np.load(os.path.join(GOLDEN_DIR, "f2.npz"))
+    z["eri"].astype("<f8").tofile(str(tmp_path / "eri.bin"))
+    os.remove(tmp_path / "eri.dat")
+    r2 = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r1.returncode == 0 and r2.returncode == 0, r2.stderr
+    assert [ln for ln in r1.stdout.splitlines() if "energy" in ln] == [ln for ln in r2.stdout.splitlines() if "energy" in ln]
+    inp = host.read_inputs(str(tmp_path))
+    assert np.array_equal(inp.eri, z["eri"])
+    # a truncated file is refused with the reference's error block
+    z["eri"][:-3].astype("<f8").tofile(str(tmp_path / "eri.bin"))
+    r3 = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert r3.returncode != 0 and "eri.bin" in r3.stderr
