@@ -45,6 +45,8 @@ SIGNATURES = {
     "afesp_gpu_bench_hbm": [_H, C.c_char_p, C.c_int, C.c_int, C.c_int, _dp, _dp],
     "afesp_gpu_gemm_time": [_H, _dp, _dp],
     "afesp_gpu_gemm_stats": [_H, _dp, _dp, C.POINTER(C.c_longlong)],
+    "afesp_gpu_gemm_crosscheck": [_H, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                  C.POINTER(C.c_longlong), _dp, _dp],
 }
 
 _lib = None
@@ -299,6 +301,14 @@ class AfespGpu:
         self._check("bench_dgemm", self.lib.afesp_gpu_bench_dgemm(self.h, transA.encode(), transB.encode(), int(M),
                                                                   int(N), int(K), float(beta), int(reps), C.byref(ms)))
         return ms.value
+
+    def gemm_crosscheck(self, transA, transB, M, N, K, nbatch=1, beta=0.0, reps=10):
+        """TMA-staged kernel vs cp.async kernel on one problem: (mismatching elements, ms TMA, ms cp.async)."""
+        bad, a, b = C.c_longlong(0), C.c_double(0), C.c_double(0)
+        self._check("gemm_crosscheck", self.lib.afesp_gpu_gemm_crosscheck(
+            self.h, transA.encode(), transB.encode(), int(M), int(N), int(K), int(nbatch), float(beta), int(reps),
+            C.byref(bad), C.byref(a), C.byref(b)))
+        return bad.value, a.value, b.value
 
     def gemm_time(self):
         """(milliseconds, executed flop) of all DMMA GEMM launches since option gemm_timing was set / last call."""

@@ -232,11 +232,12 @@ int afesp_gpu_set_option(afesp_handle hv, const char* key, double value) {
     else if (k == "triples_ijk_symmetry") o.triples_ijk_symmetry = value != 0.0;
     else if (k == "triples_batch_bytes") o.triples_batch_bytes = (long long)value;
     else if (k == "finalize_keep_ccsd") o.finalize_keep_ccsd = value != 0.0;
+    else if (k == "spinorb_symmetry_tol") o.spinorb_symmetry_tol = value;
     else if (k == "gemm_timing") gemm_timing_enable(value != 0.0);
     else if (k == "gemm_force_config") gemm_force_config((int)value);
     else if (k == "gemm_use_tma") {
-      // 0 off (default), 1 the gathered (T) batches, 2 every aligned GEMM.  Switching it on runs the consistency check
-      // against the cp.async kernel first (once per process); if that fails the path stays off (afesp_gpu_tma_status).
+      // 0 off, 1 the gathered (T) batches only, 2 every aligned GEMM the 64x64 tile is chosen for.  Switching it on runs
+      // the consistency check against the cp.async kernel first (once per process); if that fails the path stays off.
       if ((int)value > 0) gemm_tma_selftest(h.s.eng.stream);
       gemm_tma_scope((int)value);
     }
@@ -384,6 +385,13 @@ int afesp_gpu_ccsd_init(afesp_handle hv, int nocc, int restricted, const double*
     tm.stop();
     if (e_mp1) *e_mp1 = h.s.energy;
     if (rmst2) *rmst2 = h.s.rms;
+  });
+}
+
+int afesp_gpu_ccsd_init_info(afesp_handle hv, double info[4]) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(info != nullptr, "ccsd_init_info: null output");
+    info[0] = h.s.sym_err; info[1] = h.s.ms_slices * 1e-3; info[2] = h.s.ms_symcheck * 1e-3; info[3] = 0.0;
   });
 }
 
@@ -651,6 +659,16 @@ int afesp_gpu_bench_hbm(afesp_handle hv, const char* what, int o, int v, int rep
     AFESP_CUDA_CHECK(cudaGetLastError());
     *ms = h.last_ms / reps;
     *bytes = per * (double)n;
+  });
+}
+
+int afesp_gpu_gemm_crosscheck(afesp_handle hv, char ta, char tb, int M, int N, int K, int nbatch, double beta, int reps,
+                              long long* mismatches, double* ms_tma, double* ms_cpasync) {
+  return guarded(hv, [&](Handle& h) {
+    AFESP_REQUIRE(mismatches != nullptr, "gemm_crosscheck: null output");
+    unsigned long long bad = 0;
+    gemm_crosscheck(h.s.eng.stream, ta, tb, M, N, K, nbatch, beta, reps, &bad, ms_tma, ms_cpasync);
+    *mismatches = (long long)bad;
   });
 }
 

@@ -29,6 +29,7 @@ struct Options {
   bool triples_ijk_symmetry = true;     // (T): loop unique i<=j<=k with multiplicities instead of all o^3
   long long triples_batch_bytes = 6LL << 30;
   bool finalize_keep_ccsd = false;      // keep DIIS history and intermediates after finalize (benchmark loops)
+  double spinorb_symmetry_tol = 1e-12;  // depsilon (src/const.F90:19): abort threshold of the check at src/ccsd.f90:161
 };
 
 struct CCState {
@@ -65,6 +66,10 @@ struct CCState {
   }
   bool has(const std::string& name) const { return T.count(name) != 0; }
   void drop(const std::string& name) { T.erase(name); }
+
+  // spin-orbital integral preparation (src/ccsd.f90:106-202): error of the permutational-symmetry self-check and the
+  // device milliseconds of the slice gather and of the check (afesp_gpu_ccsd_init_info)
+  double sym_err = 0.0, ms_slices = 0.0, ms_symcheck = 0.0;
 
   bool finalized = false;
   bool have_cr = false;

@@ -29,6 +29,9 @@ void ccsd_spinorb_init(CCState& s, int diis_n) {
   AFESP_CUDA_CHECK(cudaStreamSynchronize(e.stream));
   // nine slices of <pq||rs> (src/ccsd.f90:182-194), gathered straight from the packed MO integrals: the (2n)^4
   // tensor of :108 is never formed.
+  cudaEvent_t ev[3];
+  for (auto& x : ev) AFESP_CUDA_CHECK(cudaEventCreate(&x));
+  AFESP_CUDA_CHECK(cudaEventRecord(ev[0], e.stream));
   for (const char* nm : {"oooo", "ooov", "ovoo", "oovo", "oovv", "ovvo", "ovvv", "vovv", "vvvv"}) {
     int lo[4], cnt[4];
     std::vector<int> dims;
@@ -40,6 +43,21 @@ void ccsd_spinorb_init(CCState& s, int diis_n) {
     Tensor& t = s.make(nm, dims);
     slice_spinorb(e, t.p(), s.eri_mo.p, lo, cnt);
   }
+  AFESP_CUDA_CHECK(cudaEventRecord(ev[1], e.stream));
+  // the reference's run-time assertion on <pq||rs> (src/ccsd.f90:150-167): same index set, same four identities, same
+  // threshold (depsilon); a violation aborts the calculation with the reference's message
+  if (s.red_out.n < 16) s.red_out.alloc(16);
+  spinorb_symmetry_error(e, n, s.eri_mo.p, s.red_out.p);
+  AFESP_CUDA_CHECK(cudaEventRecord(ev[2], e.stream));
+  AFESP_CUDA_CHECK(cudaMemcpyAsync(&s.sym_err, s.red_out.p, 8, cudaMemcpyDeviceToHost, e.stream));
+  AFESP_CUDA_CHECK(cudaStreamSynchronize(e.stream));
+  float ms01 = 0.f, ms12 = 0.f;
+  cudaEventElapsedTime(&ms01, ev[0], ev[1]);
+  cudaEventElapsedTime(&ms12, ev[1], ev[2]);
+  for (auto& x : ev) cudaEventDestroy(x);
+  s.ms_slices = ms01; s.ms_symcheck = ms12;
+  if (!(s.sym_err <= s.opt.spinorb_symmetry_tol))
+    throw Error(5, "Permutational symmetry of antisymmetrised integrals does not hold");
   s.t1.init({o, v}); s.t1n.init({o, v});
   s.t2.init({o, o, v, v}); s.t2n.init({o, o, v, v}); s.t2_old.init({o, o, v, v});
   fill(e.stream, s.t1.size(), 0.0, s.t1.p());

@@ -103,6 +103,8 @@ int gemm_tma_scope_get();
 // failure switches the TMA path off for the process.  State: 0 not run, 1 passed, -1 failed.
 bool gemm_tma_selftest(cudaStream_t st);
 int gemm_tma_selftest_state();
+void gemm_crosscheck(cudaStream_t st, char ta, char tb, int M, int N, int K, int nbatch, double beta, int reps,
+                     unsigned long long* bad, double* ms_tma, double* ms_ref);
 bool dgemm_tma(cudaStream_t st, bool ak, bool bk, int M, int N, int K, double alpha, const double* A, long long lda,
                const double* B, long long ldb, double beta, double* C, long long ldc, const GemmBatch* batch, int cvec);
 double gemm_timing_collect(double* flops_out, long long* launches_out = nullptr);

@@ -321,18 +321,17 @@ bool make_map(CUtensorMap* map, bool kmajor, const double* base, long long MN, l
   return r == CUDA_SUCCESS;
 }
 
-int g_tma_scope = 1;   // 0 = off, 1 = gathered (T) batches (default), 2 = every aligned 64x64-tile problem
+int g_tma_scope = 2;   // 0 = off, 1 = gathered (T) batches only, 2 (default since the round-2 soak, profiles/r02_tma_soak_*.json) = every aligned 64x64-tile problem
 
 }  // namespace
 
 namespace {
 // ---- start-up self-test ------------------------------------------------------------------------------------------
-// During this round the TMA-staged kernel produced sporadic wrong sectors on one physical B200 of the test pool
-// (serial 1651326046738: the (T)-shaped batch M=64 N=4096 K=72 failed in every run there) and never on the others,
-// while the cp.async kernel was consistent everywhere.  Whether that is a marginal part or a timing-dependent race in
-// this kernel is not settled, so the library checks the device it runs on: the shapes that
-// failed there are run through both kernels on pseudo-random data and compared on the device; any mismatch switches
-// the TMA path off for the process (the cp.async kernel then carries everything, ~5-8% slower (T)).
+// The first version of this kernel released ring slots too early (see the main-loop comment) and produced sporadic
+// wrong 32-byte sectors; the cp.async kernel (gemm.cu) shares no staging code with it.  As a guard the library runs the
+// shapes that used to fail through both kernels on pseudo-random data once per process and compares the results on the
+// device; a mismatch switches the TMA path off for the process (the cp.async kernel then carries everything).
+// gemm_crosscheck() below is the same comparison on a caller-chosen problem (soak runs, tools/gemm_soak.py).
 __global__ void k_selftest_fill(double* x, long long n, unsigned seed) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     unsigned h = (unsigned)(i * 2654435761u) ^ seed;
@@ -396,6 +395,60 @@ bool gemm_tma_selftest(cudaStream_t st) {
   g_selftest_state = total_bad == 0 ? 1 : -1;
   if (total_bad != 0) g_tma_scope = 0;
   return total_bad == 0;
+}
+
+// TMA-staged kernel against the cp.async kernel on one problem: the cp.async result is computed once, the TMA kernel
+// `reps` times on fresh copies of C, every result compared on the device.  Returns the number of elements that differ
+// by more than 1e-12 absolute (inputs are O(1e-2)) and the average device milliseconds of each kernel.
+void gemm_crosscheck(cudaStream_t st, char ta, char tb, int M, int N, int K, int nbatch, double beta, int reps,
+                     unsigned long long* bad, double* ms_tma, double* ms_ref) {
+  AFESP_REQUIRE(M > 0 && N > 0 && K > 0 && nbatch > 0 && reps > 0 && bad, "gemm_crosscheck: bad arguments");
+  const bool tA = (ta == 'T' || ta == 't'), tB = (tb == 'T' || tb == 't');
+  const long long lda = tA ? K : M, ldb = tB ? N : K;
+  const size_t na = (size_t)M * K * nbatch, nb = (size_t)K * N * nbatch, nc = (size_t)M * N * nbatch;
+  const int scope0 = g_tma_scope;
+  DBuf cnt(1), A(na + 16), B(nb + 16), C0(nc), C1(nc), C2(nc);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  AFESP_CUDA_CHECK(cudaEventCreate(&e0));
+  AFESP_CUDA_CHECK(cudaEventCreate(&e1));
+  auto elapsed = [&] { float ms = 0.f; cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1); return (double)ms; };
+  try {
+    AFESP_CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, 8, st));
+    k_selftest_fill<<<592, 256, 0, st>>>(A.p, (long long)na + 16, 17u);
+    k_selftest_fill<<<592, 256, 0, st>>>(B.p, (long long)nb + 16, 91u);
+    k_selftest_fill<<<592, 256, 0, st>>>(C0.p, (long long)nc, 5u);
+    GemmBatch bt;
+    bt.count = nbatch; bt.strideA = (long long)M * K; bt.strideB = (long long)K * N; bt.strideC = (long long)M * N;
+    const GemmBatch* pb = nbatch > 1 ? &bt : nullptr;
+    gemm_force_config(3);
+    g_tma_scope = 0;
+    AFESP_CUDA_CHECK(cudaMemcpyAsync(C1.p, C0.p, nc * 8, cudaMemcpyDeviceToDevice, st));
+    AFESP_CUDA_CHECK(cudaEventRecord(e0, st));
+    dgemm(st, ta, tb, M, N, K, 0.5, A.p, lda, B.p, ldb, beta, C1.p, M, pb);
+    AFESP_CUDA_CHECK(cudaEventRecord(e1, st));
+    if (ms_ref) *ms_ref = elapsed();
+    g_tma_scope = 2;
+    double tot = 0.0;
+    for (int r = 0; r < reps; ++r) {
+      AFESP_CUDA_CHECK(cudaMemcpyAsync(C2.p, C0.p, nc * 8, cudaMemcpyDeviceToDevice, st));
+      AFESP_CUDA_CHECK(cudaEventRecord(e0, st));
+      dgemm(st, ta, tb, M, N, K, 0.5, A.p, lda, B.p, ldb, beta, C2.p, M, pb);
+      AFESP_CUDA_CHECK(cudaEventRecord(e1, st));
+      k_selftest_cmp<<<592, 256, 0, st>>>(C1.p, C2.p, (long long)nc, 1e-12, reinterpret_cast<unsigned long long*>(cnt.p));
+      tot += elapsed();
+    }
+    if (ms_tma) *ms_tma = tot / reps;
+    AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
+    AFESP_CUDA_CHECK(cudaMemcpy(bad, cnt.p, 8, cudaMemcpyDeviceToHost));
+  } catch (...) {
+    gemm_force_config(-1);
+    g_tma_scope = scope0;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    throw;
+  }
+  gemm_force_config(-1);
+  g_tma_scope = scope0;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
 }
 
 void gemm_tma_scope(int scope) { g_tma_scope = (g_selftest_state < 0) ? 0 : scope; }

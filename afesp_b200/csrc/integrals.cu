@@ -136,6 +136,7 @@ __global__ void k_slice_phys(double* __restrict__ out, const double* __restrict_
   }
 }
 
+__device__ __forceinline__ double asym_spinorb(const double* __restrict__ g, int P, int Q, int R, int S);
 // out(P,Q,R,S) = <PQ||RS> over spin-orbitals (even = alpha, odd = beta of spatial orbital P/2), src/ccsd.f90:111-143
 __global__ void k_slice_spinorb(double* __restrict__ out, const double* __restrict__ g, SliceSpec sp) {
   const long long total = (long long)sp.n[0] * sp.n[1] * sp.n[2] * sp.n[3];
@@ -146,11 +147,45 @@ __global__ void k_slice_spinorb(double* __restrict__ out, const double* __restri
     int Q = (int)(t % sp.n[1]) + sp.lo[1]; t /= sp.n[1];
     int R = (int)(t % sp.n[2]) + sp.lo[2]; t /= sp.n[2];
     int S = (int)t + sp.lo[3];
-    int p = P >> 1, q = Q >> 1, r = R >> 1, s = S >> 1;
-    double val = 0.0;
-    if ((P & 1) == (R & 1) && (Q & 1) == (S & 1)) val += g[tri(tri(p, r), tri(q, s))];
-    if ((P & 1) == (S & 1) && (Q & 1) == (R & 1)) val -= g[tri(tri(p, s), tri(q, r))];
-    out[idx] = val;
+    out[idx] = asym_spinorb(g, P, Q, R, S);
+  }
+}
+
+// Permutational-symmetry self-check of the antisymmetrised spin-orbital integrals (src/ccsd.f90:150-167):
+//   err = sum_{p, q<=p, r<=p, s<=r} |<pq||rs> + <pq||sr>| + |<pq||rs> - <rs||pq>| + |<pq||rs> + <sr||pq>| + |<pq||rs> - <sr||qp>|
+// evaluated from the packed MO integrals through the same element function the slices are gathered with (the (2n)^4
+// tensor of :108 is never formed).  One thread per (p,q,r,s) of the full (2n)^4 box, masked to the reference's range;
+// warp-shuffle + per-block partial sums (fixed order: deterministic).
+__device__ __forceinline__ double asym_spinorb(const double* __restrict__ g, int P, int Q, int R, int S) {
+  const int p = P >> 1, q = Q >> 1, r = R >> 1, s = S >> 1;
+  double val = 0.0;
+  if ((P & 1) == (R & 1) && (Q & 1) == (S & 1)) val += g[tri(tri(p, r), tri(q, s))];
+  if ((P & 1) == (S & 1) && (Q & 1) == (R & 1)) val -= g[tri(tri(p, s), tri(q, r))];
+  return val;
+}
+__global__ void k_spinorb_symmetry(const double* __restrict__ g, int n2, double* __restrict__ partials) {
+  const long long total = (long long)n2 * n2 * n2 * n2;
+  double err = 0.0;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long t = idx;
+    const int s = (int)(t % n2); t /= n2;
+    const int r = (int)(t % n2); t /= n2;
+    const int q = (int)(t % n2);
+    const int p = (int)(t / n2);
+    if (q > p || r > p || s > r) continue;
+    const double x = asym_spinorb(g, p, q, r, s);
+    err += fabs(x + asym_spinorb(g, p, q, s, r)) + fabs(x - asym_spinorb(g, r, s, p, q)) +
+           fabs(x + asym_spinorb(g, s, r, p, q)) + fabs(x - asym_spinorb(g, s, r, q, p));
+  }
+  __shared__ double red[8];
+  for (int off = 16; off > 0; off >>= 1) err += __shfl_down_sync(0xffffffffu, err, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = err;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s2 = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s2 += red[w];
+    partials[blockIdx.x] = s2;
   }
 }
 
@@ -364,6 +399,17 @@ void mp2_energy(Engine& e, int n, int nocc, const double* eri_mo, const double* 
   double* part = reduce_scratch(e, nb);
   k_mp2<<<nb, 256, 0, e.stream>>>(eri_mo, eps, n, nocc, part);
   count_launch();
+  finish_partials(e, part, nb, 1, out_dev);
+}
+
+void spinorb_symmetry_error(Engine& e, int n, const double* eri_mo, double* out_dev) {
+  const int n2 = 2 * n;
+  const long long total = (long long)n2 * n2 * n2 * n2;
+  const int nb = std::min(grid_for(total), 148 * 8);
+  double* part = reduce_scratch(e, nb);
+  k_spinorb_symmetry<<<nb, 256, 0, e.stream>>>(eri_mo, n2, part);
+  count_launch();
+  AFESP_CUDA_CHECK(cudaGetLastError());
   finish_partials(e, part, nb, 1, out_dev);
 }
 

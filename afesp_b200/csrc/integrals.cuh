@@ -22,6 +22,10 @@ void slice_phys(Engine& e, double* out, const double* eri_mo, const int lo[4], c
 // out(P,Q,R,S) = <PQ||RS> over spin-orbital index ranges (src/ccsd.f90:111-143, 182-194)
 void slice_spinorb(Engine& e, double* out, const double* eri_mo, const int lo[4], const int cnt[4]);
 
+// err of the permutational-symmetry self-check of <pq||rs> (src/ccsd.f90:150-167), evaluated from the packed MO integrals;
+// result in out_dev[0].
+void spinorb_symmetry_error(Engine& e, int n, const double* eri_mo, double* out_dev);
+
 // Particle-particle ladder in (+/-)-symmetrised virtual-pair form (half the flop and memory of the dense v^4 slice):
 //   sum_ef c(ij,ef) <ef|ab> = 1/2 [ S Vp + A Vm ](ij,ab),  S/A = symmetric/antisymmetric parts of c in (e,f)
 // sign +1: Vp (P+ x P+), -1: Vm (P- x P-); columns [col0, col0 + ncols) only (ncols < 0: through the last column) --

@@ -9,7 +9,7 @@
  *
  * Conventions (what a Fortran caller needs):
  *   - every function returns an int status: 0 = ok, non-zero = failure (1 bad argument/state, 2 CUDA error,
- *     3 linear solve failed, 4 NCCL error); afesp_gpu_last_error() gives the text.  The shim maps a non-zero
+ *     3 linear solve failed, 4 NCCL error, 5 the reference's own run-time assertion on the integrals failed); afesp_gpu_last_error() gives the text.  The shim maps a non-zero
  *     status to `call error('afesp_gpu::<fn>', msg)` -> stderr + stop 999 (src/error_handling.f90:7-20).
  *   - scalars by value; arrays are caller-owned, contiguous, column-major real(c_double), never retained after the
  *     call returns; a NULL output pointer means "do not copy back".
@@ -83,6 +83,15 @@ int afesp_gpu_mp2_energy(afesp_handle h, int nocc, const double* eps, double* e_
  * nocc = number of doubly occupied spatial orbitals (sys%nel/2) in both formulations. */
 int afesp_gpu_ccsd_init(afesp_handle h, int nocc, int restricted, const double* eps, int diis_n_errmat,
                         double* e_mp1, double* rmst2);
+/* Spin-orbital integral preparation inside afesp_gpu_ccsd_init (restricted == 0), src/ccsd.f90:106-202: the nine
+ * slices of <pq||rs> are gathered from the packed MO integrals, then the reference's permutational-symmetry self-check
+ * (:150-167) runs on the device over the same index set.  If its error exceeds depsilon = 1e-12 (src/const.F90:19;
+ * option "spinorb_symmetry_tol") afesp_gpu_ccsd_init returns status 5 with the reference's message
+ * "Permutational symmetry of antisymmetrised integrals does not hold" (the host prints the
+ * 'Permutational symmetry error:' line from info[0] and stops through error('ccsd::do_ccsd', ...), :161-164).
+ * info[0] = the accumulated error, info[1] = device seconds of the slice gather, info[2] = device seconds of the
+ * check, info[3] = 0 (reserved).  Valid after afesp_gpu_ccsd_init returned 0 or 5. */
+int afesp_gpu_ccsd_init_info(afesp_handle h, double info[4]);
 /* One pass of the iteration body up to and including update_cc_energy (src/ccsd.f90:340-359 / 230-246):
  * stash amplitudes for DIIS, intermediates, amplitude equations, energy.  rmst2 is the squared norm the reference
  * prints (src/ccsd.f90:1806); the host applies the convergence test of :1805. */
@@ -138,6 +147,11 @@ int afesp_gpu_bench_dgemm(afesp_handle h, char transA, char transB, int M, int N
  * "divide" (T2 = X / D_ijab, 16 B), "energy" (E_CC + sum dT2^2 in one pass, 24 B), "axpby" (24 B).
  * Returns milliseconds per launch and the algorithmic bytes per launch. */
 int afesp_gpu_bench_hbm(afesp_handle h, const char* what, int nocc, int nvirt, int reps, double* ms, double* bytes);
+/* Soak aid: the TMA-staged GEMM kernel against the cp.async kernel on one (optionally strided-batched) problem with
+ * pseudo-random operands -- the cp.async result once, the TMA kernel `reps` times, each compared on the device.
+ * Returns the number of differing elements (tolerance 1e-12 on O(1e-2) data) and the mean milliseconds per launch. */
+int afesp_gpu_gemm_crosscheck(afesp_handle h, char transA, char transB, int M, int N, int K, int nbatch, double beta,
+                              int reps, long long* mismatches, double* ms_tma, double* ms_cpasync);
 /* Raw DMMA issue-rate probe: register-resident mma.sync loop on all SMs; returns TFLOP/s (the FP64 tensor peak the
  * roofline fractions are quoted against; MEASURED_PEAKS.json has no FP64 entry). */
 int afesp_gpu_dmma_peak(afesp_handle h, double* tflops);

@@ -8,6 +8,7 @@ ladder contraction through dgemm of the image's OpenBLAS (numpy), as the referen
 from __future__ import annotations
 
 import ctypes as C
+import glob
 import os
 import subprocess
 import time
@@ -21,11 +22,66 @@ SO = os.path.join(HERE, "_ref", "libafesp_cpu_port.so")
 _dp = C.POINTER(C.c_double)
 
 
+_blas_keepalive = []
+
+
+def _find_dgemm():
+    """Fortran-interface dgemm of the image's OpenBLAS (the library numpy / scipy ship): (address, ilp64, path)."""
+    import numpy
+    import scipy
+    for pkg, pat, sym, ilp64 in ((numpy, "numpy.libs/libscipy_openblas64_*.so", "scipy_dgemm_64_", 1),
+                                 (scipy, "scipy.libs/libscipy_openblas*.so", "scipy_dgemm_", 0)):
+        base = os.path.dirname(os.path.dirname(pkg.__file__))
+        for path in sorted(glob.glob(os.path.join(base, pat))):
+            try:
+                bl = C.CDLL(path)
+                fn = getattr(bl, sym)
+            except (OSError, AttributeError):
+                continue
+            _blas_keepalive.append(bl)
+            return C.cast(fn, C.c_void_p).value, ilp64, path, bl
+    raise RuntimeError("no OpenBLAS dgemm found in numpy.libs / scipy.libs")
+
+
+def set_threads(lib, nthreads=None):
+    """Use `nthreads` (default: every host core) for the OpenMP loops AND the OpenBLAS dgemms, whatever OMP_NUM_THREADS
+    says (torchrun exports OMP_NUM_THREADS=1).  Returns the thread count in force."""
+    n = int(nthreads or os.cpu_count() or 1)
+    lib.afesp_ref_set_threads(n)
+    bl = lib._blas
+    for sym in ("scipy_openblas_set_num_threads64_", "scipy_openblas_set_num_threads", "openblas_set_num_threads"):
+        if hasattr(bl, sym):
+            getattr(bl, sym)(C.c_int(n))
+            break
+    try:  # numpy's own matmul (the ladder helper below) goes through the same library; keep it in step
+        from threadpoolctl import threadpool_limits
+        lib._tp_limit = threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return n
+
+
 def load():
-    src = os.path.join(HERE, "cpu_kernels.c")
-    if not os.path.exists(SO) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(SO)):
+    srcs = [os.path.join(HERE, f) for f in ("cpu_kernels.c", "cpu_ccsd.c")]
+    if not os.path.exists(SO) or any(os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
         subprocess.run(["make", "-C", HERE], check=True, capture_output=True)
     lib = C.CDLL(SO)
+    addr, ilp64, path, bl = _find_dgemm()
+    lib.afesp_ref_set_dgemm.argtypes = [C.c_void_p, C.c_int]
+    lib.afesp_ref_set_dgemm(addr, ilp64)
+    lib._blas, lib._blas_path = bl, path
+    lib.afesp_ref_set_threads.argtypes = [C.c_int]
+    _ip = C.POINTER(C.c_int)
+    lib.afesp_ref_ccsd_iter.argtypes = [C.c_int, C.c_int] + [_dp] * 6 + [C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, _dp]
+    lib.afesp_ref_ccsd_iter.restype = None
+    lib.afesp_ref_ao2mo.argtypes = [C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, _dp]
+    lib.afesp_ref_ao2mo.restype = None
+    lib.afesp_ref_slice.argtypes = [_dp] + [C.c_int] * 8 + [_dp]
+    lib.afesp_ref_slice.restype = None
+    lib.afesp_ref_reshape.argtypes = [_dp, _dp, _ip, C.c_char_p, C.c_int, C.c_double]
+    lib.afesp_ref_reshape.restype = None
+    lib.afesp_ref_dgemm.argtypes = [C.c_char, C.c_char, C.c_long, C.c_long, C.c_long, _dp, _dp, _dp, C.c_double, C.c_double]
+    lib.afesp_ref_dgemm.restype = None
     lib.afesp_ref_ring.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int]
     lib.afesp_ref_ring.restype = None
     lib.afesp_ref_triples.argtypes = [C.c_int, C.c_int] + [_dp] * 7 + [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, _dp]
@@ -82,3 +138,80 @@ def ladder(c_oovv, v_vvvv):
     X = 0.5 * (A @ B)
     dt = time.perf_counter() - t0
     return X.reshape((o, o, v, v), order="F"), dt
+
+
+CCSD_ITER_PARTS = ("intermediates: dgemms + reshapes", "I_ovov loop :1170-1182", "I_voov / I_vovv_p / x_voov loops",
+                   "T1 equations", "ladder dgemm :1669", "ring loop :1680-1695", "other T2 terms", "P(ia/jb) + divide")
+
+
+def slices(lib, eri_mo, n, o, vvvv_cols=None):
+    """init_cc slices (src/ccsd.f90:496-512) from the packed MO integrals, in the reference's layouts.
+    vvvv_cols=(s0, ns): only columns d in [s0, s0+ns) of v_vvvv(a,b,c,d) (the dense slice is 134 GB at nbf=400)."""
+    v = n - o
+    e = np.ascontiguousarray(eri_mo, dtype=np.float64)
+
+    def cut(lp, np_, lq, nq, lr, nr, ls, ns):
+        out = np.empty((np_, nq, nr, ns), order="F")
+        lib.afesp_ref_slice(_p(e), lp, np_, lq, nq, lr, nr, ls, ns, _p(out))
+        return out
+
+    s0, ns = (0, v) if vvvv_cols is None else vvvv_cols
+    return {"v_oovv": cut(0, o, 0, o, o, v, o, v), "v_ovov": cut(0, o, o, v, 0, o, o, v),
+            "v_vvov": cut(o, v, o, v, 0, o, o, v), "v_oovo": cut(0, o, 0, o, o, v, 0, o),
+            "v_oooo": cut(0, o, 0, o, 0, o, 0, o), "v_vvvv": cut(o, v, o, v, o, v, o + s0, ns)}
+
+
+def ccsd_iter(lib, V, eps, t1, t2, ring_bmax=0, iovov_amax=0):
+    """One spin-free CCSD iteration exactly as the reference issues it (update_restricted_intermediates +
+    update_amplitudes_restricted, src/ccsd.f90:1040-1312, 1538-1732).  Returns (t1_new, t2_new, seconds[8], wall).
+    V: dict of column-major slices (see slices()); V["v_vvvv"] may be a block of its last axis (timing sample)."""
+    o, v = t1.shape
+    a1, a2 = _F(t1).copy(order="F"), _F(t2).copy(order="F")
+    vv = V["v_vvvv"]
+    ncol = v * vv.shape[3]
+    work = {k: _F(V[k]) for k in ("v_oovv", "v_ovov", "v_vvov", "v_oovo", "v_oooo")}
+    e = np.ascontiguousarray(eps, dtype=np.float64)
+    times = np.zeros(8)
+    t0 = time.perf_counter()
+    lib.afesp_ref_ccsd_iter(o, v, _p(work["v_oovv"]), _p(work["v_ovov"]), _p(work["v_vvov"]), _p(work["v_oovo"]),
+                            _p(work["v_oooo"]), _p(_F(vv)), ncol, _p(e), _p(a1), _p(a2), int(ring_bmax),
+                            int(iovov_amax), _p(times))
+    return a1, a2, times, time.perf_counter() - t0
+
+
+def ao2mo(lib, eri_ao, Cmo, lmax=0, smax=0, want_result=True):
+    """AO->MO transform as do_mp2_spatial does it (src/mp2.f90:321-410): four O(n^5) OpenMP loop nests + serial repack.
+    Returns (eri_mo or None, seconds[5]).  lmax/smax < n: slab sample (see oracle/cpu_ccsd.c)."""
+    n = Cmo.shape[0]
+    full = (lmax in (0, n)) and (smax in (0, n))
+    e = np.ascontiguousarray(eri_ao, dtype=np.float64)
+    Cf = _F(Cmo)
+    out = np.empty_like(e) if (want_result and full) else None
+    times = np.zeros(5)
+    lib.afesp_ref_ao2mo(n, _p(e), _p(Cf), int(lmax), int(smax), _p(out) if out is not None else None, _p(times))
+    return out, times
+
+
+def synthetic_mo_integrals(nbf, nocc, seed=20260):
+    """Packed MO integrals of the synthetic workload (afesp_b200/synthetic.py) WITHOUT the O(n^5) transform, from the
+    factored form: (pq|rs) = sum_P Bmo[pq,P] Bmo[rs,P], Bmo^P = C B^P C^T.  Used to feed the CPU timing legs with the same
+    system the GPU arm runs (the CPU AO->MO itself is timed separately, on a slab).  Returns (eri_mo_packed, C, eps)."""
+    from afesp_b200 import synthetic
+
+    B, Cmo, eps = synthetic.make_factors(nbf, nocc, seed)
+    n = nbf
+    ii, jj = np.tril_indices(n)
+    Bmo = np.empty_like(B)
+    full = np.empty((n, n))
+    for P in range(B.shape[1]):
+        full[ii, jj] = B[:, P]
+        full[jj, ii] = B[:, P]
+        Bmo[:, P] = (Cmo @ full @ Cmo.T)[ii, jj]
+    G = Bmo @ Bmo.T
+    npair = ii.size
+    packed = np.empty(npair * (npair + 1) // 2)
+    pos = 0
+    for r in range(npair):
+        packed[pos:pos + r + 1] = G[r, :r + 1]
+        pos += r + 1
+    return packed, Cmo, eps

@@ -14,6 +14,8 @@ v = n - o
 what = os.environ.get("PROFILE", "T")
 rt = torch.cuda.cudart()
 g = AfespGpu(0)
+if os.environ.get("TMA_SCOPE"):
+    g.set_option("gemm_use_tma", int(os.environ["TMA_SCOPE"]))
 eri, C, eps = synthetic.make(n, o)
 g.ao2mo(n, eri, C, want_result=False)
 g.release("eri_ao")
