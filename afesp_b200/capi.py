@@ -25,6 +25,7 @@ SIGNATURES = {
     "afesp_gpu_release": [_H, C.c_char_p],
     "afesp_gpu_mp2_energy": [_H, C.c_int, _dp, _dp],
     "afesp_gpu_ccsd_init": [_H, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp],
+    "afesp_gpu_ccsd_init_info": [_H, _dp],
     "afesp_gpu_ccsd_iterate": [_H, _dp, _dp],
     "afesp_gpu_ccsd_diis": [_H],
     "afesp_gpu_ccsd_finalize": [_H, C.c_int, _dp, _dp, _dp],
@@ -201,6 +202,13 @@ class AfespGpu:
         else:
             self.o, self.v = 2 * int(nocc), 2 * (self.n - int(nocc))
         return e1.value, r.value
+
+    def ccsd_init_info(self):
+        """Spin-orbital integral preparation of the last ccsd_init (src/ccsd.f90:106-202): dict with the error of the
+        permutational-symmetry self-check and the device seconds of the slice gather and of the check."""
+        info = (C.c_double * 4)()
+        self._check("ccsd_init_info", self.lib.afesp_gpu_ccsd_init_info(self.h, info))
+        return {"symmetry_error": info[0], "slices_s": info[1], "check_s": info[2]}
 
     def ccsd_iterate(self):
         e, r = C.c_double(0), C.c_double(0)

@@ -235,6 +235,7 @@ int afesp_gpu_set_option(afesp_handle hv, const char* key, double value) {
     else if (k == "spinorb_symmetry_tol") o.spinorb_symmetry_tol = value;
     else if (k == "gemm_timing") gemm_timing_enable(value != 0.0);
     else if (k == "gemm_force_config") gemm_force_config((int)value);
+    else if (k == "gemm_tma_edge") gemm_tma_edge((int)value);
     else if (k == "gemm_use_tma") {
       // 0 off, 1 the gathered (T) batches only, 2 every aligned GEMM the 64x64 tile is chosen for.  Switching it on runs
       // the consistency check against the cp.async kernel first (once per process); if that fails the path stays off.

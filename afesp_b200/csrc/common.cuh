@@ -85,6 +85,15 @@ struct GemmBatch {
   long long Anblocks = 0, Bnblocks = 0; // number of blocks addressable through the index arrays
   const int* Aidx = nullptr;            // device arrays of `count` block indices
   const int* Bidx = nullptr;
+  // Optional second K segment ("dual" batches, the (T) driver): C[g] = A[Aidx[g]] B[Bidx[g]] + A[Aidx2[g]] B2[Bidx2[g]],
+  // both products of depth K, A blocks from the same base, B2 blocks with the geometry of B.  One launch of the
+  // TMA-staged kernel walks both segments in its k loop; the cp.async fallback runs two launches (beta, then 1).
+  const double* const* Aptr2 = nullptr;
+  const double* const* Bptr2 = nullptr;
+  const double* Bbase2 = nullptr;
+  const int* Aidx2 = nullptr;
+  const int* Bidx2 = nullptr;
+  bool dual() const { return Aptr2 != nullptr; }
 };
 void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, double alpha, const double* A,
            long long lda, const double* B, long long ldb, double beta, double* C, long long ldc,
@@ -99,6 +108,7 @@ void gemm_force_config(int cfg);  // tuning aid: -1 = automatic tile selection
 // problem the 64x64 tile is chosen for.  See DESIGN.md section 4.1.
 void gemm_tma_scope(int scope);
 int gemm_tma_scope_get();
+void gemm_tma_edge(int on);   // 1 (default): balanced last M tile + short K tail in the TMA kernel; 0: pad (A/B tests)
 // One-off consistency check of the TMA kernel against the cp.async kernel on the current device (gemm_tma.cu); a
 // failure switches the TMA path off for the process.  State: 0 not run, 1 passed, -1 failed.
 bool gemm_tma_selftest(cudaStream_t st);

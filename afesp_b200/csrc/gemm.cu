@@ -404,12 +404,15 @@ int choose_cfg(int M, int N, int nbatch, long long* tiles_out, bool tma_ok) {
     const TileCfg& t = kCfg[c];
     const long long tm = (M + t.bm - 1) / t.bm, tn = (N + t.bn - 1) / t.bn;
     const long long tiles = tm * tn * nbatch;
-    const double useful = ((double)M * N) / ((double)tm * t.bm * tn * t.bn);
+    double useful = ((double)M * N) / ((double)tm * t.bm * tn * t.bn);
+    // the TMA-staged kernel multiplies only ceil(M/8) row fragments (balanced last M tile, gemm_tma.cu)
+    if (c == 3 && tma_ok) useful = ((double)M * N) / ((double)((M + 7) / 8 * 8) * tn * t.bn);
     const double slots = sms * t.occ;
     const double waves = std::ceil(tiles / slots);
     const double fill = tiles / (waves * slots);
-    // the 64x64 tile runs through the TMA-staged kernel when the operands are aligned: 92% instead of 87% (profiles/)
-    const double eff = (c == 3 && tma_ok) ? 0.92 : t.eff;
+    // the 64x64 tile runs through the TMA-staged kernel when the operands are aligned: 94-96% of the DMMA issue rate
+    // on large problems instead of 87% (profiles/r02_tma_soak_*.json, r02_ncu_*)
+    const double eff = (c == 3 && tma_ok) ? 0.95 : t.eff;
     const double score = eff * useful * fill;
     if (score > best_score) { best_score = score; best = c; if (tiles_out) *tiles_out = tiles; }
   }
@@ -449,7 +452,9 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
   if (batch && (batch->Aptr || batch->Bptr)) vec2 = vec2 && batch->ptr_aligned16;  // alignment is the caller's promise
   else vec2 = vec2 && aligned16(A) && aligned16(B) && (!batch || (batch->strideA % 2 == 0 && batch->strideB % 2 == 0));
 
-  g_gemm_flops += 2.0 * M * N * (double)K * nbatch;
+  const bool dual = batch && batch->dual();   // two K segments per batch entry (common.cuh)
+  const double flops = 2.0 * M * N * (double)K * nbatch * (dual ? 2 : 1);
+  g_gemm_flops += flops;
 
   // tile selection (see kCfg)
   long long tiles = 0;
@@ -466,6 +471,7 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
     p.cvec = (ldc % 2 == 0) && c_al ? 1 : 0;
   }
   // split-K for skinny outputs with a long reduction
+  if (dual) AFESP_REQUIRE(batch->Aptr && batch->Bptr && batch->Bptr2 && batch->Cptr, "dgemm: dual batches need pointer arrays");
   if (nbatch == 1 && tiles * 2 <= num_sms() && K >= 512) {
     int want = (int)std::min<long long>(num_sms() * 2 / tiles, (K + 127) / 128);
     if (want > 1) {
@@ -480,7 +486,7 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
     }
   }
   std::pair<cudaEvent_t, cudaEvent_t>* evs = g_timing ? next_events() : nullptr;
-  if (evs) { cudaEventRecord(evs->first, st); g_timed_flops += 2.0 * M * N * (double)K * nbatch; g_timed_launches += 1; }
+  if (evs) { cudaEventRecord(evs->first, st); g_timed_flops += flops; g_timed_launches += 1; }
   // aligned problems on the 64x64 tile go through the TMA-staged kernel (gemm_tma.cu); everything else through cp.async
   bool used_tma = false;
   // Developer check (AFESP_GEMM_VERIFY=1, unbatched problems): run the cp.async kernel on a copy of C as well and report
@@ -494,7 +500,14 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
   }
   if (cfg == 3 && p.splitk == 1 && vec2)
     used_tma = dgemm_tma(st, ak, bk, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, batch, p.cvec);
-  if (!used_tma) launch_by_cfg(cfg, st, p, nbatch, ak, bk, vec2);
+  if (!used_tma) {
+    launch_by_cfg(cfg, st, p, nbatch, ak, bk, vec2);
+    if (dual) {  // second K segment accumulates into the same C blocks
+      Params q = p;
+      q.Ap = batch->Aptr2; q.Bp = batch->Bptr2; q.beta = 1.0;
+      launch_by_cfg(cfg, st, q, nbatch, ak, bk, vec2);
+    }
+  }
   if (do_verify) {
     if (used_tma) {
       Params q = p;

@@ -107,15 +107,158 @@ struct TmaParams {
   long long sC, ldc;
   const int* Aidx;   // per-batch block index into the A map's outermost dimension (null: batch index)
   const int* Bidx;
+  const int* Aidx2;  // dual batches: block indices of the second K segment (B blocks through the second B map)
+  const int* Bidx2;
+  int nk_seg;        // k-tiles per segment of a dual batch (0: single segment)
+  int edge_balance;  // 1: the last M tile shares its valid row fragments evenly over the four consumer warps
+  int ktail;         // 1: the last k-tile of a segment holds <= 8 valid k -> two DMMA groups instead of four
   int M, N, K, tiles_m;
   int nbatch;        // > 0: batch-fastest rasterisation on a 1-D grid (see the kernel); 0: batch = blockIdx.z
   double alpha, beta;
   int cvec;
 };
 
+// Consumer side of one CTA tile: main loop over the k-tiles of the ring + epilogue, for a warp that owns NI x NJ 8x8
+// fragments at rows rb + 8 i, columns cb + 8 j of the tile (PRED: only the first fi row fragments exist).
+//
+// Slot release.  The first version released slot s right after the DMMAs of its k-tile: `__syncwarp(); if (lane == 0)
+// arrive(empty[s])`.  The SASS showed why that produced sporadic wrong 32-byte sectors: the fragment loads were
+// generic LD.E (the shared address space was lost in the pointer round-up), the WARPSYNC had been hoisted above most
+// of them, and the SYNCS.ARRIVE was scheduled right behind the last loads and *ahead of* the DMMAs that consume them --
+// so a slot could be handed back to the producer while fragment loads of some lanes were still in flight, and the
+// next TMA write raced them.  Now (i) fragments are read with explicit ld.shared, (ii) every lane arrives for itself
+// (barrier count NCONS*32), and (iii) the release of k-tile kt-1 is issued only after the wait for k-tile kt: by then
+// the DMMAs of kt-1 have been issued, which requires all of this lane's fragment loads of kt-1 to have returned.
+//
+// K tail.  When the last k-tile of a segment holds at most 8 valid k (the rest is TMA zero fill) only two DMMA groups
+// are issued for it, on the k-sets {0,3,4,7} {1,2,5,6} (conflict-free in the MN-major layout, 2-way in the K-major one:
+// one tile per segment).
+template <bool AK, bool BKM, int NI, int NJ, bool PRED>
+__device__ __forceinline__ void consume(const TmaParams& p, unsigned char* smem, unsigned long long* full,
+                                        unsigned long long* empty, int nk, int nk1, int rb, int cb, int fi, int m0,
+                                        int n0, int batch, int lane) {
+  const int gid = lane >> 2, tig = lane & 3;
+  double acc[NI * NJ][2];
+#pragma unroll
+  for (int x = 0; x < NI * NJ; ++x) acc[x][0] = acc[x][1] = 0.0;
+  // per-thread fragment offsets (bytes) for the four k-sets; tile rows advance by 8*i
+  int aoff[4][NI], boff[4][NJ];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int k = kslot(s, tig);
+#pragma unroll
+    for (int i = 0; i < NI; ++i) aoff[s][i] = tile_off<AK>(rb + 8 * i + gid, k);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) boff[s][j] = tile_off<BKM>(cb + 8 * j + gid, k);
+  }
+  const unsigned smem_s = smem_u32(smem);
+  for (int kt = 0; kt < nk; ++kt) {
+    const int s = kt % STAGES;
+    mbar_wait(&full[s], (kt / STAGES) & 1);
+    if (kt > 0) mbar_arrive(&empty[(kt - 1) % STAGES]);
+    const unsigned sa = smem_s + s * STAGE_BYTES, sb = sa + TILE_BYTES;
+    if (p.ktail && (kt == nk1 - 1 || kt == nk - 1)) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int k = (tig >> 1) * 4 + (g ? 1 + (tig & 1) : 3 * (tig & 1));
+        double af[NI], bf[NJ];
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+          if (!PRED || i < fi) af[i] = lds_f64(sa + tile_off<AK>(rb + 8 * i + gid, k));
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) bf[j] = lds_f64(sb + tile_off<BKM>(cb + 8 * j + gid, k));
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+          if (!PRED || i < fi) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) dmma884(acc[i * NJ + j][0], acc[i * NJ + j][1], af[i], bf[j]);
+          }
+      }
+      continue;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      double af[NI], bf[NJ];
+#pragma unroll
+      for (int i = 0; i < NI; ++i)
+        if (!PRED || i < fi) af[i] = lds_f64(sa + aoff[g][i]);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) bf[j] = lds_f64(sb + boff[g][j]);
+#pragma unroll
+      for (int i = 0; i < NI; ++i)
+        if (!PRED || i < fi) {
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) dmma884(acc[i * NJ + j][0], acc[i * NJ + j][1], af[i], bf[j]);
+        }
+    }
+  }
+  // (the last k-tile's slot needs no release: nothing is loaded after it)
+
+  // ---------------- epilogue (same fragment ownership as gemm_f64_dmma) ----------------
+  double* C = p.Cp ? p.Cp[batch] : p.C + batch * p.sC;
+  const double alpha = p.alpha, beta = p.beta;
+  if (p.cvec) {
+    const bool odd = gid & 1;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      if (PRED && i >= fi) break;
+      const int m = m0 + rb + 8 * i + (gid & ~1);
+      double2 oldv[NJ];
+      if (beta != 0.0) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int n = n0 + cb + 8 * j + 2 * tig + (odd ? 1 : 0);
+          oldv[j] = make_double2(0.0, 0.0);
+          if (n < p.N && m < p.M) {
+            const double* c = C + m + (long long)n * p.ldc;
+            if (m + 1 < p.M) oldv[j] = *reinterpret_cast<const double2*>(c);
+            else oldv[j].x = *c;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const double send = odd ? acc[i * NJ + j][0] : acc[i * NJ + j][1];
+        const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
+        const double lo = odd ? recv : acc[i * NJ + j][0];
+        const double hi = odd ? acc[i * NJ + j][1] : recv;
+        const int n = n0 + cb + 8 * j + 2 * tig + (odd ? 1 : 0);
+        if (n < p.N && m < p.M) {
+          double* c = C + m + (long long)n * p.ldc;
+          double2 v = make_double2(alpha * lo, alpha * hi);
+          if (beta != 0.0) { v.x += beta * oldv[j].x; v.y += beta * oldv[j].y; }
+          if (m + 1 < p.M) *reinterpret_cast<double2*>(c) = v;
+          else *c = v.x;
+        }
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    if (PRED && i >= fi) break;
+    const int m = m0 + rb + 8 * i + gid;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int n = n0 + cb + 8 * j + 2 * tig;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (n + e < p.N) {
+          double* c = C + m + (long long)(n + e) * p.ldc;
+          double v = alpha * acc[i * NJ + j][e];
+          if (beta != 0.0) v += beta * (*c);
+          *c = v;
+        }
+      }
+    }
+  }
+}
+
 template <bool AK, bool BKM>
 __global__ void __launch_bounds__(NT, 3) gemm_f64_tma(const __grid_constant__ CUtensorMap tmA,
-                                                       const __grid_constant__ CUtensorMap tmB, const TmaParams p) {
+                                                       const __grid_constant__ CUtensorMap tmB,
+                                                       const __grid_constant__ CUtensorMap tmB2, const TmaParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle; the launch adds slack for the round-up
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -137,7 +280,8 @@ __global__ void __launch_bounds__(NT, 3) gemm_f64_tma(const __grid_constant__ CU
     m0 = (blockIdx.x % p.tiles_m) * BM; n0 = (blockIdx.x / p.tiles_m) * BN;
     batch = blockIdx.z;
   }
-  const int nk = (p.K + BK - 1) / BK;
+  const int nk1 = (p.K + BK - 1) / BK;
+  const int nk = p.nk_seg ? 2 * nk1 : nk1;   // dual batches: two K segments of nk1 tiles each
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS * 32); /* every consumer lane arrives */ }
@@ -148,130 +292,39 @@ __global__ void __launch_bounds__(NT, 3) gemm_f64_tma(const __grid_constant__ CU
   if (warp == NCONS) {
     // ---------------- producer warp ----------------
     if (lane == 0) {
-      const int ai = p.Aidx ? p.Aidx[batch] : batch;
-      const int bi = p.Bidx ? p.Bidx[batch] : batch;
+      const int ai0 = p.Aidx ? p.Aidx[batch] : batch;
+      const int bi0 = p.Bidx ? p.Bidx[batch] : batch;
+      const int ai1 = p.nk_seg ? p.Aidx2[batch] : 0;
+      const int bi1 = p.nk_seg ? p.Bidx2[batch] : 0;
       for (int kt = 0; kt < nk; ++kt) {
         const int s = kt % STAGES;
         mbar_wait(&empty[s], ((kt / STAGES) & 1) ^ 1);   // first pass falls through (fresh barrier)
         mbar_expect_tx(&full[s], STAGE_BYTES);
         unsigned char* sa = smem + s * STAGE_BYTES;
         unsigned char* sb = sa + TILE_BYTES;
-        const int k0 = kt * BK;
+        const bool seg2 = kt >= nk1;                     // only ever true for dual batches
+        const int k0 = (seg2 ? kt - nk1 : kt) * BK;
+        const int ai = seg2 ? ai1 : ai0, bi = seg2 ? bi1 : bi0;
+        const CUtensorMap* mB = seg2 ? &tmB2 : &tmB;
         if (AK) tma_load_3d(sa, &tmA, &full[s], k0, m0, ai);
         else tma_load_4d(sa, &tmA, &full[s], 0, k0, m0 >> 4, ai);
-        if (BKM) tma_load_3d(sb, &tmB, &full[s], k0, n0, bi);
-        else tma_load_4d(sb, &tmB, &full[s], 0, k0, n0 >> 4, bi);
+        if (BKM) tma_load_3d(sb, mB, &full[s], k0, n0, bi);
+        else tma_load_4d(sb, mB, &full[s], 0, k0, n0 >> 4, bi);
       }
     }
     return;
   }
   // ---------------- consumer warps ----------------
-  const int gid = lane >> 2, tig = lane & 3;
-  const int wm0 = (warp & 1) * 32, wn0 = (warp >> 1) * 32;
-  double acc[4][4][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  // per-thread fragment offsets (bytes) for the four k-sets; tile rows advance by 8*i
-  int aoff[4][4], boff[4][4];
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    const int k = kslot(s, tig);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      aoff[s][i] = tile_off<AK>(wm0 + 8 * i + gid, k);
-      boff[s][i] = tile_off<BKM>(wn0 + 8 * i + gid, k);
-    }
-  }
-  // Every warp issues the full 4x4 fragment grid, also in edge tiles.
-  //
-  // Slot release.  The first version released slot s right after the DMMAs of its k-tile: `__syncwarp(); if (lane == 0)
-  // arrive(empty[s])`.  The SASS showed why that produced sporadic wrong 32-byte sectors: the fragment loads were
-  // generic LD.E (the shared address space was lost in the pointer round-up), the WARPSYNC had been hoisted above most
-  // of them, and the SYNCS.ARRIVE was scheduled right behind the last loads and *ahead of* the DMMAs that consume them --
-  // so a slot could be handed back to the producer while fragment loads of some lanes were still in flight, and the
-  // next TMA write raced them.  Now (i) fragments are read with explicit ld.shared, (ii) every lane arrives for itself
-  // (barrier count NCONS*32), and (iii) the release of k-tile kt-1 is issued only after the wait for k-tile kt: by then
-  // the DMMAs of kt-1 have been issued, which requires all of this lane's fragment loads of kt-1 to have returned.
-  const unsigned smem_s = smem_u32(smem);
-  for (int kt = 0; kt < nk; ++kt) {
-    const int s = kt % STAGES;
-    mbar_wait(&full[s], (kt / STAGES) & 1);
-    if (kt > 0) mbar_arrive(&empty[(kt - 1) % STAGES]);
-    const unsigned sa = smem_s + s * STAGE_BYTES, sb = sa + TILE_BYTES;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      double af[4], bf[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) af[i] = lds_f64(sa + aoff[g][i]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = lds_f64(sb + boff[g][j]);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-    }
-  }
-  // (the last k-tile's slot needs no release: nothing is loaded after it)
-
-  // ---------------- epilogue (same fragment ownership as gemm_f64_dmma) ----------------
-  double* C = p.Cp ? p.Cp[batch] : p.C + batch * p.sC;
-  const double alpha = p.alpha, beta = p.beta;
-  if (p.cvec) {
-    const bool odd = gid & 1;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int m = m0 + wm0 + 8 * i + (gid & ~1);
-      double2 oldv[4];
-      if (beta != 0.0) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int n = n0 + wn0 + 8 * j + 2 * tig + (odd ? 1 : 0);
-          oldv[j] = make_double2(0.0, 0.0);
-          if (n < p.N && m < p.M) {
-            const double* c = C + m + (long long)n * p.ldc;
-            if (m + 1 < p.M) oldv[j] = *reinterpret_cast<const double2*>(c);
-            else oldv[j].x = *c;
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double send = odd ? acc[i][j][0] : acc[i][j][1];
-        const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
-        const double lo = odd ? recv : acc[i][j][0];
-        const double hi = odd ? acc[i][j][1] : recv;
-        const int n = n0 + wn0 + 8 * j + 2 * tig + (odd ? 1 : 0);
-        if (n < p.N && m < p.M) {
-          double* c = C + m + (long long)n * p.ldc;
-          double2 v = make_double2(alpha * lo, alpha * hi);
-          if (beta != 0.0) { v.x += beta * oldv[j].x; v.y += beta * oldv[j].y; }
-          if (m + 1 < p.M) *reinterpret_cast<double2*>(c) = v;
-          else *c = v.x;
-        }
-      }
-    }
-    return;
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + wm0 + 8 * i + gid;
-    if (m >= p.M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + wn0 + 8 * j + 2 * tig;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        if (n + e < p.N) {
-          double* c = C + m + (long long)(n + e) * p.ldc;
-          double v = alpha * acc[i][j][e];
-          if (beta != 0.0) v += beta * (*c);
-          *c = v;
-        }
-      }
-    }
-  }
+  // Interior tiles: each warp owns a 32x32 sub-tile (4x4 fragments).  The last M tile of a problem whose M is not a
+  // multiple of 64 would waste up to 7/8 of its DMMAs on padding rows; there the four warps instead share the
+  // f = ceil(rows/8) valid row fragments evenly: each takes ALL of them times 16 columns (f x 2 fragments), so exactly
+  // ceil(M/8) row fragments are multiplied and the work stays balanced over the SM's four tensor pipes.
+  const int mrem = p.M - m0;
+  const int fi = (mrem + 7) >> 3;
+  if (p.edge_balance && fi < 8)
+    consume<AK, BKM, 8, 2, true>(p, smem, full, empty, nk, nk1, 0, warp * 16, fi, m0, n0, batch, lane);
+  else
+    consume<AK, BKM, 4, 4, false>(p, smem, full, empty, nk, nk1, (warp & 1) * 32, (warp >> 1) * 32, 4, m0, n0, batch, lane);
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -321,6 +374,7 @@ bool make_map(CUtensorMap* map, bool kmajor, const double* base, long long MN, l
   return r == CUDA_SUCCESS;
 }
 
+int g_tma_edge = 1;    // edge handling of gemm_f64_tma (balanced last M tile, short K tail); 0 = pad everything (A/B tests)
 int g_tma_scope = 2;   // 0 = off, 1 = gathered (T) batches only, 2 (default since the round-2 soak, profiles/r02_tma_soak_*.json) = every aligned 64x64-tile problem
 
 }  // namespace
@@ -451,6 +505,7 @@ void gemm_crosscheck(cudaStream_t st, char ta, char tb, int M, int N, int K, int
   cudaEventDestroy(e0); cudaEventDestroy(e1);
 }
 
+void gemm_tma_edge(int on) { g_tma_edge = on; }
 void gemm_tma_scope(int scope) { g_tma_scope = (g_selftest_state < 0) ? 0 : scope; }
 int gemm_tma_scope_get() { return g_tma_scope; }
 
@@ -460,6 +515,8 @@ bool dgemm_tma(cudaStream_t st, bool ak, bool bk, int M, int N, int K, double al
   if (g_tma_scope == 0 || K < 1) return false;
   const bool gathered = batch && batch->Abase && batch->Bbase && batch->Aidx && batch->Bidx;
   if (g_tma_scope == 1 && !gathered) return false;
+  const bool dual = batch && batch->dual();
+  if (dual && !(gathered && batch->Bbase2 && batch->Aidx2 && batch->Bidx2)) return false;
   const int nbatch = batch ? batch->count : 1;
   const double* Abase = A;
   const double* Bbase = B;
@@ -480,10 +537,18 @@ bool dgemm_tma(cudaStream_t st, bool ak, bool bk, int M, int N, int K, double al
   }
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al16(Abase) || !al16(Bbase) || (lda & 1) || (ldb & 1) || (sA & 1) || (sB & 1)) return false;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmB2;
   if (!make_map(&tmA, ak, Abase, M, K, lda, nA, sA, BM)) return false;
   if (!make_map(&tmB, bk, Bbase, N, K, ldb, nB, sB, BN)) return false;
+  if (dual) {
+    if (!al16(batch->Bbase2) || !make_map(&tmB2, bk, batch->Bbase2, N, K, ldb, nB, sB, BN)) return false;
+  } else {
+    tmB2 = tmB;
+  }
   TmaParams p{};
+  if (dual) { p.Aidx2 = batch->Aidx2; p.Bidx2 = batch->Bidx2; p.nk_seg = (K + BK - 1) / BK; }
+  p.edge_balance = g_tma_edge ? 1 : 0;
+  p.ktail = (g_tma_edge && (K % BK) >= 1 && (K % BK) <= 8) ? 1 : 0;
   p.C = C; p.Cp = batch ? batch->Cptr : nullptr; p.sC = batch ? batch->strideC : 0; p.ldc = ldc;
   p.Aidx = Aidx; p.Bidx = Bidx; p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.cvec = cvec;
   p.tiles_m = (M + BM - 1) / BM;
@@ -504,7 +569,7 @@ bool dgemm_tma(cudaStream_t st, bool ak, bool bk, int M, int N, int K, double al
     cudaFuncSetAttribute(gemm_f64_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
     cudaFuncSetAttribute(gemm_f64_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
   });
-  auto launch = [&](auto kern) { kern<<<grid, NT, SMEM, st>>>(tmA, tmB, p); };
+  auto launch = [&](auto kern) { kern<<<grid, NT, SMEM, st>>>(tmA, tmB, tmB2, p); };
   if (ak) { if (bk) launch(gemm_f64_tma<true, true>); else launch(gemm_f64_tma<true, false>); }
   else    { if (bk) launch(gemm_f64_tma<false, true>); else launch(gemm_f64_tma<false, false>); }
   count_launch();

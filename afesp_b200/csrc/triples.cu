@@ -8,6 +8,10 @@
 //     W_ijk(a,b,c)   = sum over the six simultaneous permutations of X               (tiled combine kernel)
 // batched over as many triples as fit the work buffer, followed by one fused epilogue kernel that forms the
 // energy denominators, z3, y, the x-bar combinations and all six reductions in a single pass over W (and M3).
+// Two permutations that share their first virtual label differ only by a swap of the other two, so with a second copy
+// of the (n x v^2) operand stored (z,y)-transposed they are K-concatenated into ONE product of depth 2 nbf:
+//     Y_s(x,(u,w)) = X_s(x,u,w) + X_{s+3}(x,w,u),  s = abc, bac, cba
+// -- three GEMM outputs per triple instead of six, written once and read once by the epilogue.
 //
 // Occupied-triple symmetry: W, z3, y and M3 are covariant under simultaneous permutation of (i,a),(j,b),(k,c), so the
 // sum over the orbit of an ordered triple equals  mult * sum_abc x~(abc) u(abc)  with the symmetrised
@@ -57,8 +61,8 @@ __host__ __device__ constexpr int COMP(int q, int s) {
 __host__ __device__ constexpr double COEF(int s) { return s == 0 ? 8.0 / 6.0 : (s <= 3 ? -4.0 / 6.0 : 2.0 / 6.0); }
 
 struct FusedArgs {
-  const double* X;    // [nb][6][v^3]  per-permutation GEMM blocks X_t for the W term
-  const double* XM;   // [nb][6][v^3]  same for the M3 term (CR) or null
+  const double* X;    // [nb][3][v^3]  pair-merged GEMM blocks Y_s (s = abc, bac, cba) for the W term
+  const double* XM;   // [nb][3][v^3]  same for the M3 term (CR) or null
   const double* t1;   // (o,v)
   const double* t2;   // (o,o,v,v)
   const double* vo;   // v_oovv (o,o,v,v)
@@ -70,30 +74,46 @@ struct FusedArgs {
   double* partials;   // [gridDim.y * gridDim.x][6]
 };
 
-template <int T>
-__device__ __forceinline__ int sel3(const int (&l)[3]) { return l[T]; }
+// ---- fused epilogue, "orbit form" -----------------------------------------------------------------------------------
+// One CTA = one unordered triple of label tiles {A,B,C} (8 labels each) of one occupied triple (i,j,k); one THREAD = one
+// label triple (a,b,c) = (A+tx, B+ty, C+tz) together with its six permutations P_u(a,b,c), u = abc, bac, cba, acb, bca,
+// cab -- the "orbit".  Everything the reference evaluates per (a,b,c) couples only members of one orbit:
+//   W(P_u abc)   = sum_s Y_s[P_{u o s} abc]                         (src/ccsd.f90:2168-2173; two of its six terms per Y_s)
+//   x~(W)(P_u)   = sum_s c_s W(P_{u o s} abc)                       (make_x_bar, :2314-2318, group-averaged, see header)
+//   D3 = e_i + e_j + e_k - e_a - e_b - e_c  is the SAME for all six members
+// so after the gather below the six W (and M3, z3, y) values of the orbit sit in the thread's registers and the energy
+// expressions (:2175-2233) need no further shared-memory traffic, one reciprocal, and no per-tile bookkeeping.
+//
+// Gather: V[s][w] = Y_s at tile origin (O o w), local position (l o w).  Each of the 18 boxes is read from global memory
+// at the thread's NATURAL position (coalesced 64-byte rows, all 18 loads in flight), the 15 boxes with w != identity go
+// through shared memory once: written at l, read back at l o w.  Each box is only ever read with its own permutation w,
+// so it gets its own XOR-swizzled layout in which both the natural write and the permuted read of a half-warp
+// (tx = 0..7, two consecutive ty) touch 16 distinct 8-byte banks (enumerated in tests/test_tma_layout.py).
+constexpr int BOXW = TS * TS * TS;   // words per swizzled box (no padding)
 
-// One CTA = one unordered triple of label tiles {A,B,C} of one occupied triple (i,j,k).
-//   step 1: W_q(l) = sum_t X_t[(O o q) o p_t + l o p_t] for the six permuted tile origins q (the reference's 6-term sum,
-//           src/ccsd.f90:2168-2173), staged through shared memory so every global read is a coalesced 64-byte row;
-//   step 2: for each of the six tiles, D3, t~ = x~(W)/D3, z~, y, M3 and the six partial sums (:2175-2233).
-// W and M3 never touch global memory; each X element is read exactly once.  All permutation bookkeeping is resolved at
-// compile time (fully unrolled q/t/s loops) -- the kernel is otherwise instruction-bound.
+__device__ __forceinline__ int swz(int w, int X, int Y, int Z) {   // w is a compile-time constant after unrolling
+  switch (w) {
+    case 1: return 64 * Z + 8 * Y + (X ^ Y);
+    case 2: return 64 * Z + 8 * Y + (X ^ Z);
+    case 3: return 64 * Z + 8 * (Y ^ (Z & 1)) + X;
+    case 4: return 64 * Z + 8 * (Y ^ (X & 1)) + (X ^ Z);
+    default: return 64 * Z + 8 * (Y ^ (Z & 1)) + (X ^ Y);
+  }
+}
+
 template <bool USE_Z, bool DO_Y, bool DO_M>
 constexpr size_t fused_smem_doubles() {
-  return (size_t)12 * BOX + ((USE_Z || DO_Y) ? (54 * TS * TS + 9 * TS) : 0) + (DO_M ? 6 * BOX : 0);
+  return (size_t)15 * BOXW + ((USE_Z || DO_Y) ? (54 * TS * TS + 9 * TS) : 0);
 }
 
 template <bool USE_Z, bool DO_Y, bool DO_M, bool PAREN>
 __global__ void __launch_bounds__(TS* TS* TS, 2) k_triples_fused(const FusedArgs g) {
   extern __shared__ double sm[];
   constexpr bool AUX = USE_Z || DO_Y;
-  double* sW = sm;                                  // [6][BOX]  W at origin O o q
-  double* sS = sW + 6 * BOX;                        // [6][BOX]  staging for the X_t boxes of one q
-  double* sV = sS + 6 * BOX;                        // [3 pairs][3][3][TS*TS]  v_oovv(pair; R1, R2)
+  double* sS = sm;                                  // [3 s][5 w][BOXW] staged Y boxes with w != identity
+  double* sV = sm + 15 * BOXW;                      // [3 pairs][3][3][TS*TS]  v_oovv(pair; R1, R2)
   double* sT = sV + (AUX ? 27 * TS * TS : 0);       // [3 occ][3 ranges][TS]    t1(occ; R)
   double* sY = sT + (AUX ? 9 * TS : 0);             // [3 pairs][3][3][TS*TS]  t2(pair; R1, R2)
-  double* sM = sY + (AUX ? 27 * TS * TS : 0);       // [6][BOX]  M3 at origin O o q (CR only)
   __shared__ double red[6][TS * TS * TS / 32];
   const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
   const int tid = tx + TS * (ty + TS * tz);
@@ -104,19 +124,46 @@ __global__ void __launch_bounds__(TS* TS* TS, 2) k_triples_fused(const FusedArgs
   const int O[3] = {T3[0] * TS, T3[1] * TS, T3[2] * TS};
   const long long v3 = (long long)v * v * v, oo = (long long)o * o;
   const int l[3] = {tx, ty, tz};
-  const bool full = (O[0] + TS <= v) && (O[1] + TS <= v) && (O[2] + TS <= v);  // no edge tile involved
+  const bool full = (O[2] + TS <= v);               // tiles are ordered A <= B <= C: no edge tile involved
   const long long thr_off = tx + (long long)v * (ty + (long long)v * tz);
-  // global offset of each tile origin O o u (u = 0..5) and the thread's permuted position inside a staged box
+  // global offset of each box origin O o w and whether the thread's element of that box exists
   long long gorg[6];
-  int soff[6];
+  bool okb[6];
 #pragma unroll
-  for (int u = 0; u < 6; ++u) {
-    gorg[u] = O[PM(u, 0)] + (long long)v * (O[PM(u, 1)] + (long long)v * O[PM(u, 2)]) + thr_off;
-    soff[u] = box_off(l[PM(u, 0)], l[PM(u, 1)], l[PM(u, 2)]);
+  for (int w = 0; w < 6; ++w) {
+    gorg[w] = O[PM(w, 0)] + (long long)v * (O[PM(w, 1)] + (long long)v * O[PM(w, 2)]) + thr_off;
+    okb[w] = full || ((O[PM(w, 0)] + tx < v) && (O[PM(w, 1)] + ty < v) && (O[PM(w, 2)] + tz < v));
   }
-  const int my = box_off(tx, ty, tz);
+  int wr[6], rd[6];
+#pragma unroll
+  for (int w = 1; w < 6; ++w) {
+    wr[w] = swz(w, tx, ty, tz);
+    rd[w] = swz(w, l[PM(w, 0)], l[PM(w, 1)], l[PM(w, 2)]);
+  }
 
-  if (USE_Z || DO_Y) {
+  // out[u] = sum_s Y_s[P_{u o s}(a,b,c)], u = 0..5 (s = abc, bac, cba are involutions: V[s][w] lands in u = w o s)
+  auto gather = [&](const double* __restrict__ Yb, double (&out)[6]) {
+    double val[18];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int w = 0; w < 6; ++w) val[s * 6 + w] = okb[w] ? __ldg(Yb + s * v3 + gorg[w]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 6; ++u) out[u] = 0.0;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      out[COMP(0, s)] += val[s * 6];
+#pragma unroll
+      for (int w = 1; w < 6; ++w) sS[(s * 5 + w - 1) * BOXW + wr[w]] = val[s * 6 + w];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int w = 1; w < 6; ++w) out[COMP(w, s)] += sS[(s * 5 + w - 1) * BOXW + rd[w]];
+  };
+
+  if (AUX) {
     for (int e = tid; e < 27 * TS * TS; e += TS * TS * TS) {
       int xy = e % (TS * TS), rr = (e / (TS * TS)) % 9, pr = e / (9 * TS * TS);
       int x = O[rr / 3] + xy % TS, y = O[rr % 3] + xy / TS;
@@ -131,81 +178,51 @@ __global__ void __launch_bounds__(TS* TS* TS, 2) k_triples_fused(const FusedArgs
       sT[e] = x < v ? g.t1[occ[e / (3 * TS)] + (long long)o * x] : 0.0;
     }
   }
-  // step 1: the six W (and M3) tiles.  Software-pipelined: the six global loads of tile q+1 are in flight while tile q
-  // goes through shared memory.
-  constexpr int NQ = DO_M ? 12 : 6;
-  double val[6];
-  auto fetch = [&](int qq, double (&out)[6]) {
-    const double* Xb = (qq < 6 ? g.X : g.XM) + (long long)blockIdx.y * 6 * v3;
-    const int q = qq % 6;
-#pragma unroll
-    for (int t = 0; t < 6; ++t) {
-      const int u = COMP(q, t);  // origin of the X_t box: O o (q o p_t)
-      bool ok = full || ((O[PM(u, 0)] + tx < v) && (O[PM(u, 1)] + ty < v) && (O[PM(u, 2)] + tz < v));
-      out[t] = ok ? __ldg(Xb + t * v3 + gorg[u]) : 0.0;
-    }
-  };
-  fetch(0, val);
-#pragma unroll
-  for (int qq = 0; qq < NQ; ++qq) {
-#pragma unroll
-    for (int t = 0; t < 6; ++t) sS[t * BOX + my] = val[t];
-    __syncthreads();
-    if (qq + 1 < NQ) fetch(qq + 1, val);
-    double w = 0.0;
-#pragma unroll
-    for (int t = 0; t < 6; ++t) w += sS[t * BOX + soff[t]];
-    (qq < 6 ? sW : sM)[(qq % 6) * BOX + my] = w;
-    __syncthreads();
+  double W[6], M[6];
+  gather(g.X + (long long)blockIdx.y * 3 * v3, W);
+  if (DO_M) {
+    __syncthreads();                                  // the staging boxes are reused
+    gather(g.XM + (long long)blockIdx.y * 3 * v3, M);
   }
-  // step 2: energies of the six tiles
+  // energies of the orbit (:2175-2233)
   double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  const double eijk = g.eo[td.i] + g.eo[td.j] + g.eo[td.k];
-  double evl[3][3];  // ev of the thread's label in range r at local index l[m]: evl[r][m]
+  const bool inside = full || ((O[0] + tx < v) && (O[1] + ty < v) && (O[2] + tz < v));
+  if (inside) {
+    const double D3 = g.eo[td.i] + g.eo[td.j] + g.eo[td.k] - g.ev[O[0] + tx] - g.ev[O[1] + ty] - g.ev[O[2] + tz];
+    const double rD = 1.0 / D3;
+    double z3[6], yv[6];
+    if (USE_Z || DO_Y) {
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
+      for (int w = 0; w < 6; ++w) {
+        // labels (a',b',c') = P_w(a,b,c): component m lies in range w[m] with local index l[w[m]]
+        const int w0 = PM(w, 0), w1 = PM(w, 1), w2 = PM(w, 2);
+        const double ta = sT[(0 * 3 + w0) * TS + l[w0]], tb = sT[(1 * 3 + w1) * TS + l[w1]], tc = sT[(2 * 3 + w2) * TS + l[w2]];
+        const int ibc = ((0 * 3 + w1) * 3 + w2) * TS * TS + l[w1] + TS * l[w2];
+        const int iac = ((1 * 3 + w0) * 3 + w2) * TS * TS + l[w0] + TS * l[w2];
+        const int iab = ((2 * 3 + w0) * 3 + w1) * TS * TS + l[w0] + TS * l[w1];
+        if (USE_Z) z3[w] = ta * sV[ibc] + tb * sV[iac] + tc * sV[iab];                          // (:2178-2179), times rD below
+        if (DO_Y) yv[w] = ta * tb * tc + ta * sY[ibc] + tb * sY[iac] + tc * sY[iab];            // (:2183-2184)
+      }
+    }
 #pragma unroll
-    for (int m = 0; m < 3; ++m) evl[r][m] = (O[r] + l[m] < v) ? g.ev[O[r] + l[m]] : 0.0;
-#pragma unroll
-  for (int q = 0; q < 6; ++q) {
-    constexpr int dummy = 0; (void)dummy;
-    const int q0 = PM(q, 0), q1 = PM(q, 1), q2 = PM(q, 2);
-    const bool inside = full || ((O[q0] + tx < v) && (O[q1] + ty < v) && (O[q2] + tz < v));
-    if (inside) {
-      const double D3 = eijk - evl[q0][0] - evl[q1][1] - evl[q2][2];
+    for (int u = 0; u < 6; ++u) {
       double tt = 0.0, zt = 0.0;
 #pragma unroll
       for (int s = 0; s < 6; ++s) {
-        const int s0 = PM(s, 0), s1 = PM(s, 1), s2 = PM(s, 2);
-        const int u = COMP(q, s);
-        tt += COEF(s) * sW[u * BOX + soff[s]];
-        if (USE_Z) {
-          // z3 at labels (a',b',c') = L o s: component m lies in range u[m] with local index l[s[m]]   (:2178-2179)
-          const int u0 = PM(u, 0), u1 = PM(u, 1), u2 = PM(u, 2);
-          double z = sT[(0 * 3 + u0) * TS + l[s0]] * sV[((0 * 3 + u1) * 3 + u2) * TS * TS + l[s1] + TS * l[s2]] +
-                     sT[(1 * 3 + u1) * TS + l[s1]] * sV[((1 * 3 + u0) * 3 + u2) * TS * TS + l[s0] + TS * l[s2]] +
-                     sT[(2 * 3 + u2) * TS + l[s2]] * sV[((2 * 3 + u0) * 3 + u1) * TS * TS + l[s0] + TS * l[s1]];
-          zt += COEF(s) * z;
-        }
+        tt += COEF(s) * W[COMP(u, s)];
+        if (USE_Z) zt += COEF(s) * z3[COMP(u, s)];
       }
-      const double rD = 1.0 / D3;
       tt *= rD;
       zt *= rD;
-      const double w = sW[q * BOX + my];
-      acc[0] += tt * w;
-      if (PAREN) acc[1] += (tt + zt) * w;
+      acc[0] += tt * W[u];
+      if (PAREN) acc[1] += (tt + zt) * W[u];
       if (DO_Y) {
-        const double ta = sT[(0 * 3 + q0) * TS + tx], tb = sT[(1 * 3 + q1) * TS + ty], tc = sT[(2 * 3 + q2) * TS + tz];
-        const double y = ta * tb * tc + ta * sY[((0 * 3 + q1) * 3 + q2) * TS * TS + ty + TS * tz] +
-                         tb * sY[((1 * 3 + q0) * 3 + q2) * TS * TS + tx + TS * tz] +
-                         tc * sY[((2 * 3 + q0) * 3 + q1) * TS * TS + tx + TS * ty];             // (:2183-2184)
-        acc[2] += tt * y;
-        if (PAREN) acc[3] += (tt + zt) * y;
+        acc[2] += tt * yv[u];
+        if (PAREN) acc[3] += (tt + zt) * yv[u];
       }
       if (DO_M) {
-        const double m = sM[q * BOX + my];
-        acc[4] += tt * m;
-        if (PAREN) acc[5] += (tt + zt) * m;
+        acc[4] += tt * M[u];
+        if (PAREN) acc[5] += (tt + zt) * M[u];
       }
     }
   }
@@ -399,18 +416,20 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
   for (int k = 0; k < 6; ++k) sums[k] = 0.0;
 
   Trace tr(st);
-  // GEMM-ready operand layouts (the reference's reshapes at :2056-2066, re-aimed at contiguous GEMM blocks)
   // K-concatenated GEMM operands (work arrays come from the engine's pool: cudaFree of GB-sized blocks is slow).
   // With the hole term written in the layout (c,b,a) it lands in the buffer of the permutation (r,q,p) as
   //     C_pqr(x,(y,z)) = sum_d t2(p,q,x,d) v_vovv(d,r,y,z) - sum_l v_ovoo(l,x,q,p) t2(l,r,y,z)
-  // i.e. ONE GEMM of depth K = v + o = nbf per permutation:
+  // i.e. ONE product of depth K = v + o = nbf per permutation:
   //     Acat(x, [d | l]; p,q) = [ t2(p,q,x,d) | -v_oovo(p,q,x,l) ]            (v x n) for each occupied pair
   //     Bcat([d | l], (y,z); r) = [ v_vvov(z,y,r,d) ; t2(l,r,y,z) ]           (n x v^2) for each occupied index
+  //     BcatT(k, (y,z); r)      = Bcat(k, (z,y); r)
   // (the reference's reshapes at :2056-2066, re-aimed at GEMM blocks).  M3 uses I_ooov_pp / I_vovv_pp instead (:2188-2193).
+  // The two permutations with the same first label are then one dual-segment GEMM (see the file header):
+  //     Y_s(x,(u,w); i,j,k) = Acat(x,.; P0,P1) Bcat(.,(u,w); P2) + Acat(x,.; P0,P2) BcatT(.,(u,w); P1),  (P0,P1,P2) = p_s(i,j,k)
   const int n = v + o;
   const size_t n_acat = (size_t)v * n * o * o, n_bcat = (size_t)n * v2 * o;
-  Scratch sAcat(e.pool, n_acat + 16), sBcat(e.pool, n_bcat + 16);  // +16: TMA boxes over-read the last 16-row chunk
-  std::unique_ptr<Scratch> sAcatM, sBcatM;
+  Scratch sAcat(e.pool, n_acat + 16), sBcat(e.pool, n_bcat + 16), sBcatT(e.pool, n_bcat + 16);  // +16: TMA boxes over-read the last 16-row chunk
+  std::unique_ptr<Scratch> sAcatM, sBcatM, sBcatMT;
   auto put = [&](const TView& in, const char* from, const char* to, double alpha, double* out, const long long* ostr) {
     int rank = (int)std::strlen(from), perm[4], dims[4];
     for (int d = 0; d < rank; ++d) {
@@ -425,23 +444,28 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
   put(s.get("v_oovo").view(), "pqxl", "xlpq", -1.0, sAcat.p + (size_t)v * v, a_str);
   put(s.get("v_vvov").view(), "zyrd", "dyzr", 1.0, sBcat.p, b_str);
   put(s.t2.view(), "lryz", "lyzr", 1.0, sBcat.p + v, b_str);
+  put(s.get("v_vvov").view(), "yzrd", "dyzr", 1.0, sBcatT.p, b_str);
+  put(s.t2.view(), "lrzy", "lyzr", 1.0, sBcatT.p + v, b_str);
   if (do_m) {
     sAcatM.reset(new Scratch(e.pool, n_acat + 16)); sBcatM.reset(new Scratch(e.pool, n_bcat + 16));
+    sBcatMT.reset(new Scratch(e.pool, n_bcat + 16));
     put(s.t2.view(), "pqxd", "xdpq", 1.0, sAcatM->p, a_str);
     put(s.get("I_ooov_pp").view(), "qplx", "xlpq", -1.0, sAcatM->p + (size_t)v * v, a_str);
     put(s.get("I_vovv_pp").view(), "dryz", "dyzr", 1.0, sBcatM->p, b_str);
     put(s.t2.view(), "lryz", "lyzr", 1.0, sBcatM->p + v, b_str);
+    put(s.get("I_vovv_pp").view(), "drzy", "dyzr", 1.0, sBcatMT->p, b_str);
+    put(s.t2.view(), "lrzy", "lyzr", 1.0, sBcatMT->p + v, b_str);
   }
 
   std::vector<TripleDesc> tri = my_triples(o, s.opt.triples_ijk_symmetry, false, rank, nranks);
   if (tri.empty()) return;
   tr.lap(0);
-  const long long per_triple = (do_m ? 12 : 6) * v3 * 8;
+  const long long per_triple = (do_m ? 6 : 3) * v3 * 8;
   int nb = (int)std::max<long long>(1, std::min<long long>((long long)tri.size(), s.opt.triples_batch_bytes / per_triple));
-  nb = std::min(nb, 65535 / 6);
-  Scratch X(e.pool, (size_t)nb * 6 * v3);
+  nb = std::min(nb, 65535 / 3);
+  Scratch X(e.pool, (size_t)nb * 3 * v3);
   std::unique_ptr<Scratch> XM;
-  if (do_m) XM.reset(new Scratch(e.pool, (size_t)nb * 6 * v3));
+  if (do_m) XM.reset(new Scratch(e.pool, (size_t)nb * 3 * v3));
   // unordered label-tile triples A <= B <= C
   const int ntile = (v + TS - 1) / TS;
   std::vector<int> tiles_h;
@@ -449,16 +473,73 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
     for (int B = A; B < ntile; ++B)
       for (int C = B; C < ntile; ++C) { tiles_h.push_back(A); tiles_h.push_back(B); tiles_h.push_back(C); }
   const long long ntt = (long long)tiles_h.size() / 3;
+  AFESP_REQUIRE(ntt < (1LL << 31), "triples: too many label tiles");
   Scratch tiles_d(e.pool, (tiles_h.size() + 1) / 2 + 1);
   AFESP_CUDA_CHECK(cudaMemcpyAsync(tiles_d.p, tiles_h.data(), tiles_h.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  Scratch descs(e.pool, (size_t)nb * 3);  // TripleDesc is 24 bytes = 3 doubles
   static_assert(sizeof(TripleDesc) == 24, "TripleDesc layout");
-  Scratch ptrs_raw(e.pool, (size_t)nb * 6 * 5);   // 3 pointer arrays + 2 int32 block-index arrays (TMA gather form)
-  struct { double* p; } ptrs_shim{ptrs_raw.p};
   const size_t nbatches = (tri.size() + nb - 1) / nb;
-  Scratch batch_sums(e.pool, nbatches * 6);
   const bool al16 = (v % 2 == 0) && (o % 2 == 0);
-  const int perm6[6][3] = {{0, 1, 2}, {1, 0, 2}, {2, 1, 0}, {0, 2, 1}, {1, 2, 0}, {2, 0, 1}};
+  const int perm3[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 1, 0}};   // s = abc, bac, cba (first three rows of c_perm)
+
+  // Launch tables of ALL batches, built on the host and uploaded once (no per-batch synchronisation): the triple
+  // descriptors, and per GEMM block the (A pair, B index) of both K segments as block indices (TMA gather form) and as
+  // pointers (cp.async fallback).  Within a batch the blocks are sorted by their B blocks so that blocks reading the same
+  // (n x v^2) operand block -- 52 MB at nbf=200, 0.4 GB at nbf=400 -- run back to back and find it in L2; each block
+  // still writes its own slot g of the output buffer (the epilogue addresses Y by triple and s).
+  const size_t ngt = tri.size() * 3;                 // GEMM blocks over all batches
+  std::vector<int> hidx(ngt * 4);                    // [4][ngt]: Aidx, Bidx, Aidx2, Bidx2
+  std::vector<long long> hslot(ngt);                 // output slot within the batch buffer
+  for (size_t bi = 0; bi < nbatches; ++bi) {
+    const size_t t0 = bi * nb;
+    const int cb = (int)std::min<size_t>(nb, tri.size() - t0), ng = cb * 3;
+    std::vector<int> order(ng), k_pq(ng), k_r(ng), k_pq2(ng), k_r2(ng);
+    for (int tb = 0; tb < cb; ++tb) {
+      const TripleDesc& td = tri[t0 + tb];
+      const int idx[3] = {td.i, td.j, td.k};
+      for (int t = 0; t < 3; ++t) {
+        const int g = tb * 3 + t, P0 = idx[perm3[t][0]], P1 = idx[perm3[t][1]], P2 = idx[perm3[t][2]];
+        order[g] = g;
+        k_pq[g] = P0 + o * P1; k_r[g] = P2;      // X_s      : Acat(P0,P1) Bcat(P2)
+        k_pq2[g] = P0 + o * P2; k_r2[g] = P1;    // X_{s+3}^T: Acat(P0,P2) BcatT(P1)
+      }
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      return k_r[a] != k_r[b] ? k_r[a] < k_r[b] : k_r2[a] < k_r2[b];
+    });
+    for (int z = 0; z < ng; ++z) {
+      const int g = order[z];
+      const size_t w = t0 * 3 + z;
+      hidx[0 * ngt + w] = k_pq[g]; hidx[1 * ngt + w] = k_r[g];
+      hidx[2 * ngt + w] = k_pq2[g]; hidx[3 * ngt + w] = k_r2[g];
+      hslot[w] = g;
+    }
+  }
+  Scratch descs(e.pool, tri.size() * 3);             // TripleDesc is 24 bytes = 3 doubles
+  Scratch idx_d(e.pool, ngt * 2 + 2);                // 4 * ngt int32
+  AFESP_CUDA_CHECK(cudaMemcpyAsync(descs.p, tri.data(), tri.size() * sizeof(TripleDesc), cudaMemcpyHostToDevice, st));
+  AFESP_CUDA_CHECK(cudaMemcpyAsync(idx_d.p, hidx.data(), hidx.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  const int* didx = reinterpret_cast<const int*>(idx_d.p);
+  // pointer tables (5 per block: A, B, C, A2, B2) for one operand set; built once per set
+  auto make_ptrs = [&](const double* Acat, const double* Bcat, const double* BcatT, double* out, Scratch& dst) {
+    std::vector<const double*> hp(ngt * 5);
+    for (size_t w = 0; w < ngt; ++w) {
+      hp[0 * ngt + w] = Acat + (long long)hidx[0 * ngt + w] * v * n;
+      hp[1 * ngt + w] = Bcat + (long long)hidx[1 * ngt + w] * n * v2;
+      hp[2 * ngt + w] = out + hslot[w] * v3;
+      hp[3 * ngt + w] = Acat + (long long)hidx[2 * ngt + w] * v * n;
+      hp[4 * ngt + w] = BcatT + (long long)hidx[3 * ngt + w] * n * v2;
+    }
+    AFESP_CUDA_CHECK(cudaMemcpyAsync(dst.p, hp.data(), hp.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
+    AFESP_CUDA_CHECK(cudaStreamSynchronize(st));     // hp is a stack-scoped staging vector (once per (T) call)
+  };
+  Scratch ptrs_W(e.pool, ngt * 5);
+  make_ptrs(sAcat.p, sBcat.p, sBcatT.p, X.p, ptrs_W);
+  std::unique_ptr<Scratch> ptrs_M;
+  if (do_m) {
+    ptrs_M.reset(new Scratch(e.pool, ngt * 5));
+    make_ptrs(sAcatM->p, sBcatM->p, sBcatMT->p, XM->p, *ptrs_M);
+  }
+  Scratch batch_sums(e.pool, nbatches * 6);
 
   // AFESP_T_VERIFY=1: every batch also through the cp.async kernel, compared on the device; =2: control experiment,
   // the cp.async kernel against itself (both passes with the TMA path switched off)
@@ -466,78 +547,51 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
   const int scope_at_entry = gemm_tma_scope_get();
   if (verify_mode == 2) gemm_tma_scope(0);
   const bool verify_t = verify_mode == 2 || (verify_mode == 1 && gemm_tma_scope_get() != 0);
-  std::unique_ptr<Scratch> verify_buf, verify_cnt;
+  std::unique_ptr<Scratch> verify_buf, verify_cnt, verify_ptrs;
   double verify_elems = 0.0;
   if (verify_t) {
-    verify_buf.reset(new Scratch(e.pool, (size_t)nb * 6 * v3));
+    verify_buf.reset(new Scratch(e.pool, (size_t)nb * 3 * v3));
     verify_cnt.reset(new Scratch(e.pool, 2));
+    verify_ptrs.reset(new Scratch(e.pool, ngt * 5));
+    make_ptrs(sAcat.p, sBcat.p, sBcatT.p, verify_buf->p, *verify_ptrs);
     AFESP_CUDA_CHECK(cudaMemsetAsync(verify_cnt->p, 0, 16, st));
   }
   tr.lap(1);
   for (size_t bi = 0; bi < nbatches; ++bi) {
     const size_t t0 = bi * nb;
     const int cb = (int)std::min<size_t>(nb, tri.size() - t0);
-    AFESP_CUDA_CHECK(cudaMemcpyAsync(descs.p, &tri[t0], (size_t)cb * sizeof(TripleDesc), cudaMemcpyHostToDevice, st));
-    const int ng = cb * 6;
-    auto run_gemms = [&](const double* Acat, const double* Bcat, double* out) {
-      // Launch order of the ng blocks: sorted by the occupied index r of Bcat, so that blocks reading the same
-      // (n x v^2) Bcat block -- 52 MB at nbf=200, 0.4 GB at nbf=400 -- run back to back and find it in L2.  Each block
-      // still writes its own slot g of the output buffer (the fused epilogue addresses X by triple and permutation).
-      std::vector<int> order(ng), rkey(ng), pqkey(ng);
-      for (int tb = 0; tb < cb; ++tb) {
-        const TripleDesc& td = tri[t0 + tb];
-        const int idx[3] = {td.i, td.j, td.k};
-        for (int t = 0; t < 6; ++t) {
-          const int g = tb * 6 + t;
-          order[g] = g;
-          rkey[g] = idx[perm6[t][2]];
-          pqkey[g] = idx[perm6[t][0]] + o * idx[perm6[t][1]];
-        }
-      }
-      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return rkey[a] < rkey[b]; });
-      std::vector<const double*> hp((size_t)ng * 3);
-      std::vector<int> hidx((size_t)ng * 2);
-      for (int z = 0; z < ng; ++z) {
-        const int g = order[z];
-        hp[0 * ng + z] = Acat + (long long)pqkey[g] * v * n;      // (x  x [d|l])  for the occupied pair (p,q)
-        hp[1 * ng + z] = Bcat + (long long)rkey[g] * n * v2;       // ([d|l] x (y,z))  for the occupied index r
-        hp[2 * ng + z] = out + (long long)g * v3;                  // C(x,(y,z))
-        hidx[z] = pqkey[g];
-        hidx[(size_t)ng + z] = rkey[g];
-      }
-      int* didx = reinterpret_cast<int*>(ptrs_shim.p + (size_t)ng * 3);
-      AFESP_CUDA_CHECK(cudaMemcpyAsync(ptrs_shim.p, hp.data(), hp.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
-      AFESP_CUDA_CHECK(cudaMemcpyAsync(didx, hidx.data(), hidx.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-      AFESP_CUDA_CHECK(cudaStreamSynchronize(st));  // hp is a stack-scoped staging vector
-      tr.lap(2);
-      const double* const* dp = reinterpret_cast<const double* const*>(ptrs_shim.p);
+    const int ng = cb * 3;
+    auto run_gemms = [&](const double* Acat, const double* Bcat, const double* BcatT, const Scratch& ptrs) {
+      const double* const* dp = reinterpret_cast<const double* const*>(ptrs.p);
+      const size_t w0 = t0 * 3;
       GemmBatch b1;
-      b1.count = ng; b1.Aptr = dp + 0 * ng; b1.Bptr = dp + 1 * ng;
-      b1.Cptr = (double* const*)(dp + 2 * ng); b1.ptr_aligned16 = al16;
-      b1.Abase = Acat; b1.Ablock = (long long)v * n; b1.Anblocks = (long long)o * o; b1.Aidx = didx;
-      b1.Bbase = Bcat; b1.Bblock = (long long)n * v2; b1.Bnblocks = o; b1.Bidx = didx + ng;
+      b1.count = ng; b1.Aptr = dp + 0 * ngt + w0; b1.Bptr = dp + 1 * ngt + w0;
+      b1.Cptr = (double* const*)(dp + 2 * ngt + w0); b1.ptr_aligned16 = al16;
+      b1.Aptr2 = dp + 3 * ngt + w0; b1.Bptr2 = dp + 4 * ngt + w0;
+      b1.Abase = Acat; b1.Ablock = (long long)v * n; b1.Anblocks = (long long)o * o; b1.Aidx = didx + 0 * ngt + w0;
+      b1.Bbase = Bcat; b1.Bblock = (long long)n * v2; b1.Bnblocks = o; b1.Bidx = didx + 1 * ngt + w0;
+      b1.Bbase2 = BcatT; b1.Aidx2 = didx + 2 * ngt + w0; b1.Bidx2 = didx + 3 * ngt + w0;
       dgemm(st, 'N', 'N', v, (int)v2, n, 1.0, nullptr, v, nullptr, n, 0.0, nullptr, v, &b1);
       tr.lap(4);
     };
-    run_gemms(sAcat.p, sBcat.p, X.p);
+    run_gemms(sAcat.p, sBcat.p, sBcatT.p, ptrs_W);
     if (verify_t) {
       // the same batch once more through the cp.async kernel, element-wise comparison on the device
       const int scope = gemm_tma_scope_get();
       gemm_tma_scope(0);
-      run_gemms(sAcat.p, sBcat.p, verify_buf->p);
+      run_gemms(sAcat.p, sBcat.p, sBcatT.p, *verify_ptrs);
       gemm_tma_scope(scope);
       k_count_mismatch<<<148 * 8, 256, 0, st>>>(X.p, verify_buf->p, (long long)ng * v3, 1e-11,
                                                 reinterpret_cast<unsigned long long*>(verify_cnt->p));
       verify_elems += (double)ng * v3;
     }
-    if (do_m) run_gemms(sAcatM->p, sBcatM->p, XM->p);
+    if (do_m) run_gemms(sAcatM->p, sBcatM->p, sBcatMT->p, *ptrs_M);
     FusedArgs fa{};
     fa.X = X.p; fa.XM = do_m ? XM->p : nullptr; fa.t1 = s.t1.p(); fa.t2 = s.t2.p(); fa.vo = s.get("v_oovv").p();
-    fa.eo = s.eo.p(); fa.ev = s.ev.p(); fa.tr = reinterpret_cast<const TripleDesc*>(descs.p);
+    fa.eo = s.eo.p(); fa.ev = s.ev.p(); fa.tr = reinterpret_cast<const TripleDesc*>(descs.p) + t0;
     fa.tiles = reinterpret_cast<const int*>(tiles_d.p);
     fa.o = o; fa.v = v;
     const long long nblocks = ntt * cb;
-    AFESP_REQUIRE(ntt < (1LL << 31), "triples: too many label tiles");
     fa.partials = reduce_scratch(e, (size_t)nblocks * 6);
     dim3 grid((unsigned)ntt, (unsigned)cb), block(TS, TS, TS);
     {
@@ -564,7 +618,7 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
     tr.lap(6);
   }
   {
-    const char* names[] = {"operands", "setup", "ptr upload", "-", "gemm (K=v+o)", "fused epilogue", "finish"};
+    const char* names[] = {"operands", "setup", "-", "-", "gemm (K=2(v+o))", "fused epilogue", "finish"};
     tr.report(names, 7);
   }
   std::vector<double> h(nbatches * 6);

@@ -16,7 +16,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .capi import AfespGpu
+from .capi import AfespError, AfespGpu
 
 # calc_type -> (level, restricted, paren, renorm, comp_renorm)  (src/system.f90:116-165)
 CALC_TYPES = {
@@ -317,7 +317,15 @@ def ccsd_loop(gpu: AfespGpu, nocc, restricted, eps, e_tol, t_tol, diis_n, maxite
     """The iteration loop of do_ccsd_spatial / do_ccsd_spinorb (src/ccsd.f90:339-396 / 229-271) on the host side:
     the GPU does one iteration per call, the host keeps the table, the convergence test (:1805) and the DIIS call."""
     t_init = time.perf_counter()
-    e, rms = gpu.ccsd_init(nocc, restricted, eps, diis_n)
+    try:
+        e, rms = gpu.ccsd_init(nocc, restricted, eps, diis_n)
+    except AfespError as ex:
+        if ex.code == 5 and out is not None:   # the reference's assertion on <pq||rs> fired (src/ccsd.f90:161-164)
+            info = gpu.ccsd_init_info()
+            out.write(" Forming antisymmetrised spinorbital ERIs...\n Time taken: %8.6f s\n\n" % info["slices_s"])
+            out.write(" Checking that the permuational symmetry of the antisymmetrised integrals hold...\n")
+            out.write(" Permutational symmetry error: %15.6E\n" % info["symmetry_error"])
+        raise
     table = [("MP1", e, e - 0.0, rms)]
     if out is not None:
         if restricted:   # src/ccsd.f90:312-324 with the prints of init_cc (:427-526)
@@ -325,11 +333,13 @@ def ccsd_loop(gpu: AfespGpu, nocc, restricted, eps, e_tol, t_tol, diis_n, maxite
                       " Forming energy denominator matrices...\n Allocating amplitude tensors...\n"
                       " Forming ERI slices...\n Forming initial amplitude guesses...\n"
                       " Allocating stored intermediate tensors...\n")
-        else:            # src/ccsd.f90:106-220
-            dt = time.perf_counter() - t_init
-            out.write(" Forming antisymmetrised spinorbital ERIs...\n Time taken: %8.6f s\n\n" % dt)
+        else:            # src/ccsd.f90:106-220.  The (2n)^4 tensor is never formed here: the nine slices are gathered
+            # straight from the packed MO integrals (first timer), the reference's symmetry assertion runs on the device
+            # over the same index set (second timer), and nothing is left to do for the third banner.
+            info = gpu.ccsd_init_info()
+            out.write(" Forming antisymmetrised spinorbital ERIs...\n Time taken: %8.6f s\n\n" % info["slices_s"])
             out.write(" Checking that the permuational symmetry of the antisymmetrised integrals hold...\n"
-                      " Time taken: %8.6f s\n\n" % 0.0)
+                      " Time taken: %8.6f s\n\n" % info["check_s"])
             out.write(" Forming slices of antisymmetrised spinorbital ERIs\n Time taken: %8.6f s\n\n" % 0.0)
             out.write(" Initialise CC intermediate tensors and DIIS auxilliary arrays...\n"
                       " Forming energy denominator matrices...\n Allocating amplitude tensors...\n"
@@ -432,6 +442,9 @@ def run(inp: ElsInput, gpu: AfespGpu | None = None, device: int = 0, verbose: bo
                     res.timings["triples_device_ms"] = gpu.last_stage_ms()
                     res.timings["triples_s"] = time.perf_counter() - t0
                     out.write(_taken(("restricted " if restricted else "unrestricted ") + name, res.timings["triples_s"]))
+        except AfespError as ex:
+            ex.stdout = out.getvalue()   # what els.out held when the reference would have stopped (error -> stop 999)
+            raise
         finally:
             if own:
                 gpu.close()

@@ -2,16 +2,22 @@
 """Benchmark of the coupled-cluster hot path (BASELINE.json metric: CCSD s/iter & (T) wall-s; % FP64 tensor peak; vs CPU).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nbf 200 --nocc 20]
+    python bench.py --workload n2|f2|h2o|h2o-spinorb      (sample_data molecules, whole converged run; see below)
 
 One "step" = one pass of the hot path over the synthetic (nbf, nocc) system: one spin-free CCSD iteration
 (intermediates + amplitude equations + energy + DIIS extrapolation) followed by the full (T) correction
 (calc_type CCSD(T)_spatial).  `value` = seconds per step, device-resident inputs, max over ranks; the breakdown
-(ccsd_s_per_iter, t_wall_s, ao2mo_s) is carried in extra keys.  Under torchrun every rank runs the (replicated) CCSD
-iteration and its round-robin share of the (i<=j<=k) triples; the six (T) sums are combined by one NCCL allreduce inside
+(ccsd_s_per_iter, t_wall_s, ao2mo_s) is carried in extra keys.  Under torchrun every rank runs its column share of the
+CCSD GEMMs and its round-robin share of the (i<=j<=k) triples; the six (T) sums are combined by one NCCL allreduce inside
 the library ("scaling": "strong": total work fixed).
 
-`--impl reference` times the CPU port of the reference's own loops (oracle/cpu_kernels.c + OpenBLAS dgemm) on the host
-cores on a bounded sample of the same workload (the Fortran reference cannot be compiled here: no Fortran compiler).
+After the timed loop at the headline shape (nbf=200/nocc=20, BASELINE.json configs[3]) the same hot path runs ONCE at
+the north-star target shape nbf=400/nocc=40 (configs[4]; one e2e pass, then one device-timed pass) and is attached as
+`target_config` -- its ~85 s step cannot be the K-step default of a bench that has to end in minutes.
+
+`--impl reference` times the CPU port of the reference's own code path (oracle/cpu_ccsd.c, oracle/cpu_kernels.c: the same
+dgemm calls through the image's OpenBLAS, the same omp_reshape passes and naive OpenMP loop nests as src/ccsd.f90) on all
+host cores; the Fortran reference cannot be compiled here (no Fortran compiler).
 """
 import argparse
 import json
@@ -19,7 +25,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -29,6 +34,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "ccsd_iter_plus_T_seconds"
 UNIT = "s"
+PINNED = os.path.join(ROOT, "tests", "golden", "bench_pinned.json")
 
 
 # Keep stdout clean for the single JSON line: libraries loaded later (NCCL prints its version banner on stdout) write
@@ -46,76 +52,142 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-# ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_sample(nbf, nocc, budget_s):
-    """Bounded sample of the reference CPU path at shape (nbf, nocc): ladder dgemm (full), ring loop nest on a slice
-    of b, reference (T) loop on a handful of ordered triples; each extrapolated to the full loop and stated."""
-    from oracle import cpu_port
+def config_of(nbf, nocc):
+    """`config` of BOTH arms (the driver compares them): the workload and nothing else."""
+    return {"workload": f"synthetic integrals nbf={nbf} nocc={nocc} CCSD(T)_spatial", "nbf": nbf, "nocc": nocc,
+            "calc_type": "CCSD(T)_spatial"}
 
-    lib = cpu_port.load()
-    threads = int(lib.afesp_ref_threads())
-    o, v = nocc, nbf - nocc
-    rng = np.random.default_rng(1)
-    t2 = np.asfortranarray(rng.standard_normal((o, o, v, v)) * 1e-3)
-    Iov = np.asfortranarray(rng.standard_normal((o, v, o, v)) * 1e-2)
-    Ivo = np.asfortranarray(rng.standard_normal((v, o, o, v)) * 1e-2)
-    # ladder dgemm through OpenBLAS (src/ccsd.f90:1669): c(o^2 x v^2) . v_vvvv(v^2 x v^2).  The dense v^4 operand is
-    # 8.4 GB at nbf=200 and 134 GB at nbf=400, so a column block of at most 4 GB is multiplied and the time scaled.
-    ncol = int(max(1, min(v * v, (4 << 30) // (8 * v * v))))
-    vv = np.full((v * v, ncol), 1e-3, order="F")
-    cm = np.asfortranarray(t2.reshape((o * o, v * v), order="F"))
-    t0 = time.perf_counter()
-    _ = cm @ vv
-    t_ladder = (time.perf_counter() - t0) * (v * v) / ncol
-    ladder_note = "in full" if ncol == v * v else f"on {ncol} of {v * v} columns, x{v * v / ncol:.1f}"
-    del vv
-    # ring loop nest (src/ccsd.f90:1680-1695): calibrate on 1 slice of b, then spend ~budget/3
-    _, dt1 = cpu_port.ring(lib, t2, Iov, t2, Ivo, bmax=1)
-    bmax = int(max(1, min(v, (budget_s / 3.0) / max(dt1, 1e-6))))
-    _, dt = cpu_port.ring(lib, t2, Iov, t2, Ivo, bmax=bmax)
-    t_ring = dt * v / bmax
-    # (T): reference loop (src/ccsd.f90:2152-2233) on ntri ordered triples, one per thread
-    t1 = np.asfortranarray(rng.standard_normal((o, v)) * 1e-2)
-    voovv = t2
-    vvvov = np.asfortranarray(np.full((v, v, o, v), 1e-3))
-    voovo = np.asfortranarray(rng.standard_normal((o, o, v, o)) * 1e-2)
-    eps = np.concatenate([np.linspace(-2, -0.5, o), np.linspace(0.5, 3, v)])
-    ntri = threads
-    ijk = [(int(rng.integers(o)), int(rng.integers(o)), int(rng.integers(o))) for _ in range(ntri)]
-    # calibrate on one slab of the outer virtual loop, then spend ~budget/3 (all v slabs when they fit)
-    _, dt1 = cpu_port.triples(lib, t1, t2, voovv, vvvov, voovo, eps, ijk, True, False, amax=1)
-    amax = int(max(1, min(v, (budget_s / 3.0) / max(dt1, 1e-6))))
-    _, dt_t = cpu_port.triples(lib, t1, t2, voovv, vvvov, voovo, eps, ijk, True, False, amax=amax)
-    t_T = dt_t * (v / amax) * (o ** 3) / ntri
-    sample = (f"ladder dgemm o^2 x v^2 x v^2 {ladder_note} ({t_ladder:.2f}s) + ring loop nest :1680-1695 on b<{bmax} of {v} "
-              f"({dt:.2f}s, x{v / bmax:.1f}) [the other per-iteration terms of the reference are smaller dgemms and are "
-              f"not timed: lower bound] + reference (T) loop on {ntri} of {o ** 3} ordered triples, outer virtual "
-              f"index a<{amax} of {v} ({dt_t:.2f}s, x{(v / amax) * o ** 3 / ntri:.0f})")
-    return {"ccsd_s_per_iter": t_ladder + t_ring, "t_wall_s": t_T, "value": t_ladder + t_ring + t_T,
-            "cores": threads, "sample": sample, "kind": "port"}
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+class CpuReference:
+    """The reference's CPU path at shape (nbf, nocc) on every host core this process may use, whatever
+    OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1): OpenMP loops and OpenBLAS dgemms both.
+
+    Inputs are the same synthetic system the GPU arm runs (MO integrals from the factored form, MP1 amplitudes).  One
+    sample = (a) ONE COMPLETE spin-free CCSD iteration as src/ccsd.f90:1040-1312 + 1538-1732 issues it -- every dgemm
+    (ladder included) and every reshape in full; the two naive o^3v^3 loop nests (:1170-1182, :1680-1695) in full when
+    the time budget allows, else on a slab of their outermost index (>= 1/8), scaled linearly and stated; (b) the
+    reference (T) loop (:2152-2233) on one COMPLETE ordered triple per thread, scaled by o^3 / triples; (c) the AO->MO
+    quarter transforms (src/mp2.f90:321-387) on a slab of the outermost index (reported as ao2mo_s, not part of `value`,
+    which is CCSD iteration + (T) like the GPU arm's)."""
+
+    def __init__(self, nbf, nocc):
+        from oracle import cpu_port
+
+        self.cp = cpu_port
+        self.lib = cpu_port.load()
+        self.threads = cpu_port.set_threads(self.lib, host_cores())
+        self.n, self.o, self.v = nbf, nocc, nbf - nocc
+        n, o, v = self.n, self.o, self.v
+        t0 = time.perf_counter()
+        self.mo, self.Cmo, self.eps = cpu_port.synthetic_mo_integrals(n, o)
+        try:
+            avail = int([ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0].split()[1]) * 1024
+        except Exception:
+            avail = 32 << 30
+        dense = 8 * v ** 4
+        self.ncol_d = v if dense <= min(12 << 30, avail // 4) else max(1, int((4 << 30) // (8 * v ** 3)))
+        self.V = cpu_port.slices(self.lib, self.mo, n, o, vvvv_cols=(0, self.ncol_d))
+        eo, ev = self.eps[:o], self.eps[o:]
+        D2 = eo[:, None, None, None] + eo[None, :, None, None] - ev[None, None, :, None] - ev[None, None, None, :]
+        self.t2 = np.asfortranarray(self.V["v_oovv"] / D2)
+        self.t1 = np.zeros((o, v), order="F")
+        rng = np.random.default_rng(7)
+        self.triples = [tuple(int(x) for x in rng.integers(0, o, 3)) for _ in range(self.threads)]
+        self.frac = 1.0 / 8.0      # slab fraction of the two naive loop nests; raised after the first (calibration) sample
+        self.setup_s = time.perf_counter() - t0
+        self.eri_ao = None
+
+    def sample(self, budget_s):
+        cp, lib, n, o, v = self.cp, self.lib, self.n, self.o, self.v
+        # (b) (T): one complete ordered triple per thread
+        t0 = time.perf_counter()
+        _, dt_t = cp.triples(lib, self.t1, self.t2, self.V["v_oovv"], self.V["v_vvov"], self.V["v_oovo"], self.eps,
+                             self.triples, True, False)
+        t_T = dt_t * (o ** 3) / len(self.triples)
+        # (a) complete CCSD iteration; slab fraction from what is left of the budget
+        left = max(0.0, budget_s - (time.perf_counter() - t0))
+        if hasattr(self, "_naive_full_s"):
+            self.frac = float(min(1.0, max(1.0 / 8.0, (left - self._rest_s) / max(self._naive_full_s, 1e-9))))
+        bmax = max(1, min(v, int(round(self.frac * v))))
+        amax = bmax
+        _, _, parts, wall = cp.ccsd_iter(lib, self.V, self.eps, self.t1, self.t2, ring_bmax=bmax, iovov_amax=amax)
+        parts = [float(x) for x in parts]
+        ladder = parts[4] * v / self.ncol_d
+        iovov, ring = parts[1] * v / amax, parts[5] * v / bmax
+        rest = parts[0] + parts[2] + parts[3] + parts[6] + parts[7]
+        self._naive_full_s, self._rest_s = iovov + ring, rest + parts[4]
+        t_iter = rest + ladder + iovov + ring
+        return {"ccsd_s_per_iter": t_iter, "t_wall_s": t_T, "value": t_iter + t_T,
+                "parts": {"ladder_dgemm": ladder, "ring_loop": ring, "I_ovov_loop": iovov, "other": rest,
+                          "triples_sample_s": dt_t, "ccsd_sample_s": wall},
+                "slab": {"ring_b": [bmax, v], "iovov_a": [amax, v], "ladder_cols": [self.ncol_d * v, v * v],
+                         "triples": [len(self.triples), o ** 3]}}
+
+    def ao2mo(self, budget_s=6.0):
+        """AO->MO of src/mp2.f90:321-387 on an l-slab sized for ~budget_s, scaled by n / slab."""
+        from afesp_b200 import synthetic
+
+        n = self.n
+        if self.eri_ao is None:
+            if n > 240:
+                return None   # the packed AO integrals alone are 25.7 GB at nbf=400; not sampled
+            self.eri_ao, _, _ = synthetic.make(n, self.o)
+        _, t1 = self.cp.ao2mo(self.lib, self.eri_ao, self.Cmo, lmax=1, smax=1, want_result=False)
+        per_l = float(np.sum(t1[:4]))
+        lmax = int(max(1, min(n, budget_s / max(per_l, 1e-6))))
+        _, t = self.cp.ao2mo(self.lib, self.eri_ao, self.Cmo, lmax=lmax, smax=lmax, want_result=False)
+        return {"ao2mo_s": float(np.sum(t[:4])) * n / lmax, "slab": [lmax, n], "sample_s": float(np.sum(t[:4]))}
+
+    def describe(self, s):
+        sl = s["slab"]
+        f = lambda a: "in full" if a[0] >= a[1] else f"on {a[0]} of {a[1]} (x{a[1] / a[0]:.2f})"
+        return (f"one complete spin-free CCSD iteration as src/ccsd.f90:1040-1312,1538-1732 issues it (all dgemms and "
+                f"reshapes in full; ladder dgemm :1669 columns {f(sl['ladder_cols'])}; ring loop nest :1680-1695 outer index "
+                f"{f(sl['ring_b'])}; I_ovov loop nest :1170-1182 outer index {f(sl['iovov_a'])}) = "
+                f"{s['ccsd_s_per_iter']:.2f} s/iter [{s['parts']['ccsd_sample_s']:.1f} s measured] + reference (T) loop "
+                f":2152-2233 on {sl['triples'][0]} complete ordered triples (one per thread) of {sl['triples'][1]} "
+                f"(x{sl['triples'][1] / sl['triples'][0]:.0f}) = {s['t_wall_s']:.0f} s [{s['parts']['triples_sample_s']:.1f} s measured]")
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    budget = max(20.0, 150.0 / max(1, args.steps + args.warmup))
-    vals = []
-    last = None
-    for s in range(args.warmup + args.steps):
-        last = cpu_sample(args.nbf, args.nocc, budget)
+    ref = CpuReference(args.nbf, args.nocc)
+    log(f"[reference] {ref.threads} threads, inputs in {ref.setup_s:.1f}s, OpenBLAS {ref.lib._blas_path}")
+    total = args.warmup + args.steps
+    budget = max(8.0, min(60.0, 300.0 / max(1, total)))    # CPU seconds per sample: the whole run ends within minutes
+    vals, samples = [], []
+    for s in range(total):
+        smp = ref.sample(budget)
         if s >= args.warmup:
-            vals.append(last["value"])
+            vals.append(smp["value"]); samples.append(smp)
+        log(f"[reference] sample {s}: value {smp['value']:.1f}s (ccsd {smp['ccsd_s_per_iter']:.2f}, T {smp['t_wall_s']:.0f}) slab {smp['slab']}")
+    ao = ref.ao2mo()
     v = float(np.mean(vals))
+    last = samples[-1]
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic integrals nbf={args.nbf} nocc={args.nocc} CCSD(T)_spatial", "nbf": args.nbf,
-                   "nocc": args.nocc, "calc_type": "CCSD(T)_spatial"},
-        "ccsd_s_per_iter": last["ccsd_s_per_iter"], "t_wall_s": last["t_wall_s"],
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(args.nbf, args.nocc),
+        "ccsd_s_per_iter": float(np.median([s["ccsd_s_per_iter"] for s in samples])),
+        "t_wall_s": float(np.median([s["t_wall_s"] for s in samples])),
+        "ao2mo_s": ao["ao2mo_s"] if ao else None, "ao2mo_slab": ao["slab"] if ao else None,
+        "samples": {"n": len(vals), "min": float(np.min(vals)), "median": float(np.median(vals)), "max": float(np.max(vals)),
+                    "cpu_seconds_per_sample": last["parts"]["ccsd_sample_s"] + last["parts"]["triples_sample_s"]},
+        "parts_last_sample": last["parts"],
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": ref.threads, "kind": "port", "sample": ref.describe(last)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "value is the full-workload time each bounded sample extrapolates to (factors in cpu_baseline.sample); "
+                "the timed region itself is samples.cpu_seconds_per_sample per step",
     }
     emit(line)
 
@@ -162,17 +234,58 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ------------------------------------------------------------------------------------------------ parity
+def load_pins():
+    try:
+        return json.load(open(PINNED))
+    except Exception:
+        return {}
+
+
+def parity_block(n, o, e_mp2, e_mp1, traj):
+    """Energies of this run against the pinned single-GPU (replicated) values for the same shape: MP2 (also pinned by the
+    CPU oracle), MP1 and, step by step, E_CCSD and the (T) sum e_T.  Tolerance 1e-9 Eh (BASELINE.json north_star)."""
+    pins = load_pins().get(f"nbf{n}_nocc{o}")
+    if not pins:
+        return {"pinned": False, "note": f"no pinned values for nbf={n} nocc={o} in tests/golden/bench_pinned.json"}
+    tol = 1e-9
+    out = {"pinned": True, "tolerance_Eh": tol, "source": pins.get("source")}
+    diffs = {"e_mp2": abs(e_mp2 - pins["e_mp2"]), "e_mp1": abs(e_mp1 - pins["e_mp1"])}
+    if "e_mp2_oracle" in pins:
+        diffs["e_mp2_vs_cpu_oracle"] = abs(e_mp2 - pins["e_mp2_oracle"])
+    if "e_ccsd_iter1_cpu_port" in pins and traj:
+        diffs["e_ccsd_iter1_vs_cpu_port"] = abs(traj[0][0] - pins["e_ccsd_iter1_cpu_port"])
+    k = min(len(traj), len(pins["steps"]))
+    diffs["e_ccsd_max_over_steps"] = max((abs(traj[i][0] - pins["steps"][i][0]) for i in range(k)), default=0.0)
+    diffs["e_T_max_over_steps"] = max((abs(traj[i][1] - pins["steps"][i][1]) for i in range(k)), default=0.0)
+    out["steps_compared"] = k
+    out["abs_diff"] = diffs
+    out["ok"] = bool(all(d < tol for d in diffs.values()) and k > 0)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
-def run_ours(args, rank, world, local):
+def attach_comm(gpu, rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from afesp_b200 import AfespGpu
+
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.tensor(list(AfespGpu.comm_unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(uid, 0)
+    gpu.comm_init(rank, world, bytes(uid.cpu().tolist()))
+
+
+def run_shape(args, rank, world, local, n, o, steps, warmup, e2e_first=False, want_hbm=True):
+    """The hot path at one (nbf, nocc) shape: device-resident timed loop + e2e leg.  Returns the measurement dict
+    (rank 0) or None."""
     import torch
     import torch.distributed as dist
 
     from afesp_b200 import AfespGpu, synthetic
 
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n, o = args.nbf, args.nocc
     v = n - o
     big = n > 240   # host-side expansion of the packed ERIs needs npair^2 doubles: expand on the device instead
     t0 = time.perf_counter()
@@ -184,11 +297,7 @@ def run_ours(args, rank, world, local):
     log(f"[rank {rank}] synthetic inputs nbf={n} nocc={o} generated in {time.perf_counter() - t0:.1f}s")
     gpu = AfespGpu(local)
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid = torch.tensor(list(AfespGpu.comm_unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(uid, 0)
-        gpu.comm_init(rank, world, bytes(uid.cpu().tolist()))
+        attach_comm(gpu, rank, world)
 
     def barrier():
         torch.cuda.synchronize()
@@ -200,10 +309,9 @@ def run_ours(args, rank, world, local):
         gpu.set_option("gemm_use_tma", args.tma)
     tma_scope, tma_selftest = gpu.tma_status()
     peak = max(gpu.dmma_peak(), gpu.dmma_peak())
-    # ---- device-resident leg
     npair = n * (n + 1) // 2
     npk = npair * (npair + 1) // 2
-    # host copy of the packed MO integrals (input of the e2e leg): one pinned copy per node, on rank 0; the other
+    # host copy of the packed MO integrals (input of the e2e leg): pinned, one copy per node on rank 0; the other
     # ranks receive it over NVLink inside afesp_gpu_set_eri_mo
     src = None
     if rank == 0:
@@ -214,19 +322,60 @@ def run_ours(args, rank, world, local):
         gpu.ao2mo(n, want_result=False)
     else:
         gpu.ao2mo(n, eri, Cmo, want_result=False)   # also leaves AO integrals + C resident
-    gpu.ao2mo(n)                                     # resident repeat, device-timed
+        gpu.ao2mo(n)                                # resident repeat, device-timed
     ao2mo_ms = gpu.last_stage_ms()
     if rank == 0:
         gpu.get_eri_mo(src)
     gpu.release("eri_ao")
     e_mp2 = gpu.mp2_energy(o, eps)
+    h2d = int(npk * 8 + n * 8)
+    d2h = int((o * o * v * v + o * v) * 8 + 10 * 8)
+    parts = {"h2d_set_eri_mo": 0.0, "ccsd_init": 0.0, "iterate+diis": 0.0, "finalize_d2h": 0.0, "ccsd_t": 0.0}
+
+    def e2e_leg(ksteps):
+        """End to end through the C ABI with host buffers (pinned): H2D of the step's MO integrals, D2H of amplitudes."""
+        def lap(key, t_prev):
+            t = time.perf_counter()
+            parts[key] += t - t_prev
+            return t
+
+        gpu.set_option("finalize_keep_ccsd", 0)   # the product path: finalize frees the CCSD work arrays before (T)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            t = time.perf_counter()
+            gpu.set_eri_mo(n, src)
+            t = lap("h2d_set_eri_mo", t)
+            gpu.ccsd_init(o, True, eps, 8)
+            if big:
+                gpu.release("eri_mo")
+            t = lap("ccsd_init", t)
+            gpu.ccsd_iterate()
+            gpu.ccsd_diis()
+            t = lap("iterate+diis", t)
+            gpu.ccsd_finalize(want_amplitudes=True)
+            t = lap("finalize_d2h", t)
+            gpu.ccsd_t_spatial(True, False, False)
+            t = lap("ccsd_t", t)
+        barrier()
+        el = time.perf_counter() - t0
+        te = torch.tensor([el], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te.item()) / ksteps
+
+    e2e_value = None
+    if e2e_first:   # target shape: the e2e pass doubles as the warm-up of the device-timed pass
+        e2e_value = e2e_leg(1)
+        gpu.set_eri_mo(n, src)
+    # ---- device-resident leg
     gpu.set_option("finalize_keep_ccsd", 1)
     e_mp1, _ = gpu.ccsd_init(o, True, eps, 8)
     if big:
         gpu.release("eri_mo")
     comp = {"ccsd": [], "diis": [], "t": []}
     gstat = {"ccsd": [0.0, 0.0, 0], "t": [0.0, 0.0, 0]}   # DMMA GEMM (ms, flop, launches) per stage of the timed region
-    last = {}
+    traj = []
 
     def step(record):
         e, rms = gpu.ccsd_iterate()
@@ -242,11 +391,11 @@ def run_ours(args, rank, world, local):
         if record:
             ms, fl, nl = gpu.gemm_stats()
             gstat["t"][0] += ms; gstat["t"][1] += fl; gstat["t"][2] += nl
-        last.update(e_ccsd=e, rms=rms, e_T=float(sums[0]))
+        traj.append([e, float(sums[0]), rms])
         if record:
             comp["ccsd"].append(a); comp["diis"].append(b); comp["t"].append(c)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step(False)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -254,7 +403,7 @@ def run_ours(args, rank, world, local):
     gpu.set_option("gemm_timing", 1)
     gpu.timer_start()                      # CUDA events on the stream the kernels are launched on
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(True)
     dev_ms = gpu.timer_stop()
     barrier()
@@ -266,48 +415,15 @@ def run_ours(args, rank, world, local):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     elapsed, wall = float(tt[0].item()), float(tt[1].item())
-    value = elapsed / args.steps
+    value = elapsed / steps
 
-    # ---- end-to-end leg through the C ABI with host buffers (pinned): H2D of the step's MO integrals, D2H of amplitudes
-    if big:
-        gpu.set_option("finalize_keep_ccsd", 0)   # free the CCSD work arrays before (T): the next step re-initialises
-    ksteps = args.steps
-    parts = {"h2d_set_eri_mo": 0.0, "ccsd_init": 0.0, "iterate+diis": 0.0, "finalize_d2h": 0.0, "ccsd_t": 0.0}
-
-    def lap(key, t_prev):
-        t = time.perf_counter()
-        parts[key] += t - t_prev
-        return t
-
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(ksteps):
-        t = time.perf_counter()
-        gpu.set_eri_mo(n, src)
-        t = lap("h2d_set_eri_mo", t)
-        gpu.ccsd_init(o, True, eps, 8)
-        if big:
-            gpu.release("eri_mo")
-        t = lap("ccsd_init", t)
-        gpu.ccsd_iterate()
-        gpu.ccsd_diis()
-        t = lap("iterate+diis", t)
-        _, t1h, t2h = gpu.ccsd_finalize(want_amplitudes=True)
-        t = lap("finalize_d2h", t)
-        gpu.ccsd_t_spatial(True, False, False)
-        t = lap("ccsd_t", t)
-    barrier()
-    e2e_elapsed = time.perf_counter() - t0
-    te = torch.tensor([e2e_elapsed], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = float(te.item()) / ksteps
-    h2d = int(npk * 8 + n * 8)
-    d2h = int((o * o * v * v + o * v) * 8 + 10 * 8)
+    if not e2e_first:
+        e2e_value = e2e_leg(steps)
+    ksteps = 1 if e2e_first else steps
 
     # ---- HBM-bound kernels of the path (permute / denominators / energy), device resident, vs the measured copy peak
     hbm = None
-    if rank == 0:
+    if rank == 0 and want_hbm:
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
             peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)"
@@ -322,73 +438,114 @@ def run_ours(args, rank, world, local):
                         "ms": ms, "algorithmic_bytes": by, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / hbm_peak}
                 except Exception as ex:
                     hbm["kernels"][f"{what} o={oo_} v={vv_}"] = {"error": str(ex)}
-
+    out = None
     if rank == 0:
-        cpu = None
-        if world == 1 and not args.no_cpu:
-            try:
-                cpu = cpu_sample(n, o, 20.0)
-            except Exception as ex:  # the CPU leg must never take the GPU line down
-                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
-        traffic = None
+        traffic, traffic_source = None, None
         tpath = os.path.join(ROOT, "profiles", "ncu_gemm_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch", {}).get(f"nbf{n}", {}).get(
-                    "tma" if tma_scope >= 1 else "cpasync")
+                tj = json.load(open(tpath))
+                traffic = tj.get("dram_bytes_per_launch", {}).get(f"nbf{n}", {}).get("tma" if tma_scope >= 1 else "cpasync")
+                traffic_source = ("static: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of "
+                                  "this kernel at this shape, " + str(tj.get("sources", {}).get("tma" if tma_scope >= 1 else "cpasync"))
+                                  + " (not measured in this run)") if traffic else None
             except Exception:
                 traffic = None
         tot_ms = gstat["ccsd"][0] + gstat["t"][0]
         tot_fl = gstat["ccsd"][1] + gstat["t"][1]
         tf = lambda g: (g[1] / (g[0] * 1e-3) / 1e12) if g[0] > 0 else None
-        # dominant kernel: the batched (T) GEMM  C_pqr(x,(y,z)) = Acat(x,[d|l]) Bcat([d|l],(y,z)), M=v, N=v^2, K=nbf
+        # dominant kernel: the batched (T) GEMM, one launch per batch of triples: per block
+        #   Y_s(x,(u,w)) = Acat(x,[d|l]; P0,P1) Bcat([d|l],(u,w); P2) + Acat(x,[d|l]; P0,P2) BcatT([d|l],(u,w); P1)
         t_ms, t_fl, t_nl = gstat["t"]
         achieved = tf(gstat["t"])
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"synthetic integrals nbf={n} nocc={o} CCSD(T)_spatial", "nbf": n, "nocc": o,
-                       "calc_type": "CCSD(T)_spatial",
-                       "parallelism": (f"(T) ijk round-robin x{world}; CCSD GEMMs column-sharded x{world} with NCCL slab "
-                                       f"exchange, V+/- ladder integrals sharded by column block") if world > 1
-                       else "single GPU",
-                       "l2": "inputs larger than L2 (packed ladder integrals %.1f GB, (T) work buffers %.1f GB)" % (
-                           v ** 4 * 4 / 1e9, 6.0),
-                       "timing": "CUDA events on the engine's stream around the K steps, max over ranks"},
-            "wall_s_per_step": wall / args.steps,
+        out = {
+            "value": value, "ms_per_step": value * 1e3, "wall_s_per_step": wall / steps, "steps": steps, "warmup": warmup,
             "ccsd_s_per_iter": (float(np.mean(comp["ccsd"])) + float(np.mean(comp["diis"]))) / 1e3,
             "t_wall_s": float(np.mean(comp["t"])) / 1e3, "ao2mo_s": ao2mo_ms / 1e3,
-            "energies": {"e_mp2": e_mp2, "e_mp1": e_mp1, **last},
+            "energies": {"e_mp2": e_mp2, "e_mp1": e_mp1, "e_ccsd": traj[-1][0], "rms": traj[-1][2], "e_T": traj[-1][1]},
+            "trajectory": [[t[0], t[1]] for t in traj],
+            "parity": parity_block(n, o, e_mp2, e_mp1, traj),
             "gemm_tflops_executed": {"all": (tot_fl / (tot_ms * 1e-3) / 1e12) if tot_ms > 0 else None,
                                      "ccsd": tf(gstat["ccsd"]), "t": tf(gstat["t"]),
                                      "gemm_share_of_step": tot_ms * 1e-3 / elapsed if elapsed > 0 else None},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_source,
                          "kernel": ("gemm_f64_tma<N,N>" if tma_scope >= 1 else "gemm_f64_dmma<64,64,16> (cp.async ring)") +
-                                   f" batched over (ijk-permutations): (T) contraction M={v} N={v * v} K={n} per block",
+                                   f" batched over (triple, first-label permutation) blocks: (T) contraction M={v} N={v * v} "
+                                   f"K=2x{n} per block (two K segments: the permutations sharing their first label)",
                          "launches": t_nl, "flops_per_launch": (t_fl / t_nl) if t_nl else None,
                          "ms_per_launch": (t_ms / t_nl) if t_nl else None,
                          "share_of_step": t_ms * 1e-3 / elapsed if elapsed > 0 else None,
                          "all_gemms": {"achieved": (tot_fl / (tot_ms * 1e-3) / 1e12) if tot_ms > 0 else None,
-                                       "flops_per_step": tot_fl / args.steps, "ms_per_step": tot_ms / args.steps},
-                         "peak_source": "in-run register-resident DMMA.8x8x4 issue-rate probe (MEASURED_PEAKS.json has "
-                                        "no FP64 entry; vendor FP64 tensor figure 40 TFLOP/s)"},
-            "cpu_baseline": ({"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": cpu["kind"],
-                              "sample": cpu["sample"], "ccsd_s_per_iter": cpu.get("ccsd_s_per_iter"),
-                              "t_wall_s": cpu.get("t_wall_s")} if cpu else None),
+                                       "flops_per_step": tot_fl / steps, "ms_per_step": tot_ms / steps},
+                         "peak_source": "BUILDER-MEASURED: in-run register-resident DMMA.8x8x4 issue-rate probe "
+                                        "(afesp_gpu_dmma_peak); MEASURED_PEAKS.json has no FP64 entry; vendor FP64 "
+                                        "tensor figure 40 TFLOP/s"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "set_eri_mo(H2D from pinned host memory on rank 0, NVLink broadcast to the other ranks) + ccsd_init + iterate + diis + finalize(D2H t1,t2) + ccsd_t",
+                    "what": "set_eri_mo(H2D from pinned host memory) + ccsd_init + iterate + diis + finalize(D2H t1,t2) + ccsd_t"
+                            + ("; single pass that also served as warm-up of the device-timed pass" if e2e_first else ""),
                     "breakdown_s": {k: x / ksteps for k, x in parts.items()}},
-            "gpu_launches": int(l1 - l0),
-            "clocks": clocks,
-            "tma": dict(zip(("scope", "selftest"), gpu.tma_status())),
-            "hbm_kernels": hbm,
+            "gpu_launches": int(l1 - l0), "clocks": clocks,
+            "tma": {"scope": tma_scope, "selftest": tma_selftest}, "hbm_kernels": hbm,
         }
-        if world > 1:
-            line["exchange"] = "NCCL grouped broadcasts of GEMM column slabs on the compute stream"
-        emit(line)
     gpu.close()
+    return out
+
+
+def run_ours(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, o = args.nbf, args.nocc
+    v = n - o
+    m = run_shape(args, rank, world, local, n, o, args.steps, args.warmup)
+    target = None
+    if args.target and (n, o) != (400, 40):
+        try:
+            target = run_shape(args, rank, world, local, 400, 40, 1, 0, e2e_first=True, want_hbm=False)
+            if target is not None:
+                for k in ("hbm_kernels", "trajectory"):
+                    target.pop(k, None)
+                target["config"] = config_of(400, 40)
+                target["note"] = ("BASELINE.json configs[4], the north-star target shape: one e2e pass (which is also the "
+                                  "warm-up), then ONE device-timed step (W=0 after that pass, K=1)")
+        except Exception as ex:   # the target leg must never take the headline line down
+            target = {"error": f"{type(ex).__name__}: {ex}"}
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            try:
+                ref = CpuReference(n, o)
+                ref.sample(10.0)                      # calibration / cache warm-up
+                smp = ref.sample(30.0)
+                ao = ref.ao2mo(4.0)
+                cpu = {"value": smp["value"], "unit": UNIT, "cores": ref.threads, "kind": "port", "sample": ref.describe(smp),
+                       "ccsd_s_per_iter": smp["ccsd_s_per_iter"], "t_wall_s": smp["t_wall_s"],
+                       "ao2mo_s": ao["ao2mo_s"] if ao else None, "parts": smp["parts"]}
+            except Exception as ex:  # the CPU leg must never take the GPU line down
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+        line = {
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(n, o),
+            "parallelism": (f"(T) ijk round-robin x{world}; CCSD GEMMs column-sharded x{world} with NCCL slab exchange, "
+                            f"V+/- ladder integrals sharded by column block") if world > 1 else "single GPU",
+            "l2": "inputs larger than L2 (packed ladder integrals %.1f GB, (T) work buffers %.1f GB)" % (v ** 4 * 4 / 1e9, 6.0),
+            "timing": "CUDA events on the engine's stream around the K steps, max over ranks",
+        }
+        for k in ("wall_s_per_step", "ccsd_s_per_iter", "t_wall_s", "ao2mo_s", "energies", "parity", "gemm_tflops_executed",
+                  "roofline", "e2e", "gpu_launches", "clocks", "tma", "hbm_kernels"):
+            line[k] = m[k]
+        line["cpu_baseline"] = cpu
+        line["target_config"] = target
+        if args.trajectory:
+            line["trajectory"] = m["trajectory"]
+        if world > 1:
+            line["exchange"] = "NCCL slab exchange of the column-sharded CCSD GEMMs; one allreduce of the six (T) sums"
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -402,12 +559,21 @@ def main():
     ap.add_argument("--nbf", type=int, default=200)
     ap.add_argument("--nocc", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--tma", type=int, default=-1, help="gemm_use_tma: -1 library default (1: TMA-staged kernel for the "
-                                                        "(T) batches), 0 cp.async kernels only, 2 TMA for every aligned GEMM")
+    ap.add_argument("--target", type=int, default=int(os.environ.get("AFESP_BENCH_TARGET", "1")),
+                    help="1 (default): also run the nbf=400/nocc=40 target shape once and attach it as target_config")
+    ap.add_argument("--trajectory", action="store_true", help="print the per-step (E_CCSD, e_T) list (pinning runs)")
+    ap.add_argument("--tma", type=int, default=-1, help="gemm_use_tma: -1 library default (2: TMA-staged kernel for every "
+                                                        "aligned GEMM), 1 the (T) batches only, 0 cp.async kernels only")
+    ap.add_argument("--workload", default=None, help="sample_data molecule run: n2 | f2 | h2o | h2o-spinorb")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload:
+        from tools import bench_samples
+
+        bench_samples.run(args, rank, world, local, emit, log)
+        return
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -534,6 +534,21 @@ int main(int argc, char** argv) {
 
   if (s.level >= 1) {
     if (afesp_gpu_open(device, &g_h) != 0) fail("afesp_gpu::afesp_gpu_open", afesp_gpu_last_error(nullptr));
+    // Library switches (parity switches Q1-Q3, thresholds; include/afesp_gpu.h) from the environment, the way a Fortran
+    // host would pass them on: AFESP_GPU_OPTIONS="key=value,key=value"
+    if (const char* env = std::getenv("AFESP_GPU_OPTIONS")) {
+      std::string all(env);
+      size_t pos = 0;
+      while (pos < all.size()) {
+        size_t end = all.find(',', pos);
+        if (end == std::string::npos) end = all.size();
+        const std::string kv = all.substr(pos, end - pos);
+        const size_t eq = kv.find('=');
+        if (eq != std::string::npos)
+          check("set_option", afesp_gpu_set_option(g_h, kv.substr(0, eq).c_str(), std::atof(kv.substr(eq + 1).c_str())));
+        pos = end + 1;
+      }
+    }
     // coeff(mo,ao) column-major as the Fortran host holds canon_coeff: element (mo,ao) at mo + n*ao
     std::vector<double> coeff_f((size_t)n * n);
     for (int mo = 0; mo < n; ++mo)
@@ -561,12 +576,25 @@ int main(int argc, char** argv) {
     std::printf(" ----------\n CCSD\n ----------\n");
     auto ti = Clock::now();
     double e = 0.0, rms = 0.0;
-    check("ccsd_init", afesp_gpu_ccsd_init(g_h, nocc, s.restricted ? 1 : 0, scf.eps.data(), s.ccsd_diis_n_errmat, &e, &rms));
+    const int rc_init = afesp_gpu_ccsd_init(g_h, nocc, s.restricted ? 1 : 0, scf.eps.data(), s.ccsd_diis_n_errmat, &e, &rms);
     if (!s.restricted) {
-      std::printf(" Forming antisymmetrised spinorbital ERIs...\n Time taken: %8.6f s\n\n", since(ti));
-      std::printf(" Checking that the permuational symmetry of the antisymmetrised integrals hold...\n Time taken: %8.6f s\n\n", 0.0);
+      // src/ccsd.f90:106-202.  The (2n)^4 tensor is never formed: the nine slices are gathered straight from the packed MO
+      // integrals (first timer) and the reference's symmetry assertion runs on the device over the same index set (second
+      // timer); nothing is left for the third banner.  Status 5 = the assertion fired (:161-164).
+      double info[4] = {0, 0, 0, 0};
+      if (rc_init == 0 || rc_init == 5) check("ccsd_init_info", afesp_gpu_ccsd_init_info(g_h, info));
+      if (rc_init == 5) {
+        std::printf(" Forming antisymmetrised spinorbital ERIs...\n Time taken: %8.6f s\n\n", info[1]);
+        std::printf(" Checking that the permuational symmetry of the antisymmetrised integrals hold...\n");
+        std::printf(" Permutational symmetry error: %15.6E\n", info[0]);
+        fail("ccsd::do_ccsd", "Permutational symmetry of antisymmetrised integrals does not hold");
+      }
+      check("ccsd_init", rc_init);
+      std::printf(" Forming antisymmetrised spinorbital ERIs...\n Time taken: %8.6f s\n\n", info[1]);
+      std::printf(" Checking that the permuational symmetry of the antisymmetrised integrals hold...\n Time taken: %8.6f s\n\n", info[2]);
       std::printf(" Forming slices of antisymmetrised spinorbital ERIs\n Time taken: %8.6f s\n\n", 0.0);
     }
+    check("ccsd_init", rc_init);
     std::printf(" Initialise CC intermediate tensors and DIIS auxilliary arrays...\n Forming energy denominator matrices...\n"
                 " Allocating amplitude tensors...\n");
     if (s.restricted) std::printf(" Forming ERI slices...\n");

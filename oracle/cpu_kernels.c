@@ -113,4 +113,72 @@ void afesp_ref_triples(int o, int v, const double* t1, const double* t2, const d
   afesp_ref_triples_bounded(o, v, t1, t2, t2r, vvovv, vovoo, voovv, eps, ntri, ijk, doing_T, doing_R, v, out);
 }
 
+
+/* Completely renormalised variant (doing_CR, src/ccsd.f90:2188-2193, 2222-2226): the M3 array from the CR intermediates
+ * I_vovv_pp(v,o,v,v), I_ooov_pp(o,o,o,v), with the reference's strided sums.  out[0..5] = e_T, e_TT, D_T, D_TT, e_CR, e_CRT. */
+#define IVOVV(d, k, b, c) I_vovv_pp[(d) + v * ((k) + (size_t)o * ((b) + (size_t)v * (c)))]
+#define IOOOV(j, k, l, c) I_ooov_pp[(j) + o * ((k) + (size_t)o * ((l) + (size_t)o * (c)))]
+static inline double dots(const double* x, size_t sx, const double* y, size_t sy, int n) {
+  double s = 0.0;
+  for (int q = 0; q < n; ++q) s += x[q * sx] * y[q * sy];
+  return s;
+}
+void afesp_ref_triples_cr(int o, int v, const double* t1, const double* t2, const double* t2r, const double* vvovv,
+                          const double* vovoo, const double* voovv, const double* I_vovv_pp, const double* I_ooov_pp,
+                          const double* eps, int ntri, const int* ijk, int doing_T, double* out) {
+  double e_T = 0.0, e_TT = 0.0, D_T = 0.0, D_TT = 0.0, e_CR = 0.0, e_CRT = 0.0;
+  const size_t v3 = (size_t)v * v * v, se = (size_t)o * o * v /* stride of the last index of t2 */, so2 = (size_t)o * o;
+#pragma omp parallel reduction(+ : e_T, e_TT, D_T, D_TT, e_CR, e_CRT)
+  {
+    double* w = (double*)calloc(v3, sizeof(double));
+    double* t3 = (double*)calloc(v3, sizeof(double));
+    double* tb = (double*)malloc(v3 * sizeof(double));
+    double* z3 = (double*)calloc(v3, sizeof(double));
+    double* zb = (double*)calloc(v3, sizeof(double));
+    double* y = (double*)calloc(v3, sizeof(double));
+    double* m3 = (double*)calloc(v3, sizeof(double));
+#pragma omp for schedule(static, 10)
+    for (int t = 0; t < ntri; ++t) {
+      const int i = ijk[3 * t], j = ijk[3 * t + 1], k = ijk[3 * t + 2];
+      for (int a = 0; a < v; ++a)
+        for (int b = 0; b < v; ++b)
+          for (int c = 0; c < v; ++c) {
+            double x = dotv(&T2R(0, a, j, i), &VVOVV(0, k, b, c), v) - dotv(&T2(0, i, b, a), &VOVOO(0, c, j, k), o) +
+                       dotv(&T2R(0, b, i, j), &VVOVV(0, k, a, c), v) - dotv(&T2(0, j, a, b), &VOVOO(0, c, i, k), o) +
+                       dotv(&T2R(0, c, j, k), &VVOVV(0, i, b, a), v) - dotv(&T2(0, k, b, c), &VOVOO(0, a, j, i), o) +
+                       dotv(&T2R(0, a, k, i), &VVOVV(0, j, c, b), v) - dotv(&T2(0, i, c, a), &VOVOO(0, b, k, j), o) +
+                       dotv(&T2R(0, b, k, j), &VVOVV(0, i, c, a), v) - dotv(&T2(0, j, c, b), &VOVOO(0, a, k, i), o) +
+                       dotv(&T2R(0, c, i, k), &VVOVV(0, j, a, b), v) - dotv(&T2(0, k, a, c), &VOVOO(0, b, i, j), o);
+            const double d = eps[i] + eps[j] + eps[k] - eps[a + o] - eps[b + o] - eps[c + o];
+            X3(w, a, b, c) = x;
+            X3(t3, a, b, c) = x / d;
+            if (doing_T)
+              X3(z3, a, b, c) = (T1(i, a) * VOOVV(j, k, b, c) + T1(j, b) * VOOVV(i, k, a, c) + T1(k, c) * VOOVV(i, j, a, b)) / d;
+            X3(y, a, b, c) = T1(i, a) * T1(j, b) * T1(k, c) + T1(i, a) * T2(j, k, b, c) + T1(j, b) * T2(i, k, a, c) +
+                             T1(k, c) * T2(i, j, a, b);
+            X3(m3, a, b, c) =
+                dots(&T2(i, j, a, 0), se, &IVOVV(0, k, b, c), 1, v) - dots(&T2(0, i, b, a), 1, &IOOOV(j, k, 0, c), so2, o) +
+                dots(&T2(j, i, b, 0), se, &IVOVV(0, k, a, c), 1, v) - dots(&T2(0, j, a, b), 1, &IOOOV(i, k, 0, c), so2, o) +
+                dots(&T2(k, j, c, 0), se, &IVOVV(0, i, b, a), 1, v) - dots(&T2(0, k, b, c), 1, &IOOOV(j, i, 0, a), so2, o) +
+                dots(&T2(i, k, a, 0), se, &IVOVV(0, j, c, b), 1, v) - dots(&T2(0, i, c, a), 1, &IOOOV(k, j, 0, b), so2, o) +
+                dots(&T2(j, k, b, 0), se, &IVOVV(0, i, c, a), 1, v) - dots(&T2(0, j, c, b), 1, &IOOOV(k, i, 0, a), so2, o) +
+                dots(&T2(k, i, c, 0), se, &IVOVV(0, j, a, b), 1, v) - dots(&T2(0, k, a, c), 1, &IOOOV(i, j, 0, b), so2, o);
+          }
+      make_x_bar(v, t3, tb);
+      if (doing_T) make_x_bar(v, z3, zb);
+      double tmp = dotv(tb, w, (int)v3);
+      e_T += tmp;
+      if (doing_T) e_TT += tmp + dotv(zb, w, (int)v3);
+      tmp = dotv(tb, m3, (int)v3);
+      e_CR += tmp;
+      if (doing_T) e_CRT += tmp + dotv(zb, m3, (int)v3);
+      tmp = dotv(tb, y, (int)v3);
+      D_T += tmp;
+      if (doing_T) D_TT += tmp + dotv(zb, y, (int)v3);
+    }
+    free(w); free(t3); free(tb); free(z3); free(zb); free(y); free(m3);
+  }
+  out[0] = e_T; out[1] = e_TT; out[2] = D_T; out[3] = D_TT; out[4] = e_CR; out[5] = e_CRT;
+}
+
 int afesp_ref_threads(void) { return omp_get_max_threads(); }

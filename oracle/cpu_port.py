@@ -90,6 +90,8 @@ def load():
                                               [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, _dp])
     lib.afesp_ref_triples_bounded.restype = None
     lib.afesp_ref_threads.restype = C.c_int
+    lib.afesp_ref_triples_cr.argtypes = ([C.c_int, C.c_int] + [_dp] * 9 + [C.c_int, C.POINTER(C.c_int), C.c_int, _dp])
+    lib.afesp_ref_triples_cr.restype = None
     return lib
 
 
@@ -126,6 +128,23 @@ def triples(lib, t1, t2, v_oovv, v_vvov, v_oovo, eps, ijk, paren, renorm, amax=N
     lib.afesp_ref_triples_bounded(o, v, _p(a1), _p(a2), _p(t2r), _p(vvovv), _p(vovoo), _p(a3), _p(e), tri.shape[0],
                                   tri.ctypes.data_as(C.POINTER(C.c_int)), int(paren), int(renorm),
                                   v if amax is None else int(amax), _p(out))
+    return out, time.perf_counter() - t0
+
+
+def triples_cr(lib, t1, t2, v_oovv, v_vvov, v_oovo, I_vovv_pp, I_ooov_pp, eps, ijk, paren):
+    """(e_T, e_TT, D_T, D_TT, e_CR, e_CRT) over the listed ordered triples with the completely renormalised part
+    (src/ccsd.f90:2152-2233 with doing_CR); returns (sums[6], seconds)."""
+    o, v = t1.shape
+    t2r = _F(t2.transpose(3, 2, 1, 0))
+    vvovv = _F(v_vvov.transpose(3, 2, 1, 0))
+    vovoo = _F(v_oovo.transpose(3, 2, 1, 0))
+    a1, a2, a3, a4, a5 = _F(t1), _F(t2), _F(v_oovv), _F(I_vovv_pp), _F(I_ooov_pp)
+    e = np.ascontiguousarray(eps, dtype=np.float64)
+    tri = np.ascontiguousarray(np.asarray(ijk, dtype=np.int32).reshape(-1, 3))
+    out = np.zeros(6)
+    t0 = time.perf_counter()
+    lib.afesp_ref_triples_cr(o, v, _p(a1), _p(a2), _p(t2r), _p(vvovv), _p(vovoo), _p(a3), _p(a4), _p(a5), _p(e),
+                             tri.shape[0], tri.ctypes.data_as(C.POINTER(C.c_int)), int(paren), _p(out))
     return out, time.perf_counter() - t0
 
 

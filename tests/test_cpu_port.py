@@ -53,3 +53,18 @@ def test_cpu_port_full_ccsd_iteration_and_ao2mo_match_numpy_oracle():
     # the integral slices are antisymmetrised / restored in place inside the call (as in the reference, to rounding)
     g1b, g2b, _, _ = cpu_port.ccsd_iter(lib, Vc, eps, t1, t2)
     assert np.max(np.abs(g1 - g1b)) < 1e-15 and np.max(np.abs(g2 - g2b)) < 1e-15
+
+
+def test_cpu_port_cr_triples_match_numpy_oracle():
+    n, o = 12, 3
+    eri, Cm, eps = synthetic.make(n, o, seed=5)
+    mo = orc.ao2mo_packed(eri, Cm)
+    cc = orc.ccsd_spatial(mo, eps, o, 1e-9, 1e-10, 8, 50, want_cr=True)
+    V = cc["V"]
+    lib = cpu_port.load()
+    ijk = [(i, j, k) for i in range(o) for j in range(o) for k in range(o)]
+    sums, _ = cpu_port.triples_cr(lib, cc["t1"], cc["t2"], V["v_oovv"], V["v_vvov"], V["v_oovo"], cc["I_vovv_pp"],
+                                  cc["I_ooov_pp"], eps, ijk, True)
+    ref = orc.triples_spatial_sums(cc["t1"], cc["t2"], V["v_oovv"], V["v_vvov"], V["v_oovo"], eps, True, False, True,
+                                   cc["I_vovv_pp"], cc["I_ooov_pp"])
+    assert np.max(np.abs(sums - np.array(ref))) < 1e-13

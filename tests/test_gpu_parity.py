@@ -3,6 +3,8 @@
 Tolerances (BASELINE.json north_star): energies within 1e-9 Eh, converged amplitudes within 1e-8, identical
 iteration counts.  Index permutations are bit-exact; GEMMs are compared at 1e-12 relative to the operand scale.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -290,6 +292,47 @@ def test_spinorbital_ccsd_t_as_coded_matches_oracle(gpu, oracle_runs):
         assert abs(e - oe) < E_TOL and abs(rms - orms) < 1e-9
     assert abs(res.e_ccsd - (-0.311554581875)) < E_TOL
     assert abs(res.energies["e_ccsd_t"] - r["e_ccsd_t"]) < E_TOL
+
+
+def test_spinorbital_symmetry_assertion_runs_and_aborts(gpu, tmp_path):
+    """src/ccsd.f90:150-167: the permutational-symmetry self-check of <pq||rs> is executed on the device (error and its
+    device time come back through afesp_gpu_ccsd_init_info, the host prints them); above the threshold the calculation
+    stops with the reference's message.  The packed 8-fold storage cannot hold a symmetry-breaking integral, so the abort
+    path is driven through the threshold (depsilon, src/const.F90:19) instead of a corrupted input."""
+    import subprocess
+
+    from afesp_b200 import host
+    from afesp_b200.capi import AfespError
+    from tests._fixtures import els_host_binary, write_sample_dir
+
+    inp = load_els_input("h2o", "CCSD_spinorb")
+    res = host.run(inp, gpu=gpu)
+    info = gpu.ccsd_init_info()
+    assert info["symmetry_error"] == 0.0 and info["check_s"] > 0.0 and info["slices_s"] > 0.0
+    lines = res.stdout.splitlines()
+    k = lines.index(" Checking that the permuational symmetry of the antisymmetrised integrals hold...")
+    assert abs(float(lines[k + 1].split()[2]) - info["check_s"]) < 1e-6 and float(lines[k + 1].split()[2]) > 0.0
+    # oracle: the same four identities over the full index range
+    sysm = load_system("h2o", "CCSD_spinorb")
+    orc.do_rhf(sysm)
+    asym = orc.spinorb_antisym(orc.ao2mo_packed(sysm.eri, sysm.coeff), sysm.nbasis)
+    assert orc.spinorb_symmetry_error(asym) == 0.0
+    gpu.set_option("spinorb_symmetry_tol", -1.0)
+    try:
+        with pytest.raises(AfespError) as ei:
+            host.run(inp, gpu=gpu)
+    finally:
+        gpu.set_option("spinorb_symmetry_tol", 1e-12)
+    assert ei.value.code == 5 and "Permutational symmetry of antisymmetrised integrals does not hold" in str(ei.value)
+    assert " Permutational symmetry error:" in ei.value.stdout and "Initialisation done" not in ei.value.stdout
+    # the C++ host: error block of src/error_handling.f90 naming ccsd::do_ccsd, non-zero stop, nothing after the check
+    write_sample_dir("h2o", str(tmp_path), calc_type="CCSD_spinorb")
+    env = dict(os.environ, AFESP_GPU_OPTIONS="spinorb_symmetry_tol=-1")
+    r = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode != 0 and "ccsd::do_ccsd" in r.stderr and "does not hold" in r.stderr
+    assert " Permutational symmetry error:" in r.stdout and "Initialisation done" not in r.stdout
+    r = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "Initialisation done" in r.stdout
 
 
 # ---------------------------------------------------------------- (T) sharding and symmetry properties

@@ -53,3 +53,26 @@ def test_fragment_loads_are_bank_conflict_free_in_both_layouts():
 def test_the_natural_k_grouping_would_conflict():
     natural = lambda s, t: 4 * s + t
     assert max(_half_warp_conflicts(False, natural), _half_warp_conflicts(True, natural)) >= 2
+
+
+def test_fused_triples_epilogue_box_swizzles_are_conflict_free():
+    """afesp_b200/csrc/triples.cu `swz`: each staged 8x8x8 box is written at the thread's natural position and read back
+    at the position permuted by w; in its own XOR-swizzled layout both accesses of every half-warp (tx = 0..7, two
+    consecutive ty, fixed tz) touch 16 distinct 8-byte banks, and the layout is a bijection onto the 512-word box."""
+    perms = [(0, 1, 2), (1, 0, 2), (2, 1, 0), (0, 2, 1), (1, 2, 0), (2, 0, 1)]   # c_perm of triples.cu
+    swz = {1: lambda X, Y, Z: 64 * Z + 8 * Y + (X ^ Y),
+           2: lambda X, Y, Z: 64 * Z + 8 * Y + (X ^ Z),
+           3: lambda X, Y, Z: 64 * Z + 8 * (Y ^ (Z & 1)) + X,
+           4: lambda X, Y, Z: 64 * Z + 8 * (Y ^ (X & 1)) + (X ^ Z),
+           5: lambda X, Y, Z: 64 * Z + 8 * (Y ^ (Z & 1)) + (X ^ Y)}
+    for w, f in swz.items():
+        assert sorted(f(x, y, z) for x in range(8) for y in range(8) for z in range(8)) == list(range(512))
+        p = perms[w]
+        for tz in range(8):
+            for t0 in range(0, 8, 2):
+                half = [(tx, ty, tz) for ty in (t0, t0 + 1) for tx in range(8)]
+                assert len({f(*l) % 16 for l in half}) == 16, ("write", w)
+                assert len({f(l[p[0]], l[p[1]], l[p[2]]) % 16 for l in half}) == 16, ("read", w)
+    # the padded 9x9x8 box of the previous version conflicted 2-way on every access, natural ones included
+    old = lambda X, Y, Z: (Z * 9 + Y) * 9 + X
+    assert len({old(tx, ty, 0) % 16 for ty in (0, 1) for tx in range(8)}) == 15
