@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 #include <functional>
+#include <set>
 
 #include "../../include/afesp_gpu.h"
 #include "ccsd.cuh"
@@ -85,6 +86,9 @@ struct Handle {
 };
 
 std::string g_open_error;
+// One handle per device and process: the caching allocator and the GEMM workspace are per device and rely on
+// stream-ordered reuse, i.e. on a single stream per device.
+std::set<int>& g_open_devices = *new std::set<int>;
 
 // Cached free blocks go back to the driver only when they add up to a sizeable part of the HBM (large shapes, where
 // the next stage needs the room); small runs keep them so repeated init/finalize cycles never touch cudaMalloc.
@@ -167,6 +171,11 @@ int afesp_gpu_open(int device, afesp_handle* out) {
                    std::to_string(prop.major) + "." + std::to_string(prop.minor);
     return 2;
   }
+  if (g_open_devices.count(device)) {
+    g_open_error = "afesp_gpu_open: device " + std::to_string(device) + " already has an open handle in this process (one "
+                   "handle per device: close it first)";
+    return 1;
+  }
   Handle* h = new Handle();
   h->device = device;
   if (cudaStreamCreate(&h->s.eng.stream) != cudaSuccess || cudaEventCreate(&h->ev0) != cudaSuccess ||
@@ -181,13 +190,16 @@ int afesp_gpu_open(int device, afesp_handle* out) {
       gemm_tma_selftest(h->s.eng.stream);
     } catch (const std::exception& e) {
       g_open_error = std::string("afesp_gpu_open: TMA self-test could not run: ") + e.what();
-      cudaStreamDestroy(h->s.eng.stream);
+      cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+      cudaStream_t st = h->s.eng.stream;
       delete h;
+      cudaStreamDestroy(st);
       return 2;
     }
   }
   h->launches0 = g_launch_count;
   h->flops0 = g_gemm_flops;
+  g_open_devices.insert(device);
   *out = h;
   return 0;
 }
@@ -210,6 +222,7 @@ int afesp_gpu_close(afesp_handle hv) {
   if (h->tm0) cudaEventDestroy(h->tm0);
   if (h->tm1) cudaEventDestroy(h->tm1);
   cudaStream_t st = h->s.eng.stream;
+  g_open_devices.erase(h->device);
   delete h;
   if (st) cudaStreamDestroy(st);
   device_trim();
@@ -243,7 +256,12 @@ int afesp_gpu_set_option(afesp_handle hv, const char* key, double value) {
       gemm_tma_scope((int)value);
     }
     else if (k == "dist_min_flops") h.s.eng.dist.min_flops = value;   // GEMMs below this stay replicated
-    else if (k == "dist_ccsd") h.s.eng.dist.enabled = value != 0.0;       // 0: replicate CCSD / AO->MO, shard only (T)
+    else if (k == "dist_ccsd") {   // 0: replicate CCSD / AO->MO, shard only (T)
+      AFESP_REQUIRE(!(h.s.vpm_sharded && !h.s.finalized && value == 0.0),
+                    "set_option: dist_ccsd cannot be switched off while the ladder integrals of the current CCSD state are "
+                    "sharded (call afesp_gpu_ccsd_init again afterwards)");
+      h.s.eng.dist.enabled = value != 0.0;
+    }
     else throw Error(1, "set_option: unknown key " + k);
   });
 }
@@ -414,6 +432,7 @@ int afesp_gpu_ccsd_iterate(afesp_handle hv, double* e_cc, double* rmst2) {
 int afesp_gpu_ccsd_diis(afesp_handle hv) {
   return guarded(hv, [&](Handle& h) {
     assemble_finalize_checks(h);
+    AFESP_REQUIRE(!h.s.finalized, "ccsd_diis: state already finalised");
     StageTimer tm(&h);
     cc_diis_update(h.s);
     tm.stop();
@@ -434,7 +453,9 @@ int afesp_gpu_ccsd_finalize(afesp_handle hv, int want_cr, double* t1_diag, doubl
       ccsd_spatial_cr_intermediates(s);
     }
     // release what the (T) stage does not need (the reference's cc_int goes out of scope, src/ccsd.f90:386-392)
-    if (s.opt.finalize_keep_ccsd) {
+    if (s.opt.finalize_keep_ccsd && !(want_cr && s.have_cr)) {
+      // benchmark loops: keep the DIIS history and the intermediates so that ccsd_iterate can be called again.  (Not after
+      // the CR intermediates were built: that step consumes V+/-, I_oooo, ... -- the state is then finalised as usual.)
       tm.stop();
       if (t1) AFESP_CUDA_CHECK(cudaMemcpy(t1, s.t1.p(), s.t1.size() * 8, cudaMemcpyDeviceToHost));
       if (t2) AFESP_CUDA_CHECK(cudaMemcpy(t2, s.t2.p(), s.t2.size() * 8, cudaMemcpyDeviceToHost));

@@ -14,7 +14,7 @@ namespace afesp {
 // CC-DIIS ring (src/ccsd.f90:46-67, 577-676): stores the un-extrapolated amplitudes T_i and e_i = T_i - T'_{i-1}.
 struct CCDiis {
   int nerr = 8;
-  bool use = true;
+  bool use = false;   // set by init(); a default-constructed ring (after finalize) must not be extrapolated
   int slot = 0, n_active = 0;
   std::vector<Tensor> t1, t2, e1, e2;
   Tensor t1_s, t2_s;

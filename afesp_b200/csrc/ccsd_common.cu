@@ -6,6 +6,7 @@
 namespace afesp {
 
 void CCDiis::init(int nerr_, int o, int v) {
+  AFESP_REQUIRE(nerr_ <= 8, "CC-DIIS: at most 8 error vectors are supported (ccsd_diis_n_errmat <= 8)");
   nerr = nerr_;
   use = nerr >= 2;  // src/ccsd.f90:593-595
   slot = 0; n_active = 0;

@@ -104,6 +104,7 @@ extern double g_gemm_flops;
 // the live roofline figure.  gemm_timing_collect() synchronises and returns the accumulated milliseconds.
 void gemm_timing_enable(bool on);
 void gemm_force_config(int cfg);  // tuning aid: -1 = automatic tile selection
+int gemm_force_config_get();
 // TMA-staged operand path: scope 0 = off, 1 = gathered batches only (the (T) contraction; default), 2 = every aligned
 // problem the 64x64 tile is chosen for.  See DESIGN.md section 4.1.
 void gemm_tma_scope(int scope);

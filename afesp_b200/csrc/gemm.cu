@@ -288,8 +288,14 @@ __global__ void scale_c(double* C, int M, int N, long long ldc, double beta) {
   }
 }
 
-int g_num_sms = 0;
-DBuf g_ws;  // split-K workspace, grown on demand
+constexpr int kMaxDev = 64;
+int g_num_sms[kMaxDev] = {0};   // per device ordinal
+inline int current_device() {
+  int dev = 0;
+  AFESP_CUDA_CHECK(cudaGetDevice(&dev));
+  AFESP_REQUIRE(dev >= 0 && dev < kMaxDev, "gemm: device ordinal out of range");
+  return dev;
+}
 
 // per-launch event timing (off by default)
 bool g_timing = false;
@@ -319,12 +325,9 @@ std::pair<cudaEvent_t, cudaEvent_t>* next_events() {
 }
 
 int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    AFESP_CUDA_CHECK(cudaGetDevice(&dev));
-    AFESP_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  return g_num_sms;
+  const int dev = current_device();
+  if (!g_num_sms[dev]) AFESP_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev));
+  return g_num_sms[dev];
 }
 
 template <int BM, int BN, int BK, int WM, int WN, int STAGES, int MINB, bool AK, bool BKM, int VEC>
@@ -332,10 +335,11 @@ void launch_cfg(cudaStream_t st, const Params& p, int nbatch) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   constexpr size_t SMEM = (size_t)STAGES * (Tile<BM, BK, AK>::SIZE + Tile<BN, BK, BKM>::SIZE) * sizeof(double);
   auto kern = gemm_f64_dmma<BM, BN, BK, WM, WN, STAGES, MINB, AK, BKM, VEC>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDev] = {false};   // the attribute is per device
+  const int dev = current_device();
+  if (!attr_set[dev]) {
     AFESP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   Params q = p;
   q.tiles_m = (p.M + BM - 1) / BM;
@@ -479,9 +483,9 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
       int splits = (K + kchunk - 1) / kchunk;
       if (splits > 1) {
         p.splitk = splits; p.kchunk = kchunk;
-        size_t need = (size_t)splits * M * N;
-        if (g_ws.n < need) g_ws.alloc(need);
-        p.ws = g_ws.p;
+        // workspace from the per-device caching allocator; released after the reduce kernel is queued (reuse is
+        // stream-ordered: one stream per device)
+        p.ws = device_alloc((size_t)splits * M * N);
       }
     }
   }
@@ -550,12 +554,14 @@ void dgemm(cudaStream_t st, char transA, char transB, int M, int N, int K, doubl
     splitk_reduce<<<(int)std::min<long long>((MN + 255) / 256, 2048), 256, 0, st>>>(p.ws, p.splitk, M, N, alpha,
                                                                                    beta, C, ldc);
     count_launch();
+    device_free(p.ws);
     AFESP_CUDA_CHECK(cudaGetLastError());
   }
   if (evs) cudaEventRecord(evs->second, st);
 }
 
 void gemm_force_config(int cfg) { g_force_cfg = cfg; }
+int gemm_force_config_get() { return g_force_cfg; }
 
 void gemm_timing_enable(bool on) {
   if (on && !g_timing) { g_timed_ms = 0.0; g_timed_flops = 0.0; g_timed_launches = 0; g_ev_used = 0; }

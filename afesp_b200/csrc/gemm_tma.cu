@@ -110,8 +110,7 @@ struct TmaParams {
   const int* Aidx2;  // dual batches: block indices of the second K segment (B blocks through the second B map)
   const int* Bidx2;
   int nk_seg;        // k-tiles per segment of a dual batch (0: single segment)
-  int edge_balance;  // 1: the last M tile shares its valid row fragments evenly over the four consumer warps
-  int ktail;         // 1: the last k-tile of a segment holds <= 8 valid k -> two DMMA groups instead of four
+  int m_tile0;       // first m-tile of this launch (the ragged last m-tile of a problem is launched separately)
   int M, N, K, tiles_m;
   int nbatch;        // > 0: batch-fastest rasterisation on a 1-D grid (see the kernel); 0: batch = blockIdx.z
   double alpha, beta;
@@ -119,7 +118,7 @@ struct TmaParams {
 };
 
 // Consumer side of one CTA tile: main loop over the k-tiles of the ring + epilogue, for a warp that owns NI x NJ 8x8
-// fragments at rows rb + 8 i, columns cb + 8 j of the tile (PRED: only the first fi row fragments exist).
+// fragments at rows rb + 8 i, columns cb + 8 j of the tile.
 //
 // Slot release.  The first version released slot s right after the DMMAs of its k-tile: `__syncwarp(); if (lane == 0)
 // arrive(empty[s])`.  The SASS showed why that produced sporadic wrong 32-byte sectors: the fragment loads were
@@ -130,13 +129,13 @@ struct TmaParams {
 // (barrier count NCONS*32), and (iii) the release of k-tile kt-1 is issued only after the wait for k-tile kt: by then
 // the DMMAs of kt-1 have been issued, which requires all of this lane's fragment loads of kt-1 to have returned.
 //
-// K tail.  When the last k-tile of a segment holds at most 8 valid k (the rest is TMA zero fill) only two DMMA groups
-// are issued for it, on the k-sets {0,3,4,7} {1,2,5,6} (conflict-free in the MN-major layout, 2-way in the K-major one:
-// one tile per segment).
-template <bool AK, bool BKM, int NI, int NJ, bool PRED>
+// K tail (KTAIL, chosen on the host).  When the last k-tile of a segment holds at most 8 valid k (the rest is TMA zero
+// fill) that tile is peeled out of the loop and only two DMMA groups are issued for it, on the k-sets {0,3,4,7}
+// {1,2,5,6} (conflict-free in the MN-major layout, 2-way in the K-major one: one tile per segment).
+template <bool AK, bool BKM, int NI, int NJ, bool KTAIL>
 __device__ __forceinline__ void consume(const TmaParams& p, unsigned char* smem, unsigned long long* full,
-                                        unsigned long long* empty, int nk, int nk1, int rb, int cb, int fi, int m0,
-                                        int n0, int batch, int lane) {
+                                        unsigned long long* empty, int nk, int nk1, int rb, int cb, int m0, int n0,
+                                        int batch, int lane) {
   const int gid = lane >> 2, tig = lane & 3;
   double acc[NI * NJ][2];
 #pragma unroll
@@ -152,44 +151,49 @@ __device__ __forceinline__ void consume(const TmaParams& p, unsigned char* smem,
     for (int j = 0; j < NJ; ++j) boff[s][j] = tile_off<BKM>(cb + 8 * j + gid, k);
   }
   const unsigned smem_s = smem_u32(smem);
-  for (int kt = 0; kt < nk; ++kt) {
+  auto tile4 = [&](int kt) {
     const int s = kt % STAGES;
     mbar_wait(&full[s], (kt / STAGES) & 1);
     if (kt > 0) mbar_arrive(&empty[(kt - 1) % STAGES]);
     const unsigned sa = smem_s + s * STAGE_BYTES, sb = sa + TILE_BYTES;
-    if (p.ktail && (kt == nk1 - 1 || kt == nk - 1)) {
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const int k = (tig >> 1) * 4 + (g ? 1 + (tig & 1) : 3 * (tig & 1));
-        double af[NI], bf[NJ];
-#pragma unroll
-        for (int i = 0; i < NI; ++i)
-          if (!PRED || i < fi) af[i] = lds_f64(sa + tile_off<AK>(rb + 8 * i + gid, k));
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) bf[j] = lds_f64(sb + tile_off<BKM>(cb + 8 * j + gid, k));
-#pragma unroll
-        for (int i = 0; i < NI; ++i)
-          if (!PRED || i < fi) {
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) dmma884(acc[i * NJ + j][0], acc[i * NJ + j][1], af[i], bf[j]);
-          }
-      }
-      continue;
-    }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       double af[NI], bf[NJ];
 #pragma unroll
-      for (int i = 0; i < NI; ++i)
-        if (!PRED || i < fi) af[i] = lds_f64(sa + aoff[g][i]);
+      for (int i = 0; i < NI; ++i) af[i] = lds_f64(sa + aoff[g][i]);
 #pragma unroll
       for (int j = 0; j < NJ; ++j) bf[j] = lds_f64(sb + boff[g][j]);
 #pragma unroll
       for (int i = 0; i < NI; ++i)
-        if (!PRED || i < fi) {
 #pragma unroll
-          for (int j = 0; j < NJ; ++j) dmma884(acc[i * NJ + j][0], acc[i * NJ + j][1], af[i], bf[j]);
-        }
+        for (int j = 0; j < NJ; ++j) dmma884(acc[i * NJ + j][0], acc[i * NJ + j][1], af[i], bf[j]);
+    }
+  };
+  auto tile2 = [&](int kt) {
+    const int s = kt % STAGES;
+    mbar_wait(&full[s], (kt / STAGES) & 1);
+    if (kt > 0) mbar_arrive(&empty[(kt - 1) % STAGES]);
+    const unsigned sa = smem_s + s * STAGE_BYTES, sb = sa + TILE_BYTES;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int k = (tig >> 1) * 4 + (g ? 1 + (tig & 1) : 3 * (tig & 1));
+      double af[NI], bf[NJ];
+#pragma unroll
+      for (int i = 0; i < NI; ++i) af[i] = lds_f64(sa + tile_off<AK>(rb + 8 * i + gid, k));
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) bf[j] = lds_f64(sb + tile_off<BKM>(cb + 8 * j + gid, k));
+#pragma unroll
+      for (int i = 0; i < NI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) dmma884(acc[i * NJ + j][0], acc[i * NJ + j][1], af[i], bf[j]);
+    }
+  };
+  if (!KTAIL) {
+    for (int kt = 0; kt < nk; ++kt) tile4(kt);
+  } else {
+    for (int kt0 = 0; kt0 < nk; kt0 += nk1) {
+      for (int kt = kt0; kt < kt0 + nk1 - 1; ++kt) tile4(kt);
+      tile2(kt0 + nk1 - 1);
     }
   }
   // (the last k-tile's slot needs no release: nothing is loaded after it)
@@ -201,7 +205,6 @@ __device__ __forceinline__ void consume(const TmaParams& p, unsigned char* smem,
     const bool odd = gid & 1;
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
-      if (PRED && i >= fi) break;
       const int m = m0 + rb + 8 * i + (gid & ~1);
       double2 oldv[NJ];
       if (beta != 0.0) {
@@ -236,7 +239,6 @@ __device__ __forceinline__ void consume(const TmaParams& p, unsigned char* smem,
   }
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
-    if (PRED && i >= fi) break;
     const int m = m0 + rb + 8 * i + gid;
     if (m >= p.M) continue;
 #pragma unroll
@@ -255,7 +257,13 @@ __device__ __forceinline__ void consume(const TmaParams& p, unsigned char* smem,
   }
 }
 
-template <bool AK, bool BKM>
+// EDGE = false: interior kernel, each consumer warp owns a 32x32 sub-tile (4x4 fragments); launched over the m-tiles
+// that are complete (or over all of them when the edge handling is off).
+// EDGE = true: the LAST m-tile of a problem whose M is not a multiple of 64, launched separately.  Padding rows would
+// waste up to 7/8 of that tile's DMMAs, so the four warps share its f = ceil(rows/8) valid row fragments evenly: each
+// takes ALL of them times 16 columns (f x 2 fragments; one fully unrolled body per f) -- exactly ceil(M/8) row fragments
+// are multiplied and the work stays balanced over the SM's four tensor pipes.
+template <bool AK, bool BKM, bool EDGE, bool KTAIL>
 __global__ void __launch_bounds__(NT, 3) gemm_f64_tma(const __grid_constant__ CUtensorMap tmA,
                                                        const __grid_constant__ CUtensorMap tmB,
                                                        const __grid_constant__ CUtensorMap tmB2, const TmaParams p) {
@@ -274,10 +282,10 @@ __global__ void __launch_bounds__(NT, 3) gemm_f64_tma(const __grid_constant__ CU
     const unsigned per_n = (unsigned)p.tiles_m * (unsigned)p.nbatch;
     const unsigned nt = blockIdx.x / per_n, rem = blockIdx.x - nt * per_n;
     batch = (int)(rem / (unsigned)p.tiles_m);
-    m0 = (int)(rem - (unsigned)batch * p.tiles_m) * BM;
+    m0 = ((int)(rem - (unsigned)batch * p.tiles_m) + p.m_tile0) * BM;
     n0 = (int)nt * BN;
   } else {
-    m0 = (blockIdx.x % p.tiles_m) * BM; n0 = (blockIdx.x / p.tiles_m) * BN;
+    m0 = ((int)(blockIdx.x % p.tiles_m) + p.m_tile0) * BM; n0 = (blockIdx.x / p.tiles_m) * BN;
     batch = blockIdx.z;
   }
   const int nk1 = (p.K + BK - 1) / BK;
@@ -315,16 +323,20 @@ __global__ void __launch_bounds__(NT, 3) gemm_f64_tma(const __grid_constant__ CU
     return;
   }
   // ---------------- consumer warps ----------------
-  // Interior tiles: each warp owns a 32x32 sub-tile (4x4 fragments).  The last M tile of a problem whose M is not a
-  // multiple of 64 would waste up to 7/8 of its DMMAs on padding rows; there the four warps instead share the
-  // f = ceil(rows/8) valid row fragments evenly: each takes ALL of them times 16 columns (f x 2 fragments), so exactly
-  // ceil(M/8) row fragments are multiplied and the work stays balanced over the SM's four tensor pipes.
-  const int mrem = p.M - m0;
-  const int fi = (mrem + 7) >> 3;
-  if (p.edge_balance && fi < 8)
-    consume<AK, BKM, 8, 2, true>(p, smem, full, empty, nk, nk1, 0, warp * 16, fi, m0, n0, batch, lane);
-  else
-    consume<AK, BKM, 4, 4, false>(p, smem, full, empty, nk, nk1, (warp & 1) * 32, (warp >> 1) * 32, 4, m0, n0, batch, lane);
+  if (!EDGE) {
+    consume<AK, BKM, 4, 4, KTAIL>(p, smem, full, empty, nk, nk1, (warp & 1) * 32, (warp >> 1) * 32, m0, n0, batch, lane);
+  } else {
+    const int fi = (p.M - m0 + 7) >> 3;   // 1..7 valid row fragments (CTA-uniform)
+    switch (fi) {
+      case 1: consume<AK, BKM, 1, 2, KTAIL>(p, smem, full, empty, nk, nk1, 0, warp * 16, m0, n0, batch, lane); break;
+      case 2: consume<AK, BKM, 2, 2, KTAIL>(p, smem, full, empty, nk, nk1, 0, warp * 16, m0, n0, batch, lane); break;
+      case 3: consume<AK, BKM, 3, 2, KTAIL>(p, smem, full, empty, nk, nk1, 0, warp * 16, m0, n0, batch, lane); break;
+      case 4: consume<AK, BKM, 4, 2, KTAIL>(p, smem, full, empty, nk, nk1, 0, warp * 16, m0, n0, batch, lane); break;
+      case 5: consume<AK, BKM, 5, 2, KTAIL>(p, smem, full, empty, nk, nk1, 0, warp * 16, m0, n0, batch, lane); break;
+      case 6: consume<AK, BKM, 6, 2, KTAIL>(p, smem, full, empty, nk, nk1, 0, warp * 16, m0, n0, batch, lane); break;
+      default: consume<AK, BKM, 7, 2, KTAIL>(p, smem, full, empty, nk, nk1, 0, warp * 16, m0, n0, batch, lane); break;
+    }
+  }
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -374,6 +386,21 @@ bool make_map(CUtensorMap* map, bool kmajor, const double* base, long long MN, l
   return r == CUDA_SUCCESS;
 }
 
+// side stream (per device) for the edge-tile launch of a GEMM, forked from / joined to the caller's stream with events
+struct SideStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+SideStream& side_stream() {
+  static SideStream ss[64];
+  int dev = 0;
+  AFESP_CUDA_CHECK(cudaGetDevice(&dev));
+  SideStream& s = ss[(dev >= 0 && dev < 64) ? dev : 0];
+  if (!s.st) {
+    AFESP_CUDA_CHECK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    AFESP_CUDA_CHECK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    AFESP_CUDA_CHECK(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+  }
+  return s;
+}
+
 int g_tma_edge = 1;    // edge handling of gemm_f64_tma (balanced last M tile, short K tail); 0 = pad everything (A/B tests)
 int g_tma_scope = 2;   // 0 = off, 1 = gathered (T) batches only, 2 (default since the round-2 soak, profiles/r02_tma_soak_*.json) = every aligned 64x64-tile problem
 
@@ -399,15 +426,22 @@ __global__ void k_selftest_cmp(const double* a, const double* b, long long n, do
     if (fabs(a[i] - b[i]) > tol) ++c;
   if (c) atomicAdd(bad, c);
 }
-int g_selftest_state = 0;   // 0 not run, 1 passed, -1 failed (TMA switched off)
+int g_selftest_state_dev[64] = {0};   // per device ordinal: 0 not run, 1 passed, -1 failed (TMA off on that device)
+int& selftest_state() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return g_selftest_state_dev[(dev >= 0 && dev < 64) ? dev : 0];
+}
 }  // namespace
 
-int gemm_tma_selftest_state() { return g_selftest_state; }
+int gemm_tma_selftest_state() { return selftest_state(); }
 
-// Runs once per process (first handle).  Returns true when the TMA kernel reproduced the cp.async kernel on every case.
+// Runs once per device (first handle on it).  Returns true when the TMA kernel reproduced the cp.async kernel on every case.
 bool gemm_tma_selftest(cudaStream_t st) {
+  int& g_selftest_state = selftest_state();
   if (g_selftest_state != 0) return g_selftest_state > 0;
   if (std::getenv("AFESP_TMA_SELFTEST") && std::atoi(std::getenv("AFESP_TMA_SELFTEST")) == 0) { g_selftest_state = 1; return true; }
+  const int force0 = gemm_force_config_get();
   struct Case { int M, N, K, batch, reps; double beta; };
   const Case cases[] = {{64, 4096, 72, 48, 12, 0.0},      // (T)-shaped batch at v = 64, nbf = 72: K tail, 5 k-tiles
                         {144, 13456, 144, 1, 4, 1.0},     // I_oooo . c with accumulate, edge M tile
@@ -440,11 +474,11 @@ bool gemm_tma_selftest(cudaStream_t st) {
     }
     AFESP_CUDA_CHECK(cudaMemcpy(&total_bad, cnt.p, 8, cudaMemcpyDeviceToHost));
   } catch (...) {
-    gemm_force_config(-1);
+    gemm_force_config(force0);
     g_tma_scope = scope0;
     throw;
   }
-  gemm_force_config(-1);
+  gemm_force_config(force0);
   g_tma_scope = scope0;
   g_selftest_state = total_bad == 0 ? 1 : -1;
   if (total_bad != 0) g_tma_scope = 0;
@@ -460,7 +494,7 @@ void gemm_crosscheck(cudaStream_t st, char ta, char tb, int M, int N, int K, int
   const bool tA = (ta == 'T' || ta == 't'), tB = (tb == 'T' || tb == 't');
   const long long lda = tA ? K : M, ldb = tB ? N : K;
   const size_t na = (size_t)M * K * nbatch, nb = (size_t)K * N * nbatch, nc = (size_t)M * N * nbatch;
-  const int scope0 = g_tma_scope;
+  const int scope0 = g_tma_scope, force0 = gemm_force_config_get();
   DBuf cnt(1), A(na + 16), B(nb + 16), C0(nc), C1(nc), C2(nc);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   AFESP_CUDA_CHECK(cudaEventCreate(&e0));
@@ -495,18 +529,18 @@ void gemm_crosscheck(cudaStream_t st, char ta, char tb, int M, int N, int K, int
     AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
     AFESP_CUDA_CHECK(cudaMemcpy(bad, cnt.p, 8, cudaMemcpyDeviceToHost));
   } catch (...) {
-    gemm_force_config(-1);
+    gemm_force_config(force0);
     g_tma_scope = scope0;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     throw;
   }
-  gemm_force_config(-1);
+  gemm_force_config(force0);
   g_tma_scope = scope0;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
 }
 
 void gemm_tma_edge(int on) { g_tma_edge = on; }
-void gemm_tma_scope(int scope) { g_tma_scope = (g_selftest_state < 0) ? 0 : scope; }
+void gemm_tma_scope(int scope) { g_tma_scope = (selftest_state() < 0) ? 0 : scope; }
 int gemm_tma_scope_get() { return g_tma_scope; }
 
 // Returns false when the TMA path does not apply (the caller then runs the cp.async kernel).
@@ -547,32 +581,59 @@ bool dgemm_tma(cudaStream_t st, bool ak, bool bk, int M, int N, int K, double al
   }
   TmaParams p{};
   if (dual) { p.Aidx2 = batch->Aidx2; p.Bidx2 = batch->Bidx2; p.nk_seg = (K + BK - 1) / BK; }
-  p.edge_balance = g_tma_edge ? 1 : 0;
-  p.ktail = (g_tma_edge && (K % BK) >= 1 && (K % BK) <= 8) ? 1 : 0;
   p.C = C; p.Cp = batch ? batch->Cptr : nullptr; p.sC = batch ? batch->strideC : 0; p.ldc = ldc;
   p.Aidx = Aidx; p.Bidx = Bidx; p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.cvec = cvec;
-  p.tiles_m = (M + BM - 1) / BM;
-  const long long tiles = (long long)p.tiles_m * ((N + BN - 1) / BN);
-  if (tiles >= (1LL << 31) || nbatch > 65535) return false;
+  const bool ktail = g_tma_edge && (K % BK) >= 1 && (K % BK) <= 8;
+  const int tiles_m_all = (M + BM - 1) / BM;
+  const int fi_last = (M - (tiles_m_all - 1) * BM + 7) / 8;              // valid row fragments of the last m-tile
+  const bool edge = g_tma_edge && fi_last < 8;
+  const long long tiles_n = (N + BN - 1) / BN;
+  if ((long long)tiles_m_all * tiles_n >= (1LL << 31) || nbatch > 65535) return false;
   constexpr size_t SMEM = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;
-  dim3 grid((unsigned)tiles, 1, nbatch);
-  p.nbatch = 0;
-  if (nbatch > 1 && tiles * nbatch < (1LL << 31)) {
-    p.nbatch = nbatch;
-    grid = dim3((unsigned)(tiles * nbatch), 1, 1);
+  auto launch = [&](auto kern, int m_tile0, int tiles_m) {
+    if (tiles_m <= 0) return;
+    TmaParams q = p;
+    q.m_tile0 = m_tile0; q.tiles_m = tiles_m;
+    const long long tiles = (long long)tiles_m * tiles_n;
+    dim3 grid((unsigned)tiles, 1, nbatch);
+    q.nbatch = 0;
+    if (nbatch > 1 && tiles * nbatch < (1LL << 31)) {
+      q.nbatch = nbatch;
+      grid = dim3((unsigned)(tiles * nbatch), 1, 1);
+    }
+    // raise the dynamic shared-memory limit of this instantiation on the current device (idempotent, cheap)
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    kern<<<grid, NT, SMEM, st>>>(tmA, tmB, tmB2, q);
+    count_launch();
+  };
+  auto launch_kind = [&](auto edge_tag, int m_tile0, int tiles_m) {
+    constexpr bool E = decltype(edge_tag)::value;
+    if (ktail) {
+      if (ak) { if (bk) launch(gemm_f64_tma<true, true, E, true>, m_tile0, tiles_m); else launch(gemm_f64_tma<true, false, E, true>, m_tile0, tiles_m); }
+      else    { if (bk) launch(gemm_f64_tma<false, true, E, true>, m_tile0, tiles_m); else launch(gemm_f64_tma<false, false, E, true>, m_tile0, tiles_m); }
+    } else {
+      if (ak) { if (bk) launch(gemm_f64_tma<true, true, E, false>, m_tile0, tiles_m); else launch(gemm_f64_tma<true, false, E, false>, m_tile0, tiles_m); }
+      else    { if (bk) launch(gemm_f64_tma<false, true, E, false>, m_tile0, tiles_m); else launch(gemm_f64_tma<false, false, E, false>, m_tile0, tiles_m); }
+    }
+  };
+  if (edge && tiles_m_all > 1) {
+    // the ragged last m-tile (rows shared evenly by the warps) runs on a side stream, concurrently with the complete
+    // m-tiles: the two launches write disjoint rows of C and read the same operand tiles
+    SideStream& ss = side_stream();
+    cudaStream_t main_st = st;
+    AFESP_CUDA_CHECK(cudaEventRecord(ss.fork, main_st));
+    AFESP_CUDA_CHECK(cudaStreamWaitEvent(ss.st, ss.fork, 0));
+    st = ss.st;
+    launch_kind(std::true_type{}, tiles_m_all - 1, 1);
+    AFESP_CUDA_CHECK(cudaEventRecord(ss.join, ss.st));
+    st = main_st;
+    launch_kind(std::false_type{}, 0, tiles_m_all - 1);
+    AFESP_CUDA_CHECK(cudaStreamWaitEvent(main_st, ss.join, 0));
+  } else if (edge) {
+    launch_kind(std::true_type{}, 0, 1);
+  } else {
+    launch_kind(std::false_type{}, 0, tiles_m_all);
   }
-  // all four instantiations share one function-pointer type: raise their dynamic shared-memory limit together, once
-  static std::once_flag once;
-  std::call_once(once, [&] {
-    cudaFuncSetAttribute(gemm_f64_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-    cudaFuncSetAttribute(gemm_f64_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-    cudaFuncSetAttribute(gemm_f64_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-    cudaFuncSetAttribute(gemm_f64_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-  });
-  auto launch = [&](auto kern) { kern<<<grid, NT, SMEM, st>>>(tmA, tmB, tmB2, p); };
-  if (ak) { if (bk) launch(gemm_f64_tma<true, true>); else launch(gemm_f64_tma<true, false>); }
-  else    { if (bk) launch(gemm_f64_tma<false, true>); else launch(gemm_f64_tma<false, false>); }
-  count_launch();
   AFESP_CUDA_CHECK(cudaGetLastError());
   return true;
 }

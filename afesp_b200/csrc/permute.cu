@@ -264,7 +264,8 @@ void permute_strided(cudaStream_t st, int rank, const int* dims, const int* perm
   for (int d = 0; d < rank; ++d) {
     int a = perm[d];
     if (dims[a] == 1) continue;
-    if (r > 0 && istr[r - 1] * odims[r - 1] == istr_full[a] && ostr_d[r - 1] * odims[r - 1] == ostr_full[d]) {
+    if (r > 0 && istr[r - 1] * odims[r - 1] == istr_full[a] && ostr_d[r - 1] * odims[r - 1] == ostr_full[d] &&
+        (long long)odims[r - 1] * dims[a] < (1LL << 31)) {   // merged extents stay 32-bit: larger arrays keep two axes
       odims[r - 1] *= dims[a];
     } else {
       odims[r] = dims[a];

@@ -58,119 +58,20 @@ def config_of(nbf, nocc):
             "calc_type": "CCSD(T)_spatial"}
 
 
-def host_cores():
-    try:
-        return len(os.sched_getaffinity(0))
-    except AttributeError:
-        return os.cpu_count() or 1
-
-
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-class CpuReference:
-    """The reference's CPU path at shape (nbf, nocc) on every host core this process may use, whatever
-    OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1): OpenMP loops and OpenBLAS dgemms both.
-
-    Inputs are the same synthetic system the GPU arm runs (MO integrals from the factored form, MP1 amplitudes).  One
-    sample = (a) ONE COMPLETE spin-free CCSD iteration as src/ccsd.f90:1040-1312 + 1538-1732 issues it -- every dgemm
-    (ladder included) and every reshape in full; the two naive o^3v^3 loop nests (:1170-1182, :1680-1695) in full when
-    the time budget allows, else on a slab of their outermost index (>= 1/8), scaled linearly and stated; (b) the
-    reference (T) loop (:2152-2233) on one COMPLETE ordered triple per thread, scaled by o^3 / triples; (c) the AO->MO
-    quarter transforms (src/mp2.f90:321-387) on a slab of the outermost index (reported as ao2mo_s, not part of `value`,
-    which is CCSD iteration + (T) like the GPU arm's)."""
-
-    def __init__(self, nbf, nocc):
-        from oracle import cpu_port
-
-        self.cp = cpu_port
-        self.lib = cpu_port.load()
-        self.threads = cpu_port.set_threads(self.lib, host_cores())
-        self.n, self.o, self.v = nbf, nocc, nbf - nocc
-        n, o, v = self.n, self.o, self.v
-        t0 = time.perf_counter()
-        self.mo, self.Cmo, self.eps = cpu_port.synthetic_mo_integrals(n, o)
-        try:
-            avail = int([ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0].split()[1]) * 1024
-        except Exception:
-            avail = 32 << 30
-        dense = 8 * v ** 4
-        self.ncol_d = v if dense <= min(12 << 30, avail // 4) else max(1, int((4 << 30) // (8 * v ** 3)))
-        self.V = cpu_port.slices(self.lib, self.mo, n, o, vvvv_cols=(0, self.ncol_d))
-        eo, ev = self.eps[:o], self.eps[o:]
-        D2 = eo[:, None, None, None] + eo[None, :, None, None] - ev[None, None, :, None] - ev[None, None, None, :]
-        self.t2 = np.asfortranarray(self.V["v_oovv"] / D2)
-        self.t1 = np.zeros((o, v), order="F")
-        rng = np.random.default_rng(7)
-        self.triples = [tuple(int(x) for x in rng.integers(0, o, 3)) for _ in range(self.threads)]
-        self.frac = 1.0 / 8.0      # slab fraction of the two naive loop nests; raised after the first (calibration) sample
-        self.setup_s = time.perf_counter() - t0
-        self.eri_ao = None
-
-    def sample(self, budget_s):
-        cp, lib, n, o, v = self.cp, self.lib, self.n, self.o, self.v
-        # (b) (T): one complete ordered triple per thread
-        t0 = time.perf_counter()
-        _, dt_t = cp.triples(lib, self.t1, self.t2, self.V["v_oovv"], self.V["v_vvov"], self.V["v_oovo"], self.eps,
-                             self.triples, True, False)
-        t_T = dt_t * (o ** 3) / len(self.triples)
-        # (a) complete CCSD iteration; slab fraction from what is left of the budget
-        left = max(0.0, budget_s - (time.perf_counter() - t0))
-        if hasattr(self, "_naive_full_s"):
-            self.frac = float(min(1.0, max(1.0 / 8.0, (left - self._rest_s) / max(self._naive_full_s, 1e-9))))
-        bmax = max(1, min(v, int(round(self.frac * v))))
-        amax = bmax
-        _, _, parts, wall = cp.ccsd_iter(lib, self.V, self.eps, self.t1, self.t2, ring_bmax=bmax, iovov_amax=amax)
-        parts = [float(x) for x in parts]
-        ladder = parts[4] * v / self.ncol_d
-        iovov, ring = parts[1] * v / amax, parts[5] * v / bmax
-        rest = parts[0] + parts[2] + parts[3] + parts[6] + parts[7]
-        self._naive_full_s, self._rest_s = iovov + ring, rest + parts[4]
-        t_iter = rest + ladder + iovov + ring
-        return {"ccsd_s_per_iter": t_iter, "t_wall_s": t_T, "value": t_iter + t_T,
-                "parts": {"ladder_dgemm": ladder, "ring_loop": ring, "I_ovov_loop": iovov, "other": rest,
-                          "triples_sample_s": dt_t, "ccsd_sample_s": wall},
-                "slab": {"ring_b": [bmax, v], "iovov_a": [amax, v], "ladder_cols": [self.ncol_d * v, v * v],
-                         "triples": [len(self.triples), o ** 3]}}
-
-    def ao2mo(self, budget_s=6.0):
-        """AO->MO of src/mp2.f90:321-387 on an l-slab sized for ~budget_s, scaled by n / slab."""
-        from afesp_b200 import synthetic
-
-        n = self.n
-        if self.eri_ao is None:
-            if n > 240:
-                return None   # the packed AO integrals alone are 25.7 GB at nbf=400; not sampled
-            self.eri_ao, _, _ = synthetic.make(n, self.o)
-        _, t1 = self.cp.ao2mo(self.lib, self.eri_ao, self.Cmo, lmax=1, smax=1, want_result=False)
-        per_l = float(np.sum(t1[:4]))
-        lmax = int(max(1, min(n, budget_s / max(per_l, 1e-6))))
-        _, t = self.cp.ao2mo(self.lib, self.eri_ao, self.Cmo, lmax=lmax, smax=lmax, want_result=False)
-        return {"ao2mo_s": float(np.sum(t[:4])) * n / lmax, "slab": [lmax, n], "sample_s": float(np.sum(t[:4]))}
-
-    def describe(self, s):
-        sl = s["slab"]
-        f = lambda a: "in full" if a[0] >= a[1] else f"on {a[0]} of {a[1]} (x{a[1] / a[0]:.2f})"
-        return (f"one complete spin-free CCSD iteration as src/ccsd.f90:1040-1312,1538-1732 issues it (all dgemms and "
-                f"reshapes in full; ladder dgemm :1669 columns {f(sl['ladder_cols'])}; ring loop nest :1680-1695 outer index "
-                f"{f(sl['ring_b'])}; I_ovov loop nest :1170-1182 outer index {f(sl['iovov_a'])}) = "
-                f"{s['ccsd_s_per_iter']:.2f} s/iter [{s['parts']['ccsd_sample_s']:.1f} s measured] + reference (T) loop "
-                f":2152-2233 on {sl['triples'][0]} complete ordered triples (one per thread) of {sl['triples'][1]} "
-                f"(x{sl['triples'][1] / sl['triples'][0]:.0f}) = {s['t_wall_s']:.0f} s [{s['parts']['triples_sample_s']:.1f} s measured]")
-
-
 def run_reference(args, rank):
+    """The reference's CPU path (oracle/cpu_reference.py, a subprocess with its own thread environment: every host core
+    for the OpenMP loops and the OpenBLAS dgemms).  One sample per step; see CpuReference for what a sample is."""
     if rank != 0:
         return
-    ref = CpuReference(args.nbf, args.nocc)
-    log(f"[reference] {ref.threads} threads, inputs in {ref.setup_s:.1f}s, OpenBLAS {ref.lib._blas_path}")
+    from oracle import cpu_reference
+
     total = args.warmup + args.steps
     budget = max(8.0, min(60.0, 300.0 / max(1, total)))    # CPU seconds per sample: the whole run ends within minutes
-    vals, samples = [], []
-    for s in range(total):
-        smp = ref.sample(budget)
-        if s >= args.warmup:
-            vals.append(smp["value"]); samples.append(smp)
-        log(f"[reference] sample {s}: value {smp['value']:.1f}s (ccsd {smp['ccsd_s_per_iter']:.2f}, T {smp['t_wall_s']:.0f}) slab {smp['slab']}")
-    ao = ref.ao2mo()
+    res = cpu_reference.run_subprocess(args.nbf, args.nocc, total, budget)
+    samples = res["samples"][args.warmup:]
+    vals = [s["value"] for s in samples]
+    ao = res["ao2mo"]
     v = float(np.mean(vals))
     last = samples[-1]
     line = {
@@ -183,9 +84,9 @@ def run_reference(args, rank):
         "samples": {"n": len(vals), "min": float(np.min(vals)), "median": float(np.median(vals)), "max": float(np.max(vals)),
                     "cpu_seconds_per_sample": last["parts"]["ccsd_sample_s"] + last["parts"]["triples_sample_s"]},
         "parts_last_sample": last["parts"],
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": ref.threads, "kind": "port", "sample": ref.describe(last)},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": res["threads"], "kind": "port", "sample": last["describe"]},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "thread_env": res["env"],
         "note": "value is the full-workload time each bounded sample extrapolates to (factors in cpu_baseline.sample); "
                 "the timed region itself is samples.cpu_seconds_per_sample per step",
     }
@@ -250,17 +151,21 @@ def parity_block(n, o, e_mp2, e_mp1, traj):
         return {"pinned": False, "note": f"no pinned values for nbf={n} nocc={o} in tests/golden/bench_pinned.json"}
     tol = 1e-9
     out = {"pinned": True, "tolerance_Eh": tol, "source": pins.get("source")}
-    diffs = {"e_mp2": abs(e_mp2 - pins["e_mp2"]), "e_mp1": abs(e_mp1 - pins["e_mp1"])}
+    diffs = {}
+    if "e_mp2" in pins:
+        diffs.update({"e_mp2": abs(e_mp2 - pins["e_mp2"]), "e_mp1": abs(e_mp1 - pins["e_mp1"])})
     if "e_mp2_oracle" in pins:
         diffs["e_mp2_vs_cpu_oracle"] = abs(e_mp2 - pins["e_mp2_oracle"])
     if "e_ccsd_iter1_cpu_port" in pins and traj:
         diffs["e_ccsd_iter1_vs_cpu_port"] = abs(traj[0][0] - pins["e_ccsd_iter1_cpu_port"])
-    k = min(len(traj), len(pins["steps"]))
-    diffs["e_ccsd_max_over_steps"] = max((abs(traj[i][0] - pins["steps"][i][0]) for i in range(k)), default=0.0)
-    diffs["e_T_max_over_steps"] = max((abs(traj[i][1] - pins["steps"][i][1]) for i in range(k)), default=0.0)
+    steps = pins.get("steps", [])
+    k = min(len(traj), len(steps))
+    if k:
+        diffs["e_ccsd_max_over_steps"] = max(abs(traj[i][0] - steps[i][0]) for i in range(k))
+        diffs["e_T_max_over_steps"] = max(abs(traj[i][1] - steps[i][1]) for i in range(k))
     out["steps_compared"] = k
     out["abs_diff"] = diffs
-    out["ok"] = bool(all(d < tol for d in diffs.values()) and k > 0)
+    out["ok"] = bool(diffs and all(d < tol for d in diffs.values()))
     return out
 
 
@@ -507,8 +412,9 @@ def run_ours(args, rank, world, local):
         try:
             target = run_shape(args, rank, world, local, 400, 40, 1, 0, e2e_first=True, want_hbm=False)
             if target is not None:
-                for k in ("hbm_kernels", "trajectory"):
-                    target.pop(k, None)
+                target.pop("hbm_kernels", None)
+                if not args.trajectory:
+                    target.pop("trajectory", None)
                 target["config"] = config_of(400, 40)
                 target["note"] = ("BASELINE.json configs[4], the north-star target shape: one e2e pass (which is also the "
                                   "warm-up), then ONE device-timed step (W=0 after that pass, K=1)")
@@ -518,11 +424,11 @@ def run_ours(args, rank, world, local):
         cpu = None
         if world == 1 and not args.no_cpu:
             try:
-                ref = CpuReference(n, o)
-                ref.sample(10.0)                      # calibration / cache warm-up
-                smp = ref.sample(30.0)
-                ao = ref.ao2mo(4.0)
-                cpu = {"value": smp["value"], "unit": UNIT, "cores": ref.threads, "kind": "port", "sample": ref.describe(smp),
+                from oracle import cpu_reference
+
+                res = cpu_reference.run_subprocess(n, o, 2, 25.0, ao2mo_budget=4.0)   # first sample calibrates the slabs
+                smp, ao = res["samples"][-1], res["ao2mo"]
+                cpu = {"value": smp["value"], "unit": UNIT, "cores": res["threads"], "kind": "port", "sample": smp["describe"],
                        "ccsd_s_per_iter": smp["ccsd_s_per_iter"], "t_wall_s": smp["t_wall_s"],
                        "ao2mo_s": ao["ao2mo_s"] if ao else None, "parts": smp["parts"]}
             except Exception as ex:  # the CPU leg must never take the GPU line down

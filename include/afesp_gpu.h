@@ -16,6 +16,9 @@
  *   - the library prints nothing: the host program keeps every line of els.out.
  *   - one handle = one CUDA device; all state between calls (integrals, amplitudes, intermediates, DIIS history)
  *     stays on that device.  Calls on one handle must not overlap (the caller is single-threaded, main.F90).
+ *     At most ONE open handle per device and process (a second afesp_gpu_open on the same device fails until the first
+ *     is closed); handles on different devices of one process are independent.  The kernel-selection and measurement
+ *     options ("gemm_use_tma", "gemm_force_config", "gemm_tma_edge", "gemm_timing") are process-wide.
  *   - there is no CPU fallback: without a usable CUDA device afesp_gpu_open fails.
  *
  * Packed two-electron integrals use the reference's 8-fold canonical order (src/integrals.f90:196-210):
@@ -44,11 +47,14 @@ const char* afesp_gpu_last_error(afesp_handle h); /* h may be NULL: error of the
  *   "finalize_keep_ccsd"       afesp_gpu_ccsd_finalize keeps the DIIS history and intermediates (benchmark loops)
  *   "gemm_timing"              bracket every DMMA GEMM launch with CUDA events (see afesp_gpu_gemm_time)
  * Kernel selection:
- *   "gemm_use_tma"             0 = cp.async kernels only; 1 (default) = the TMA-staged kernel for the gathered (T)
- *                              batches; 2 = also for every other aligned GEMM the 64x64 tile is chosen for.  With a
+ *   "gemm_use_tma"             0 = cp.async kernels only; 1 = the TMA-staged kernel for the gathered (T) batches only;
+ *                              2 (default) = also for every other aligned GEMM the 64x64 tile is chosen for.  With a
  *                              value > 0 a consistency check against the cp.async kernel runs once per process
  *                              (at afesp_gpu_open / when switched on); if it fails the path is off (afesp_gpu_tma_status)
  *   "gemm_force_config"        tile menu entry (tuning aid), -1 = automatic
+ *   "gemm_tma_edge"            1 (default): the TMA kernel multiplies only ceil(M/8) row fragments (ragged last m-tile shared
+ *                              evenly by the warps) and two instead of four DMMA groups for a K tail of <= 8; 0: pad (A/B tests)
+ *   "spinorb_symmetry_tol"     abort threshold of the spin-orbital symmetry self-check (default 1e-12, see ccsd_init_info)
  *   "dist_ccsd", "dist_min_flops"   see the multi-GPU section below */
 int afesp_gpu_set_option(afesp_handle h, const char* key, double value);
 /* State of the TMA-staged GEMM path: *scope = value of "gemm_use_tma" in force; *selftest = 1 when the start-up

@@ -393,3 +393,42 @@ def test_synthetic_chain_matches_oracle_and_device_generated_integrals(gpu):
     got = host.assemble_triples(e, sums, const, True, False, True)
     for k in ["e_ccsd_t", "e_ccsd_tt", "e_rccsd_t", "e_rccsd_tt", "e_crccsd_t", "e_crccsd_tt", "D_T", "D_TT"]:
         assert abs(got[k] - en[k]) < E_TOL, k
+
+
+# ---------------------------------------------------------------- handle / state guards
+def test_handle_and_state_guards(gpu):
+    """One handle per device and process; DIIS is refused on a finalised state and with more than 8 error vectors
+    (status codes, not crashes)."""
+    from afesp_b200 import AfespGpu, synthetic
+    from afesp_b200.capi import AfespError
+
+    with pytest.raises(AfespError) as ei:
+        AfespGpu(0)
+    assert "already has an open handle" in str(ei.value)
+    n, o = 12, 2
+    eri, Cm, eps = synthetic.make(n, o, seed=2)
+    gpu.ao2mo(n, eri, Cm, want_result=False)
+    with pytest.raises(AfespError) as ei:
+        gpu.ccsd_init(o, True, eps, 9)
+    assert "at most 8 error vectors" in str(ei.value)
+    gpu.ccsd_init(o, True, eps, 8)
+    gpu.ccsd_iterate()
+    gpu.ccsd_diis()
+    gpu.ccsd_finalize()
+    with pytest.raises(AfespError) as ei:
+        gpu.ccsd_diis()
+    assert ei.value.code == 1 and "finalised" in str(ei.value)
+    with pytest.raises(AfespError):
+        gpu.ccsd_iterate()
+    # finalize_keep_ccsd (benchmark loops) keeps iterating possible -- unless the CR intermediates consumed the work arrays
+    gpu.set_option("finalize_keep_ccsd", 1)
+    try:
+        gpu.ccsd_init(o, True, eps, 8)
+        gpu.ccsd_iterate(); gpu.ccsd_diis(); gpu.ccsd_finalize()
+        gpu.ccsd_iterate(); gpu.ccsd_diis()
+        gpu.ccsd_finalize(want_cr=True)
+        with pytest.raises(AfespError) as ei:
+            gpu.ccsd_iterate()
+        assert "finalised" in str(ei.value)
+    finally:
+        gpu.set_option("finalize_keep_ccsd", 0)
