@@ -218,10 +218,15 @@ class AfespGpu:
     def ccsd_diis(self):
         self._check("ccsd_diis", self.lib.afesp_gpu_ccsd_diis(self.h))
 
-    def ccsd_finalize(self, want_cr=False, want_amplitudes=False):
+    def ccsd_finalize(self, want_cr=False, want_amplitudes=False, out=None):
+        """out = (t1_buffer, t2_buffer): caller-provided flat float64 arrays (e.g. pinned host memory) for the amplitudes."""
         d = C.c_double(0)
         t1 = t2 = None
-        if want_amplitudes:
+        if out is not None:
+            t1, t2 = out
+            want_amplitudes = True
+            assert t1.size == self.o * self.v and t2.size == self.o * self.o * self.v * self.v
+        elif want_amplitudes:
             t1 = np.empty(self.o * self.v)
             t2 = np.empty(self.o * self.o * self.v * self.v)
         self._check("ccsd_finalize", self.lib.afesp_gpu_ccsd_finalize(self.h, int(bool(want_cr)), C.byref(d),

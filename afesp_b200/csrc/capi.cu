@@ -255,6 +255,7 @@ int afesp_gpu_set_option(afesp_handle hv, const char* key, double value) {
       if ((int)value > 0) gemm_tma_selftest(h.s.eng.stream);
       gemm_tma_scope((int)value);
     }
+    else if (k == "dist_overlap_chunks") h.s.eng.dist.overlap_chunks = std::max(1, std::min(8, (int)value));
     else if (k == "dist_min_flops") h.s.eng.dist.min_flops = value;   // GEMMs below this stay replicated
     else if (k == "dist_ccsd") {   // 0: replicate CCSD / AO->MO, shard only (T)
       AFESP_REQUIRE(!(h.s.vpm_sharded && !h.s.finalized && value == 0.0),
@@ -338,20 +339,37 @@ int afesp_gpu_release(afesp_handle hv, const char* what) {
   });
 }
 
+static void allreduce_sum(Handle& h, double* vals, int n);
 int afesp_gpu_set_eri_mo(afesp_handle hv, int n, const double* eri_mo) {
   return guarded(hv, [&](Handle& h) {
-    const Dist& d = h.s.eng.dist;
+    Dist& d = h.s.eng.dist;
     const bool collective = d.nranks > 1 && d.comm != nullptr;
-    AFESP_REQUIRE(n > 0 && (eri_mo || (collective && d.rank != 0)), "set_eri_mo: bad arguments");
+    AFESP_REQUIRE(n > 0 && (eri_mo || collective), "set_eri_mo: bad arguments");
     const long long np = npacked_of(n);
     cudaStream_t st = h.s.eng.stream;
     if ((long long)h.s.eri_mo.n != np) h.s.eri_mo.alloc((size_t)np);
-    if (eri_mo) AFESP_CUDA_CHECK(cudaMemcpyAsync(h.s.eri_mo.p, eri_mo, np * 8, cudaMemcpyHostToDevice, st));
-    if (collective) {
-      // One host copy per node is enough: rank 0 uploads, the other ranks receive over NVLink.  Ranks that pass their
-      // own host array take part in the broadcast too (it delivers identical data).
-      int any_null = eri_mo ? 0 : 1;
-      (void)any_null;
+    if (!collective) {
+      AFESP_CUDA_CHECK(cudaMemcpyAsync(h.s.eri_mo.p, eri_mo, np * 8, cudaMemcpyHostToDevice, st));
+      AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
+      h.s.n = n;
+      return;
+    }
+    // Collective.  How many ranks hold the host array?  (one tiny allreduce)
+    double have[1] = {eri_mo ? 1.0 : 0.0};
+    allreduce_sum(h, have, 1);
+    const int nhave = (int)(have[0] + 0.5);
+    if (nhave == d.nranks) {
+      // every rank can read the array (replicated host copies, or one copy in shared memory): each uploads 1/nranks of
+      // it over ITS OWN PCIe link, then the shares are exchanged over NVLink
+      std::vector<std::pair<long long, long long>> ranges(d.nranks);
+      for (int r = 0; r < d.nranks; ++r) ranges[r] = {np * r / d.nranks, np * (r + 1) / d.nranks};
+      const long long lo = ranges[d.rank].first, cnt = ranges[d.rank].second - lo;
+      if (cnt > 0) AFESP_CUDA_CHECK(cudaMemcpyAsync(h.s.eri_mo.p + lo, eri_mo + lo, cnt * 8, cudaMemcpyHostToDevice, st));
+      d.exchange(h.s.eri_mo.p, ranges, st);
+    } else {
+      // one host copy per node: rank 0 uploads, the other ranks receive it over NVLink
+      AFESP_REQUIRE(nhave >= 1 && (d.rank != 0 || eri_mo), "set_eri_mo: rank 0 must pass the host array");
+      if (d.rank == 0) AFESP_CUDA_CHECK(cudaMemcpyAsync(h.s.eri_mo.p, eri_mo, np * 8, cudaMemcpyHostToDevice, st));
       AFESP_REQUIRE(d.group_start() == 0, "ncclGroupStart failed");
       AFESP_REQUIRE(d.bcast(h.s.eri_mo.p, h.s.eri_mo.p, (size_t)np, 0, d.comm, st) == 0, "ncclBroadcast failed");
       AFESP_REQUIRE(d.group_end() == 0, "ncclGroupEnd failed");

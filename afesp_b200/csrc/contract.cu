@@ -112,6 +112,18 @@ void Dist::exchange(double* base, const std::vector<std::pair<long long, long lo
   AFESP_REQUIRE(group_end() == 0, "ncclGroupEnd failed");
 }
 
+void Dist::ensure_comm_stream() {
+  if (comm_stream) return;
+  AFESP_CUDA_CHECK(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+  for (auto& ev : ev_piece) AFESP_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  AFESP_CUDA_CHECK(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+}
+
+// C(M x N) = alpha op(A) op(B) + beta C with the output columns dealt to the ranks.  Every rank holds the same C on
+// entry; it updates ITS column slab in place (beta included: no scratch copy, no second pass) and the updated slabs are
+// then broadcast in place, so every rank leaves with the same C again.  The slab is computed in `overlap_chunks`
+// pieces: the broadcasts of piece c (one grouped NCCL call on the communication stream, after an event) run over
+// NVLink while the GEMM of piece c+1 runs on the compute stream; the compute stream waits for the last piece only.
 void dgemm_sharded(Engine& e, char ta, char tb, int M, int N, int K, double alpha, const double* A, long long lda,
                    const double* B, long long ldb, double beta, double* C, bool b_local, bool force) {
   Dist& d = e.dist;
@@ -121,26 +133,43 @@ void dgemm_sharded(Engine& e, char ta, char tb, int M, int N, int K, double alph
     dgemm(e.stream, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, M);
     return;
   }
-  long long c0, c1;
-  d.col_range(N, d.rank, &c0, &c1);
-  // beta != 0: the slabs are gathered in a scratch matrix and then folded into C (every rank applies the same update)
-  std::unique_ptr<Scratch> tmp;
-  double* out = C;
-  if (beta != 0.0) { tmp.reset(new Scratch(e.pool, (size_t)M * N)); out = tmp->p; }
-  if (c1 > c0) {
-    const bool tB = (tb == 'T' || tb == 't');
-    const double* Bs = b_local ? B : (tB ? B + c0 : B + c0 * ldb);
-    dgemm(e.stream, ta, tb, M, (int)(c1 - c0), K, alpha, A, lda, Bs, ldb, 0.0, out + c0 * M, M);
-  }
-  std::vector<std::pair<long long, long long>> ranges(d.nranks);
-  for (int r = 0; r < d.nranks; ++r) {
+  const bool tB = (tb == 'T' || tb == 't');
+  int nch = std::max(1, std::min(d.overlap_chunks, 8));
+  if (nch > 1) d.ensure_comm_stream();
+  // piece c of rank r: columns [lo, hi) of r's slab, split in multiples of 64 columns (the same rule on every rank)
+  auto piece = [&](int r, int c, long long* lo, long long* hi) {
     long long a, b;
     d.col_range(N, r, &a, &b);
-    ranges[r] = {a * M, b * M};
+    const long long units = (b - a + 63) / 64, per = (units + nch - 1) / nch;
+    *lo = std::min(b, a + per * c * 64);
+    *hi = std::min(b, a + per * (c + 1) * 64);
+  };
+  long long c0, c1;
+  d.col_range(N, d.rank, &c0, &c1);
+  for (int c = 0; c < nch; ++c) {
+    long long lo, hi;
+    piece(d.rank, c, &lo, &hi);
+    if (hi > lo) {
+      const double* Bs = b_local ? (tB ? B + (lo - c0) : B + (lo - c0) * ldb) : (tB ? B + lo : B + lo * ldb);
+      dgemm(e.stream, ta, tb, M, (int)(hi - lo), K, alpha, A, lda, Bs, ldb, beta, C + lo * M, M);
+    }
+    std::vector<std::pair<long long, long long>> ranges(d.nranks);
+    for (int r = 0; r < d.nranks; ++r) {
+      long long a, b;
+      piece(r, c, &a, &b);
+      ranges[r] = {a * M, b * M};
+    }
+    if (nch == 1) {
+      d.exchange(C, ranges, e.stream);
+    } else {
+      AFESP_CUDA_CHECK(cudaEventRecord(d.ev_piece[c], e.stream));
+      AFESP_CUDA_CHECK(cudaStreamWaitEvent(d.comm_stream, d.ev_piece[c], 0));
+      d.exchange(C, ranges, d.comm_stream);
+    }
   }
-  d.exchange(out, ranges, e.stream);
-  if (beta != 0.0) {
-    axpby(e.stream, (long long)M * N, 1.0, out, beta, C);   // tmp returns to the pool: reuse is stream-ordered
+  if (nch > 1) {
+    AFESP_CUDA_CHECK(cudaEventRecord(d.ev_done, d.comm_stream));
+    AFESP_CUDA_CHECK(cudaStreamWaitEvent(e.stream, d.ev_done, 0));
   }
 }
 

@@ -96,15 +96,29 @@ inline int oovv_grid(int v) {
   return (int)std::max<long long>(1, std::min<long long>(chunks, 148LL * 8));
 }
 
-// Note on the division: measured on B200 the divide kernel reaches 63% of the copy peak with the IEEE '/', 93% with a
-// multiplication in its place (k_divide_d2_probe) and 58% with a float-seeded Newton reciprocal -- the quarter-rate
-// MUFU / conversion slots, not the DFMA count, are what the division costs, so the plain correctly-rounded division
-// stays (bit-identical to the reference's T = X / D).
+// Division.  The IEEE '/' costs this kernel a third of its bandwidth (63% of the copy peak against 93% with a
+// multiplication in its place, k_divide_d2_probe): not the DFMA count but the slow-path check and call sequence around
+// it, which serialises the four independent elements a thread has in flight.  fdiv() is branch-free instead: the
+// hardware reciprocal seed (MUFU.RCP64H, relative error 2^-23), two Newton steps to full precision, and one residual
+// correction of the quotient -- 1 MUFU + 7 DFMA, |error| <= 1 ulp (the reference itself is built with -ffast-math).
+// Denominators of the CC equations are sums of orbital-energy differences: finite, far from the subnormal range.
+__device__ __forceinline__ double fdiv(double x, double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  double q = x * y;
+  const double r = fma(-d, q, x);
+  return fma(r, y, q);
+}
+
 __global__ void __launch_bounds__(OOVV_T) k_divide_d2_fast(double* __restrict__ out, const double* __restrict__ x,
                                                             const double* __restrict__ eo, const double* __restrict__ ev,
                                                             int o, int v) {
   oovv_walk<true, 4>(o, v, eo, ev, [&](long long idx, int ij, int c, const OovvTables& t) {
-    out[idx] = x[idx] / (t.eoo[ij] - t.evv[c]);
+    out[idx] = fdiv(x[idx], t.eoo[ij] - t.evv[c]);
   });
 }
 
@@ -285,7 +299,10 @@ __global__ void __launch_bounds__(OOVV_T) k_energy_fast(const double* __restrict
     if (SPINORB) {
       acc[0] += 0.25 * vo[idx] * (tv + 2.0 * t1[i + o * a] * t1[j + o * b]);
     } else {
-      const double vx = vo[ij + oo * (b + (long long)v * a)];
+      // <ij|ba> = <ji|ab>: the exchange partner sits in the SAME (a,b) plane at the transposed (i,j) position -- a second
+      // read of the contiguous run this block is streaming (L1/L2 hit) instead of a gather from the (b,a) plane, which
+      // doubled the DRAM traffic of v_oovv (the two elements are copies of one packed integral: bit-identical)
+      const double vx = vo[idx - ij + (j + o * i)];
       acc[0] += (2.0 * vo[idx] - vx) * (tv + t1[i + o * a] * t1[j + o * b]);
     }
     const double d = tv - t2_old[idx];

@@ -117,6 +117,8 @@ struct SlabParams {
   int sdims[MAXR];     // output extents of the slab axes
   int sistr[MAXR];     // input stride (inside the slab) of the axis feeding output slab axis d
   int S, G;
+  int pad_every;       // one padding word after every `pad_every` slab elements (0: none), see below
+  int Sp;              // padded slab size in shared memory
   int nrest;
   int rdims[MAXR];
   long long ristr[MAXR], rostr[MAXR];
@@ -124,14 +126,23 @@ struct SlabParams {
   double alpha, beta;
 };
 
+// Shared-memory position of slab element `off` (input order).  The permuted read walks the slab with the input stride of
+// the output-fastest axis -- e.g. stride o for (i,j)->(j,i): with o = 20 or 40 the 16 lanes of a half-warp would hit 4
+// or 2 of the 16 eight-byte banks.  One padding word per run of the input-fastest axis makes that stride odd.
+__device__ __forceinline__ int slab_pos(int off, int pad_every) { return pad_every ? off + off / pad_every : off; }
+// the same without an integer division, for the streaming loop: off < 4096 and pad_every >= 8, so the float quotient of
+// (off + 0.5) is at least 0.5/pad_every away from an integer -- far more than its rounding error
+__device__ __forceinline__ int slab_pos_fast(int off, float inv_pad) { return off + (int)(((float)off + 0.5f) * inv_pad); }
+
 __global__ void __launch_bounds__(256) permute_slab(const SlabParams p, const double* __restrict__ in,
                                                     double* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char slab_sm[];
-  double* buf = reinterpret_cast<double*>(slab_sm);                       // [G*S]
-  long long* ibase = reinterpret_cast<long long*>(buf + (size_t)p.G * p.S);  // [G]
+  double* buf = reinterpret_cast<double*>(slab_sm);                       // [G*Sp]
+  long long* ibase = reinterpret_cast<long long*>(buf + (size_t)p.G * p.Sp);  // [G]
   long long* obase = ibase + p.G;                                         // [G]
-  int* tab = reinterpret_cast<int*>(obase + p.G);                         // [S]
-  const int tid = threadIdx.x, S = p.S;
+  int* tab = reinterpret_cast<int*>(obase + p.G);                         // [S] padded position read by output element s
+  const int tid = threadIdx.x, S = p.S, Sp = p.Sp;
+  const float inv_pad = p.pad_every ? 1.0f / (float)p.pad_every : 0.0f;
   for (int s = tid; s < S; s += 256) {
     int rem = s, off = 0;
     for (int d = 0; d < p.k; ++d) {
@@ -139,7 +150,7 @@ __global__ void __launch_bounds__(256) permute_slab(const SlabParams p, const do
       off += c * p.sistr[d];
       rem = q;
     }
-    tab[s] = off;
+    tab[s] = slab_pos(off, p.pad_every);
   }
   const int s0 = tid % S, g0 = tid / S;
   for (long long slab0 = (long long)blockIdx.x * p.G; slab0 < p.rest_total; slab0 += (long long)gridDim.x * p.G) {
@@ -160,30 +171,94 @@ __global__ void __launch_bounds__(256) permute_slab(const SlabParams p, const do
     int e = tid;
     for (; e + 3 * 256 < n; e += 4 * 256) {   // four independent loads in flight per thread
       double v[4];
+      int pos[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         v[u] = in[ibase[g] + s];
+        pos[u] = g * Sp + slab_pos_fast(s, inv_pad);
         s += 256;
         while (s >= S) { s -= S; ++g; }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) buf[e + u * 256] = v[u];
+      for (int u = 0; u < 4; ++u) buf[pos[u]] = v[u];
     }
     for (; e < n; e += 256) {
-      buf[e] = in[ibase[g] + s];
+      buf[g * Sp + slab_pos_fast(s, inv_pad)] = in[ibase[g] + s];
       s += 256;
       while (s >= S) { s -= S; ++g; }
     }
     __syncthreads();
     s = s0; g = g0;
-    for (int e = tid; e < n; e += 256) {
-      double* o = out + obase[g] + s;
-      double v = p.alpha * buf[g * S + tab[s]];
-      if (p.beta != 0.0) v += p.beta * (*o);
-      *o = v;
-      s += 256;
-      while (s >= S) { s -= S; ++g; }
+    if (p.beta == 0.0) {
+      for (int e2 = tid; e2 < n; e2 += 256) {
+        out[obase[g] + s] = p.alpha * buf[g * Sp + tab[s]];
+        s += 256;
+        while (s >= S) { s -= S; ++g; }
+      }
+    } else {
+      int e2 = tid;
+      for (; e2 + 3 * 256 < n; e2 += 4 * 256) {   // the four reads of `out` in flight together
+        double* o[4];
+        double old[4], nv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          o[u] = out + obase[g] + s;
+          old[u] = *o[u];
+          nv[u] = buf[g * Sp + tab[s]];
+          s += 256;
+          while (s >= S) { s -= S; ++g; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) *o[u] = p.alpha * nv[u] + p.beta * old[u];
+      }
+      for (; e2 < n; e2 += 256) {
+        double* o = out + obase[g] + s;
+        *o = p.alpha * buf[g * Sp + tab[s]] + p.beta * (*o);
+        s += 256;
+        while (s >= S) { s -= S; ++g; }
+      }
     }
+  }
+}
+
+// Transpose for a SHORT input-fastest axis (n0 < 48, e.g. the occupied index o = 20 / 40 of (i,j,a,b) -> (b,a,j,i)):
+// a tile holds the whole run of n0 elements for 64 values of the axis that becomes output-fastest, so the stores are
+// 512-byte rows and the loads are complete n0*8-byte runs (a 32x32 tile would run the second tile column 1/4 full).
+__global__ void __launch_bounds__(256) permute_transpose_narrow(const TransParams p, const double* __restrict__ in,
+                                                                double* __restrict__ out) {
+  __shared__ double tile[64][49];
+  const int n0 = p.n0;
+  const int tiles_b = (p.nb + 63) / 64;
+  const float inv = 1.0f / (float)n0;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  for (int by = blockIdx.y; by < tiles_b; by += gridDim.y)
+  for (long long rest = blockIdx.z; rest < p.rest_total; rest += gridDim.z) {
+    const int b0 = by * 64;
+    long long rem = rest, ibase = 0, obase = 0;
+    for (int d = 0; d < p.nrest; ++d) {
+      long long q = rem / p.rdims[d];
+      long long c = rem - q * p.rdims[d];
+      ibase += c * p.ristr[d];
+      obase += c * p.rostr[d];
+      rem = q;
+    }
+    for (int e = threadIdx.x; e < 64 * n0; e += 256) {
+      int r = (int)(((float)e + 0.5f) * inv);      // e / n0 (exact for e < 64 * 48)
+      int i = e - r * n0;
+      if (i < 0) { --r; i += n0; } else if (i >= n0) { ++r; i -= n0; }
+      if (b0 + r < p.nb) tile[r][i] = in[ibase + i + (long long)(b0 + r) * p.istr_b];
+    }
+    __syncthreads();
+    for (int i = ty; i < n0; i += 4) {
+      const int b = b0 + tx;
+      if (b < p.nb) {
+        double* o = out + obase + b + (long long)i * p.ostr_0;
+        double v = p.alpha * tile[tx][i];
+        if (p.beta != 0.0) v += p.beta * (*o);
+        *o = v;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -312,7 +387,7 @@ void permute_strided(cudaStream_t st, int rank, const int* dims, const int* perm
       bool dense_out = true;
       long long acc = 1;
       for (int d = 0; d < k; ++d) { dense_out = dense_out && (ostr_d[d] == acc); acc *= odims[d]; }
-      if (!dense_out || acc > 4000) break;   // buffer + table + bases must fit the 48 KB default dynamic shared memory
+      if (!dense_out || acc > 3600) break;   // buffer (+ padding) + tables + bases must fit the 48 KB default dynamic shared memory
       // input side: the same axes, sorted by input stride, must tile [0, acc) densely
       int idx[MAXR];
       for (int d = 0; d < k; ++d) idx[d] = d;
@@ -324,7 +399,14 @@ void permute_strided(cudaStream_t st, int rank, const int* dims, const int* perm
     }
     if (kslab > 0) {
       SlabParams p{};
-      p.k = kslab; p.S = (int)S; p.G = (int)std::max<long long>(1, 4000 / S);
+      p.k = kslab; p.S = (int)S;
+      // padding: one word per run of the slab's input-fastest axis when that run length is even (odd strides already
+      // spread over the banks)
+      int run = 0;
+      for (int d = 0; d < kslab; ++d) if (istr[d] == 1) run = odims[d];
+      p.pad_every = (run >= 8 && run % 2 == 0 && run < S) ? run : 0;
+      p.Sp = p.pad_every ? (int)(S + S / p.pad_every) : (int)S;
+      p.G = (int)std::max<long long>(1, 4000 / p.Sp);
       for (int d = 0; d < kslab; ++d) { p.sdims[d] = odims[d]; p.sistr[d] = (int)istr[d]; }
       p.nrest = r - kslab; p.rest_total = 1;
       for (int d = kslab; d < r; ++d) {
@@ -332,7 +414,7 @@ void permute_strided(cudaStream_t st, int rank, const int* dims, const int* perm
         p.rest_total *= odims[d];
       }
       p.alpha = alpha; p.beta = beta;
-      const size_t smem = (size_t)p.G * p.S * 8 + (size_t)p.G * 16 + (size_t)p.S * 4;
+      const size_t smem = (size_t)p.G * p.Sp * 8 + (size_t)p.G * 16 + (size_t)p.S * 4;   // <= 3600 * (9 + 4) + ... < 48 KB
       const long long passes = (p.rest_total + p.G - 1) / p.G;
       const int blocks = (int)std::max<long long>(1, std::min<long long>(passes, 148LL * 8));
       permute_slab<<<blocks, 256, smem, st>>>(p, in, out);
@@ -357,7 +439,10 @@ void permute_strided(cudaStream_t st, int rank, const int* dims, const int* perm
       ++p.nrest;
     }
     p.alpha = alpha; p.beta = beta;
-    if (p.n0 >= 48 && p.nb >= 48) {
+    if (p.n0 < 48 && p.nb >= 64) {
+      dim3 grid(1, (unsigned)std::min<long long>((p.nb + 63) / 64, 65535), (unsigned)std::min<long long>(p.rest_total, 65535));
+      permute_transpose_narrow<<<grid, 256, 0, st>>>(p, in, out);
+    } else if (p.n0 >= 48 && p.nb >= 48) {
       dim3 grid((p.n0 + 63) / 64, (unsigned)std::min<long long>((p.nb + 63) / 64, 65535),
                 (unsigned)std::min<long long>(p.rest_total, 65535));
       permute_transpose64<<<grid, 256, 0, st>>>(p, in, out);

@@ -75,6 +75,13 @@ struct Dist {
   int (*send)(const void* buf, size_t count, int peer, void* comm, cudaStream_t st) = nullptr;
   int (*recv)(void* buf, size_t count, int peer, void* comm, cudaStream_t st) = nullptr;
   double min_flops = 4e9;   // GEMMs below this stay replicated (exchange latency would dominate)
+  int overlap_chunks = 1;   // > 1: a rank's column slab is computed in this many pieces and the exchange of piece c runs on
+                            // the communication stream while piece c+1 is computed (option "dist_overlap_chunks").  Measured
+                            // on 2 x B200 at nbf=200 (profiles/r02_bench_n200_2gpu_overlap_chunks.json): 27.4 / 29.2 / 33.8 ms per
+                            // CCSD iteration with 1 / 2 / 4 pieces -- the smaller GEMMs and the NCCL kernels competing for SMs
+                            // cost more than the hidden transfer saves, so the default stays serial
+  cudaStream_t comm_stream = nullptr;            // created on first use
+  cudaEvent_t ev_piece[8] = {nullptr}, ev_done = nullptr;
   double exchanged_bytes = 0.0;  // bytes this rank received through slab exchanges (bench accounting)
   bool enabled = true;           // option dist_ccsd: 0 keeps CCSD / AO->MO replicated (only (T) is partitioned)
   bool active() const { return enabled && nranks > 1 && comm != nullptr; }
@@ -87,6 +94,7 @@ struct Dist {
   }
   // every rank broadcasts the element range it owns of a replicated array: ranges[r] = [begin, end) in doubles
   void exchange(double* base, const std::vector<std::pair<long long, long long>>& ranges, cudaStream_t st);
+  void ensure_comm_stream();
 };
 
 struct Engine {

@@ -212,16 +212,59 @@ def run_shape(args, rank, world, local, n, o, steps, warmup, e2e_first=False, wa
 
     if args.tma >= 0:
         gpu.set_option("gemm_use_tma", args.tma)
+    if args.dist_chunks > 0:
+        gpu.set_option("dist_overlap_chunks", args.dist_chunks)
     tma_scope, tma_selftest = gpu.tma_status()
     peak = max(gpu.dmma_peak(), gpu.dmma_peak())
     npair = n * (n + 1) // 2
     npk = npair * (npair + 1) // 2
-    # host copy of the packed MO integrals (input of the e2e leg): pinned, one copy per node on rank 0; the other
-    # ranks receive it over NVLink inside afesp_gpu_set_eri_mo
-    src = None
-    if rank == 0:
+    # host copy of the packed MO integrals (input of the e2e leg): ONE copy per node.  Single GPU: a pinned buffer.  Several
+    # ranks: a shared-memory file (/dev/shm) written by rank 0 and mapped + page-locked (cudaHostRegister) by every rank,
+    # so that each rank uploads its 1/N share over its own PCIe link inside afesp_gpu_set_eri_mo.
+    src, shm_path, shm_registered = None, None, False
+    if world == 1:
         pinned = torch.empty(npk, dtype=torch.float64).pin_memory()
         src = pinned.numpy()
+    else:
+        ok = 0.0
+        shm_path = "/dev/shm/afesp_bench_%s_%d.bin" % (os.environ.get("MASTER_PORT", "0"), n)
+        try:
+            st = os.statvfs("/dev/shm")
+            if st.f_bavail * st.f_frsize > npk * 8 * 1.1:
+                if rank == 0:
+                    np.memmap(shm_path, dtype=np.float64, mode="w+", shape=(npk,)).flush()
+                ok = 1.0
+        except OSError:
+            ok = 0.0
+        flag = torch.tensor([ok if rank == 0 else 1.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() > 0.5:
+            src = np.memmap(shm_path, dtype=np.float64, mode="r+", shape=(npk,))
+            rc = torch.cuda.cudart().cudaHostRegister(src.ctypes.data, src.nbytes, 0)
+            rc = rc[0] if isinstance(rc, tuple) else rc
+            shm_registered = int(rc) == 0
+            if not shm_registered:
+                torch.cuda.cudart().cudaGetLastError()   # clear the (non-sticky) error
+        flag = torch.tensor([1.0 if shm_registered else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() < 0.5:
+            # no page-locked shared mapping on this box (small /dev/shm, registration refused): one pinned copy on rank 0,
+            # the other ranks receive the integrals over NVLink inside afesp_gpu_set_eri_mo
+            if shm_registered:
+                torch.cuda.cudart().cudaHostUnregister(src.ctypes.data)
+            shm_registered = False
+            src = None
+            if rank == 0:
+                try:
+                    os.unlink(shm_path)
+                except OSError:
+                    pass
+                src = torch.empty(npk, dtype=torch.float64).pin_memory().numpy()
+            shm_path = None
+    amp_out = None
+    if rank == 0:   # pinned landing buffers for the D2H of T1/T2 (only rank 0 asks for the amplitudes)
+        amp_out = (torch.empty(o * v, dtype=torch.float64).pin_memory().numpy(),
+                   torch.empty(o * o * v * v, dtype=torch.float64).pin_memory().numpy())
     if big:
         gpu.synth_eri_ao(n, Bfac, Cmo)
         gpu.ao2mo(n, want_result=False)
@@ -231,6 +274,7 @@ def run_shape(args, rank, world, local, n, o, steps, warmup, e2e_first=False, wa
     ao2mo_ms = gpu.last_stage_ms()
     if rank == 0:
         gpu.get_eri_mo(src)
+    barrier()   # the shared host copy is complete before any rank reads its share
     gpu.release("eri_ao")
     e_mp2 = gpu.mp2_energy(o, eps)
     h2d = int(npk * 8 + n * 8)
@@ -258,7 +302,7 @@ def run_shape(args, rank, world, local, n, o, steps, warmup, e2e_first=False, wa
             gpu.ccsd_iterate()
             gpu.ccsd_diis()
             t = lap("iterate+diis", t)
-            gpu.ccsd_finalize(want_amplitudes=True)
+            gpu.ccsd_finalize(out=amp_out)   # D2H of T1/T2 into pinned memory on rank 0 (None elsewhere: no copy)
             t = lap("finalize_d2h", t)
             gpu.ccsd_t_spatial(True, False, False)
             t = lap("ccsd_t", t)
@@ -387,13 +431,25 @@ def run_shape(args, rank, world, local, n, o, steps, warmup, e2e_first=False, wa
                                         "(afesp_gpu_dmma_peak); MEASURED_PEAKS.json has no FP64 entry; vendor FP64 "
                                         "tensor figure 40 TFLOP/s"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "set_eri_mo(H2D from pinned host memory) + ccsd_init + iterate + diis + finalize(D2H t1,t2) + ccsd_t"
+                    "what": "set_eri_mo(H2D from pinned host memory" + ((", each rank its 1/N share over its own PCIe link, "
+                            "shares exchanged over NVLink" if shm_path else ", rank 0 uploads, NVLink broadcast") if world > 1 else "") + ") + ccsd_init + iterate + diis + "
+                            "finalize(D2H t1,t2 into pinned memory) + ccsd_t"
                             + ("; single pass that also served as warm-up of the device-timed pass" if e2e_first else ""),
                     "breakdown_s": {k: x / ksteps for k, x in parts.items()}},
             "gpu_launches": int(l1 - l0), "clocks": clocks,
             "tma": {"scope": tma_scope, "selftest": tma_selftest}, "hbm_kernels": hbm,
         }
     gpu.close()
+    if shm_path is not None:
+        if shm_registered:
+            torch.cuda.cudart().cudaHostUnregister(src.ctypes.data)
+        del src
+        barrier()
+        if rank == 0:
+            try:
+                os.unlink(shm_path)
+            except OSError:
+                pass
     return out
 
 
@@ -470,6 +526,7 @@ def main():
     ap.add_argument("--trajectory", action="store_true", help="print the per-step (E_CCSD, e_T) list (pinning runs)")
     ap.add_argument("--tma", type=int, default=-1, help="gemm_use_tma: -1 library default (2: TMA-staged kernel for every "
                                                         "aligned GEMM), 1 the (T) batches only, 0 cp.async kernels only")
+    ap.add_argument("--dist-chunks", type=int, default=0, help="dist_overlap_chunks of the sharded CCSD GEMMs (0: library default)")
     ap.add_argument("--workload", default=None, help="sample_data molecule run: n2 | f2 | h2o | h2o-spinorb")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -78,8 +78,9 @@ int afesp_gpu_get_eri_mo(afesp_handle h, double* eri_mo);
 /* Free device memory the next stage does not need: what = "eri_ao" | "eri_mo" | "scratch". */
 int afesp_gpu_release(afesp_handle h, const char* what);
 /* Load packed MO integrals directly (a host that already holds int_store%eri_mo).  With a communicator attached the
- * call is collective: rank 0 passes the host array, the other ranks may pass NULL and receive the device copy over
- * NVLink (one host copy per node instead of one per GPU). */
+ * call is collective.  If EVERY rank passes the array (replicated host copies, or one copy per node in shared memory)
+ * each rank uploads 1/nranks of it over its own PCIe link and the shares are exchanged over NVLink; if only some do,
+ * rank 0 must be one of them: it uploads the whole array and the other ranks (which may pass NULL) receive it over NVLink. */
 int afesp_gpu_set_eri_mo(afesp_handle h, int nbasis, const double* eri_mo);
 /* MP2 correlation energy from the device-resident MO integrals (src/mp2.f90:418-438); eps = sys%canon_levels(n). */
 int afesp_gpu_mp2_energy(afesp_handle h, int nocc, const double* eps, double* e_mp2);

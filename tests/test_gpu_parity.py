@@ -335,6 +335,29 @@ def test_spinorbital_symmetry_assertion_runs_and_aborts(gpu, tmp_path):
     assert r.returncode == 0 and "Initialisation done" in r.stdout
 
 
+def test_h2o_cc_pvtz_spinorbital_ccsd_t_matches_reference_els_cpu_out(gpu):
+    """BASELINE.json configs[1] input (sample_data/h2o-cc-pvtz, 58 basis functions, 116 spin-orbitals) with the two-electron
+    integrals regenerated by the host-side generator (the checkout ships no eri.dat): the whole program reproduces the
+    reference's own els_cpu.out -- 22 SCF iterations, MP2, the MP1 line and all 19 spin-orbital CCSD iterations to 1e-9 Eh
+    and E[CCSD(T)] = -0.4340327558.  This is the current code version, so it pins Q1 (transposed F_oo term) as coded and
+    the spin-orbital (T) against reference output, not only against the oracle."""
+    from afesp_b200 import host
+
+    Gz = G["h2o_tz"]
+    res = host.run(load_els_input("h2o_tz", "CCSD(T)_spinorb"), gpu=gpu)
+    assert len(res.scf_table) == len(Gz["scf"]) == 22
+    for (it, e, _, rms), (git, ge, _, grms) in zip(res.scf_table, Gz["scf"]):
+        assert it == git and abs(e - ge) < 2e-9
+    assert abs(res.e_mp2 - Gz["e_mp2_8"]) < 1e-8
+    rows = res.ccsd_table
+    assert len(rows) == len(Gz["ccsd"]) == 20 and rows[0][0] == "MP1"
+    for (it, e, _, rms), (git, ge, _, grms) in zip(rows, Gz["ccsd"]):
+        assert it == git and abs(e - ge) < E_TOL and abs(rms - grms) < 1e-9, (it, e, ge)
+    assert abs(res.e_ccsd - Gz["e_ccsd_12"]) < E_TOL
+    assert abs(res.energies["e_ccsd_t"] - Gz["final"]["CCSD(T) correlation energy"]) < E_TOL
+    assert abs(res.energies["e_ccsd_t"] - Gz["e_ccsd_t_9"]) < E_TOL
+
+
 # ---------------------------------------------------------------- (T) sharding and symmetry properties
 def test_triples_partition_sums_and_symmetry_switch(gpu, oracle_runs):
     from afesp_b200 import host
