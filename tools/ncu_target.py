@@ -16,10 +16,17 @@ rt = torch.cuda.cudart()
 g = AfespGpu(0)
 if os.environ.get("TMA_SCOPE"):
     g.set_option("gemm_use_tma", int(os.environ["TMA_SCOPE"]))
-eri, C, eps = synthetic.make(n, o)
-g.ao2mo(n, eri, C, want_result=False)
+if n > 240:   # the packed AO integrals are expanded on the device from the low-rank factors
+    Bf, C, eps = synthetic.make_factors(n, o)
+    g.synth_eri_ao(n, Bf, C)
+    g.ao2mo(n, want_result=False)
+else:
+    eri, C, eps = synthetic.make(n, o)
+    g.ao2mo(n, eri, C, want_result=False)
 g.release("eri_ao")
 g.ccsd_init(o, True, eps, 8)
+if n > 240:
+    g.release("eri_mo")
 g.ccsd_iterate()
 g.ccsd_diis()
 if what == "CCSD":
