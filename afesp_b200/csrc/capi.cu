@@ -24,6 +24,7 @@ struct NcclApi {
   int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*CommDestroy)(NcclComm) = nullptr;
   int (*Broadcast)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
   int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
@@ -42,6 +43,7 @@ struct NcclApi {
     CommDestroy = (int (*)(NcclComm))dlsym(lib, "ncclCommDestroy");
     GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
     Broadcast = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(lib, "ncclBroadcast");
+    AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))dlsym(lib, "ncclAllGather");
     Send = (int (*)(const void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(lib, "ncclSend");
     Recv = (int (*)(void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(lib, "ncclRecv");
     GroupStart = (int (*)())dlsym(lib, "ncclGroupStart");
@@ -62,6 +64,9 @@ int dist_group_start() { return g_nccl.GroupStart(); }
 int dist_group_end() { return g_nccl.GroupEnd(); }
 int dist_bcast(const void* s, void* r, size_t n, int root, void* comm, cudaStream_t st) {
   return g_nccl.Broadcast(s, r, n, kNcclDouble, root, comm, st);
+}
+int dist_allgather(const void* s, void* r, size_t n, void* comm, cudaStream_t st) {
+  return g_nccl.AllGather ? g_nccl.AllGather(s, r, n, kNcclDouble, comm, st) : -1;
 }
 int dist_send(const void* b, size_t n, int peer, void* comm, cudaStream_t st) {
   return g_nccl.Send(b, n, kNcclDouble, peer, comm, st);
@@ -255,6 +260,7 @@ int afesp_gpu_set_option(afesp_handle hv, const char* key, double value) {
       if ((int)value > 0) gemm_tma_selftest(h.s.eng.stream);
       gemm_tma_scope((int)value);
     }
+    else if (k == "dist_allgather") h.s.eng.dist.use_allgather = value != 0.0;
     else if (k == "dist_overlap_chunks") h.s.eng.dist.overlap_chunks = std::max(1, std::min(8, (int)value));
     else if (k == "dist_min_flops") h.s.eng.dist.min_flops = value;   // GEMMs below this stay replicated
     else if (k == "dist_ccsd") {   // 0: replicate CCSD / AO->MO, shard only (T)
@@ -553,6 +559,7 @@ int afesp_gpu_comm_init(afesp_handle hv, int rank, int nranks, const char id[128
     d.rank = rank; d.nranks = nranks; d.comm = h.comm;
     d.group_start = dist_group_start; d.group_end = dist_group_end;
     d.bcast = dist_bcast; d.send = dist_send; d.recv = dist_recv;
+    d.allgather = g_nccl.AllGather ? dist_allgather : nullptr;
   });
 }
 

@@ -135,6 +135,26 @@ void dgemm_sharded(Engine& e, char ta, char tb, int M, int N, int K, double alph
   }
   const bool tB = (tb == 'T' || tb == 't');
   int nch = std::max(1, std::min(d.overlap_chunks, 8));
+  if (nch == 1 && d.use_allgather && d.allgather) {
+    // Equal slabs of `per` columns (the col_range unit, padded past N on the last ranks) in a scratch matrix
+    // G(M x per*nranks): every rank computes its slab straight into its place (beta: its columns of C are copied in
+    // first), ONE in-place ncclAllGather moves all slabs, and the N valid columns are copied back into C.
+    const long long units = (N + 63) / 64, per = (units + d.nranks - 1) / d.nranks * 64;
+    long long c0, c1;
+    d.col_range(N, d.rank, &c0, &c1);
+    Scratch G(e.pool, (size_t)M * per * d.nranks);
+    double* mine = G.p + (size_t)M * per * d.rank;
+    if (c1 > c0) {
+      if (beta != 0.0)
+        AFESP_CUDA_CHECK(cudaMemcpyAsync(mine, C + c0 * M, (size_t)(c1 - c0) * M * 8, cudaMemcpyDeviceToDevice, e.stream));
+      const double* Bs = b_local ? B : (tB ? B + c0 : B + c0 * ldb);
+      dgemm(e.stream, ta, tb, M, (int)(c1 - c0), K, alpha, A, lda, Bs, ldb, beta, mine, M);
+    }
+    AFESP_REQUIRE(d.allgather(mine, G.p, (size_t)M * per, d.comm, e.stream) == 0, "ncclAllGather failed");
+    d.exchanged_bytes += 8.0 * M * per * (d.nranks - 1);
+    AFESP_CUDA_CHECK(cudaMemcpyAsync(C, G.p, (size_t)M * N * 8, cudaMemcpyDeviceToDevice, e.stream));
+    return;
+  }
   if (nch > 1) d.ensure_comm_stream();
   // piece c of rank r: columns [lo, hi) of r's slab, split in multiples of 64 columns (the same rule on every rank)
   auto piece = [&](int r, int c, long long* lo, long long* hi) {

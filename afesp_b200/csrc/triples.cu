@@ -36,7 +36,11 @@ constexpr int BOX = TS * TP * TP;   // doubles per staged box
 __constant__ int c_perm[6][3] = {{0, 1, 2}, {1, 0, 2}, {2, 1, 0}, {0, 2, 1}, {1, 2, 0}, {2, 0, 1}};
 __constant__ double c_coef[6] = {8.0 / 6.0, -4.0 / 6.0, -4.0 / 6.0, -4.0 / 6.0, 2.0 / 6.0, 2.0 / 6.0};
 
-struct TripleDesc { int i, j, k; double weight; };
+// One occupied triple of a (T) launch.  slot[s] = block of the batch buffer holding Y_s (s = abc, bac, cba).  Coincident
+// occupied indices make blocks redundant (spin-free driver): i == j gives Y_bac = Y_abc (slot[1] = slot[0]); j == k
+// gives Y_cba(x,u,w) = Y_bac(x,w,u) (flag bit 1: the epilogue takes the cba values from the bac gather, no block at all).
+struct TripleDesc { int i, j, k, flags; double weight; int slot[3]; int pad; };
+constexpr int kCbaFromBac = 2;
 
 __device__ __forceinline__ int box_off(int x, int y, int z) { return (z * TP + y) * TP + x; }
 
@@ -61,8 +65,9 @@ __host__ __device__ constexpr int COMP(int q, int s) {
 __host__ __device__ constexpr double COEF(int s) { return s == 0 ? 8.0 / 6.0 : (s <= 3 ? -4.0 / 6.0 : 2.0 / 6.0); }
 
 struct FusedArgs {
-  const double* X;    // [nb][3][v^3]  pair-merged GEMM blocks Y_s (s = abc, bac, cba) for the W term
-  const double* XM;   // [nb][3][v^3]  same for the M3 term (CR) or null
+  const double* X;    // [blocks][v^3]  pair-merged GEMM blocks Y_s (s = abc, bac, cba) for the W term, addressed through
+                      //                TripleDesc::slot
+  const double* XM;   // [blocks][v^3]  same for the M3 term (CR) or null
   const double* t1;   // (o,v)
   const double* t2;   // (o,o,v,v)
   const double* vo;   // v_oovv (o,o,v,v)
@@ -141,26 +146,49 @@ __global__ void __launch_bounds__(TS* TS* TS, 2) k_triples_fused(const FusedArgs
     rd[w] = swz(w, l[PM(w, 0)], l[PM(w, 1)], l[PM(w, 2)]);
   }
 
-  // out[u] = sum_s Y_s[P_{u o s}(a,b,c)], u = 0..5 (s = abc, bac, cba are involutions: V[s][w] lands in u = w o s)
-  auto gather = [&](const double* __restrict__ Yb, double (&out)[6]) {
+  // out[u] = sum_s Y_s[P_{u o s}(a,b,c)], u = 0..5 (s = abc, bac, cba are involutions: V[s][w] lands in u = w o s).
+  // Blocks that coincide for i == j (Y_bac = Y_abc: same slot, the L2 serves the second read) are simply read again;
+  // for j == k (flag kCbaFromBac) Y_cba(x,u,w) = Y_bac(x,w,u), i.e. V[cba][w] = V[bac][w o acb]: no loads, no staging.
+  const bool cba_from_bac = (td.flags & kCbaFromBac) != 0;   // CTA-uniform
+  const int ns = cba_from_bac ? 2 : 3;
+  auto gather = [&](const double* __restrict__ Ybase, double (&out)[6]) {
     double val[18];
 #pragma unroll
-    for (int s = 0; s < 3; ++s)
+    for (int s = 0; s < 3; ++s) {
+      if (s < ns) {
+        const double* __restrict__ Yb = Ybase + (long long)td.slot[s] * v3;
 #pragma unroll
-      for (int w = 0; w < 6; ++w) val[s * 6 + w] = okb[w] ? __ldg(Yb + s * v3 + gorg[w]) : 0.0;
+        for (int w = 0; w < 6; ++w) val[s * 6 + w] = okb[w] ? __ldg(Yb + gorg[w]) : 0.0;
+      }
+    }
 #pragma unroll
     for (int u = 0; u < 6; ++u) out[u] = 0.0;
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
-      out[COMP(0, s)] += val[s * 6];
+      if (s < ns) {
+        out[COMP(0, s)] += val[s * 6];
 #pragma unroll
-      for (int w = 1; w < 6; ++w) sS[(s * 5 + w - 1) * BOXW + wr[w]] = val[s * 6 + w];
+        for (int w = 1; w < 6; ++w) sS[(s * 5 + w - 1) * BOXW + wr[w]] = val[s * 6 + w];
+      }
     }
     __syncthreads();
+    double v1[6];   // the bac gather, kept for the j == k case
 #pragma unroll
-    for (int s = 0; s < 3; ++s)
+    for (int s = 0; s < 3; ++s) {
+      if (s < ns) {
 #pragma unroll
-      for (int w = 1; w < 6; ++w) out[COMP(w, s)] += sS[(s * 5 + w - 1) * BOXW + rd[w]];
+        for (int w = 1; w < 6; ++w) {
+          const double x = sS[(s * 5 + w - 1) * BOXW + rd[w]];
+          out[COMP(w, s)] += x;
+          if (s == 1) v1[w] = x;
+        }
+        if (s == 1) v1[0] = val[6];
+      }
+    }
+    if (cba_from_bac) {
+#pragma unroll
+      for (int w = 0; w < 6; ++w) out[COMP(w, 2)] += v1[COMP(w, 3)];
+    }
   };
 
   if (AUX) {
@@ -179,10 +207,10 @@ __global__ void __launch_bounds__(TS* TS* TS, 2) k_triples_fused(const FusedArgs
     }
   }
   double W[6], M[6];
-  gather(g.X + (long long)blockIdx.y * 3 * v3, W);
+  gather(g.X, W);
   if (DO_M) {
     __syncthreads();                                  // the staging boxes are reused
-    gather(g.XM + (long long)blockIdx.y * 3 * v3, M);
+    gather(g.XM, M);
   }
   // energies of the orbit (:2175-2233)
   double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -349,12 +377,12 @@ std::vector<TripleDesc> my_triples(int o, bool symmetric, bool strict, int rank,
         for (int k = j; k < o; ++k) {
           if (strict && (i == j || j == k)) continue;
           double w = (i == j && j == k) ? 1.0 : ((i == j || j == k) ? 3.0 : 6.0);
-          all.push_back({i, j, k, w});
+          all.push_back({i, j, k, 0, w, {0, 0, 0}, 0});
         }
   } else {
     for (int i = 0; i < o; ++i)
       for (int j = 0; j < o; ++j)
-        for (int k = 0; k < o; ++k) all.push_back({i, j, k, 1.0});
+        for (int k = 0; k < o; ++k) all.push_back({i, j, k, 0, 1.0, {0, 0, 0}, 0});
   }
   std::vector<TripleDesc> mine;
   for (size_t t = 0; t < all.size(); ++t)
@@ -460,12 +488,41 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
   std::vector<TripleDesc> tri = my_triples(o, s.opt.triples_ijk_symmetry, false, rank, nranks);
   if (tri.empty()) return;
   tr.lap(0);
-  const long long per_triple = (do_m ? 6 : 3) * v3 * 8;
-  int nb = (int)std::max<long long>(1, std::min<long long>((long long)tri.size(), s.opt.triples_batch_bytes / per_triple));
-  nb = std::min(nb, 65535 / 3);
-  Scratch X(e.pool, (size_t)nb * 3 * v3);
+  // GEMM blocks per triple: 3, or fewer when occupied indices coincide (see TripleDesc): i == j -> {abc, cba},
+  // j == k -> {abc, bac}, i == j == k -> {abc}.  At nocc = 20 / 40 that removes 8.7 % / 4.6 % of the (T) flop.
+  const int perm3[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 1, 0}};   // s = abc, bac, cba (first three rows of c_perm)
+  const long long cap_blocks = std::max<long long>(3, std::min<long long>(65535, s.opt.triples_batch_bytes / ((do_m ? 2 : 1) * v3 * 8)));
+  struct Batch { size_t t0; int ntri; size_t b0; int nblk; };
+  std::vector<Batch> batches;
+  struct Blk { int pq, r, pq2, r2; long long slot; };
+  std::vector<Blk> blks;                             // GEMM blocks of all batches, batch after batch
+  {
+    Batch cur{0, 0, 0, 0};
+    for (size_t t = 0; t < tri.size(); ++t) {
+      TripleDesc& td = tri[t];
+      const bool same_ij = td.i == td.j, same_jk = td.j == td.k;
+      const int need = 1 + (same_ij ? 0 : 1) + (same_jk ? 0 : 1);
+      if (cur.nblk + need > cap_blocks) { batches.push_back(cur); cur = Batch{t, 0, blks.size(), 0}; }
+      const int idx[3] = {td.i, td.j, td.k};
+      td.flags = same_jk ? kCbaFromBac : 0;
+      for (int sidx = 0; sidx < 3; ++sidx) {
+        if (sidx == 1 && same_ij) { td.slot[1] = td.slot[0]; continue; }
+        if (sidx == 2 && same_jk) { td.slot[2] = td.slot[1]; continue; }
+        const int P0 = idx[perm3[sidx][0]], P1 = idx[perm3[sidx][1]], P2 = idx[perm3[sidx][2]];
+        td.slot[sidx] = cur.nblk;
+        blks.push_back({P0 + o * P1, P2, P0 + o * P2, P1, cur.nblk});   // Acat(P0,P1) Bcat(P2) + Acat(P0,P2) BcatT(P1)
+        ++cur.nblk;
+      }
+      ++cur.ntri;
+    }
+    batches.push_back(cur);
+  }
+  const size_t nbatches = batches.size();
+  long long max_blk = 0;
+  for (const Batch& b : batches) max_blk = std::max<long long>(max_blk, b.nblk);
+  Scratch X(e.pool, (size_t)max_blk * v3);
   std::unique_ptr<Scratch> XM;
-  if (do_m) XM.reset(new Scratch(e.pool, (size_t)nb * 3 * v3));
+  if (do_m) XM.reset(new Scratch(e.pool, (size_t)max_blk * v3));
   // unordered label-tile triples A <= B <= C
   const int ntile = (v + TS - 1) / TS;
   std::vector<int> tiles_h;
@@ -476,45 +533,33 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
   AFESP_REQUIRE(ntt < (1LL << 31), "triples: too many label tiles");
   Scratch tiles_d(e.pool, (tiles_h.size() + 1) / 2 + 1);
   AFESP_CUDA_CHECK(cudaMemcpyAsync(tiles_d.p, tiles_h.data(), tiles_h.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  static_assert(sizeof(TripleDesc) == 24, "TripleDesc layout");
-  const size_t nbatches = (tri.size() + nb - 1) / nb;
+  static_assert(sizeof(TripleDesc) == 40, "TripleDesc layout");
   const bool al16 = (v % 2 == 0) && (o % 2 == 0);
-  const int perm3[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 1, 0}};   // s = abc, bac, cba (first three rows of c_perm)
 
   // Launch tables of ALL batches, built on the host and uploaded once (no per-batch synchronisation): the triple
   // descriptors, and per GEMM block the (A pair, B index) of both K segments as block indices (TMA gather form) and as
   // pointers (cp.async fallback).  Within a batch the blocks are sorted by their B blocks so that blocks reading the same
   // (n x v^2) operand block -- 52 MB at nbf=200, 0.4 GB at nbf=400 -- run back to back and find it in L2; each block
-  // still writes its own slot g of the output buffer (the epilogue addresses Y by triple and s).
-  const size_t ngt = tri.size() * 3;                 // GEMM blocks over all batches
+  // still writes its own slot of the output buffer (the epilogue addresses Y through TripleDesc::slot).
+  const size_t ngt = blks.size();                    // GEMM blocks over all batches
   std::vector<int> hidx(ngt * 4);                    // [4][ngt]: Aidx, Bidx, Aidx2, Bidx2
   std::vector<long long> hslot(ngt);                 // output slot within the batch buffer
-  for (size_t bi = 0; bi < nbatches; ++bi) {
-    const size_t t0 = bi * nb;
-    const int cb = (int)std::min<size_t>(nb, tri.size() - t0), ng = cb * 3;
-    std::vector<int> order(ng), k_pq(ng), k_r(ng), k_pq2(ng), k_r2(ng);
-    for (int tb = 0; tb < cb; ++tb) {
-      const TripleDesc& td = tri[t0 + tb];
-      const int idx[3] = {td.i, td.j, td.k};
-      for (int t = 0; t < 3; ++t) {
-        const int g = tb * 3 + t, P0 = idx[perm3[t][0]], P1 = idx[perm3[t][1]], P2 = idx[perm3[t][2]];
-        order[g] = g;
-        k_pq[g] = P0 + o * P1; k_r[g] = P2;      // X_s      : Acat(P0,P1) Bcat(P2)
-        k_pq2[g] = P0 + o * P2; k_r2[g] = P1;    // X_{s+3}^T: Acat(P0,P2) BcatT(P1)
-      }
-    }
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-      return k_r[a] != k_r[b] ? k_r[a] < k_r[b] : k_r2[a] < k_r2[b];
+  for (const Batch& b : batches) {
+    std::vector<int> order(b.nblk);
+    for (int z = 0; z < b.nblk; ++z) order[z] = z;
+    const Blk* bb = blks.data() + b.b0;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+      return bb[x].r != bb[y].r ? bb[x].r < bb[y].r : bb[x].r2 < bb[y].r2;
     });
-    for (int z = 0; z < ng; ++z) {
-      const int g = order[z];
-      const size_t w = t0 * 3 + z;
-      hidx[0 * ngt + w] = k_pq[g]; hidx[1 * ngt + w] = k_r[g];
-      hidx[2 * ngt + w] = k_pq2[g]; hidx[3 * ngt + w] = k_r2[g];
-      hslot[w] = g;
+    for (int z = 0; z < b.nblk; ++z) {
+      const Blk& k = bb[order[z]];
+      const size_t w = b.b0 + z;
+      hidx[0 * ngt + w] = k.pq; hidx[1 * ngt + w] = k.r;
+      hidx[2 * ngt + w] = k.pq2; hidx[3 * ngt + w] = k.r2;
+      hslot[w] = k.slot;
     }
   }
-  Scratch descs(e.pool, tri.size() * 3);             // TripleDesc is 24 bytes = 3 doubles
+  Scratch descs(e.pool, tri.size() * 5);             // TripleDesc is 40 bytes = 5 doubles
   Scratch idx_d(e.pool, ngt * 2 + 2);                // 4 * ngt int32
   AFESP_CUDA_CHECK(cudaMemcpyAsync(descs.p, tri.data(), tri.size() * sizeof(TripleDesc), cudaMemcpyHostToDevice, st));
   AFESP_CUDA_CHECK(cudaMemcpyAsync(idx_d.p, hidx.data(), hidx.size() * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -550,7 +595,7 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
   std::unique_ptr<Scratch> verify_buf, verify_cnt, verify_ptrs;
   double verify_elems = 0.0;
   if (verify_t) {
-    verify_buf.reset(new Scratch(e.pool, (size_t)nb * 3 * v3));
+    verify_buf.reset(new Scratch(e.pool, (size_t)max_blk * v3));
     verify_cnt.reset(new Scratch(e.pool, 2));
     verify_ptrs.reset(new Scratch(e.pool, ngt * 5));
     make_ptrs(sAcat.p, sBcat.p, sBcatT.p, verify_buf->p, *verify_ptrs);
@@ -558,12 +603,11 @@ void triples_spatial(CCState& s, bool paren, bool renorm, bool comp_renorm, int 
   }
   tr.lap(1);
   for (size_t bi = 0; bi < nbatches; ++bi) {
-    const size_t t0 = bi * nb;
-    const int cb = (int)std::min<size_t>(nb, tri.size() - t0);
-    const int ng = cb * 3;
+    const size_t t0 = batches[bi].t0, w0 = batches[bi].b0;
+    const int cb = batches[bi].ntri;
+    const int ng = batches[bi].nblk;
     auto run_gemms = [&](const double* Acat, const double* Bcat, const double* BcatT, const Scratch& ptrs) {
       const double* const* dp = reinterpret_cast<const double* const*>(ptrs.p);
-      const size_t w0 = t0 * 3;
       GemmBatch b1;
       b1.count = ng; b1.Aptr = dp + 0 * ngt + w0; b1.Bptr = dp + 1 * ngt + w0;
       b1.Cptr = (double* const*)(dp + 2 * ngt + w0); b1.ptr_aligned16 = al16;
@@ -663,7 +707,7 @@ void triples_spinorb(CCState& s, int rank, int nranks, double* e_T) {
   Scratch X(e.pool, (size_t)nb * v3);
   const int ntile = (v + TS - 1) / TS;
   const long long blocks_per_triple = (long long)ntile * ntile * ntile;
-  DBuf descs((size_t)nb * 3);
+  DBuf descs((size_t)nb * 5);   // TripleDesc is 40 bytes = 5 doubles
   DevPtrs ptrs;
   ptrs.ensure((size_t)nb * 13);
   const size_t nbatches = (tri.size() + nb - 1) / nb;

@@ -53,6 +53,11 @@ module afesp_gpu
          real(c_double), dimension(*), intent(in) :: eps
          real(c_double), intent(out) :: e_mp2
       end function
+      integer(c_int) function afesp_gpu_ccsd_init_info(h, info) bind(C, name='afesp_gpu_ccsd_init_info')
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: h
+         real(c_double), dimension(4), intent(out) :: info
+      end function
       integer(c_int) function afesp_gpu_ccsd_init(h, nocc, restricted, eps, diis_n, e_mp1, rmst2) &
             bind(C, name='afesp_gpu_ccsd_init')
          import :: c_int, c_ptr, c_double
@@ -172,14 +177,31 @@ contains
       use system, only: system_t
       type(system_t), intent(inout) :: sys
       logical, intent(in) :: restricted
-      real(c_double) :: e, e_old, rms, t1d
+      real(c_double) :: e, e_old, rms, t1d, info(4)
       integer :: iter
+      integer(c_int) :: rc
       integer(kind=8) :: t0, t1, c_rate
       logical :: conv
       write(iunit, '(1X, 10("-"))'); write(iunit, '(1X, A)') 'CCSD'; write(iunit, '(1X, 10("-"))')
       call system_clock(count=t0, count_rate=c_rate)
-      call check(afesp_gpu_ccsd_init(gpu_handle, int(sys%nel/2, c_int), merge(1_c_int, 0_c_int, restricted), &
-                                     sys%canon_levels, int(sys%ccsd_diis_n_errmat, c_int), e, rms), 'ccsd_init')
+      rc = afesp_gpu_ccsd_init(gpu_handle, int(sys%nel/2, c_int), merge(1_c_int, 0_c_int, restricted), &
+                               sys%canon_levels, int(sys%ccsd_diis_n_errmat, c_int), e, rms)
+      if (.not. restricted) then
+         ! src/ccsd.f90:106-202: the slices of <pq||rs> are gathered straight from the packed MO integrals and the
+         ! reference's permutational-symmetry assertion (:150-167) runs on the device; status 5 = it fired
+         if (rc == 0 .or. rc == 5) call check(afesp_gpu_ccsd_init_info(gpu_handle, info), 'ccsd_init_info')
+         write(iunit, '(1X, A)') 'Forming antisymmetrised spinorbital ERIs...'
+         write(iunit, '(1X, A, 1X, F8.6, A)') 'Time taken:', info(2), " s"
+         write(iunit, *)
+         write(iunit, '(1X, A)') 'Checking that the permuational symmetry of the antisymmetrised integrals hold...'
+         if (rc == 5) then
+            write(iunit, '(1X, A, 1X, E15.6)') 'Permutational symmetry error:', info(1)
+            call error('ccsd::do_ccsd', 'Permutational symmetry of antisymmetrised integrals does not hold')
+         end if
+         write(iunit, '(1X, A, 1X, F8.6, A)') 'Time taken:', info(3), " s"
+         write(iunit, *)
+      end if
+      call check(rc, 'ccsd_init')
       write(iunit, '(75("-"))')
       write(iunit, '(1X, A, 3X, A, 3X, A, 3X, A, 3X, A)') &
          'Iteration','     Energy    ','    deltaE     ','  delta RMS T2 ', '  Time  '

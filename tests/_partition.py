@@ -1,4 +1,4 @@
-"""Host-side mirror of the (i,j,k) work deal used by the device code (afesp_b200/csrc/triples.cu: my_triples).
+"""Test-side mirror of the (i,j,k) work deal used by the device code (afesp_b200/csrc/triples.cu: my_triples).
 
 Unique triples i <= j <= k (orbit weights 6/3/1) are enumerated in lexicographic order and dealt round-robin:
 work unit t belongs to rank t % nranks.  Every rank's share is independent; the six (T) sums add across ranks."""

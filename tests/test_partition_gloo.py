@@ -11,7 +11,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from afesp_b200 import AfespGpu, partition, synthetic
+from afesp_b200 import AfespGpu, synthetic
+from tests import _partition as partition
 from oracle import afesp_oracle as orc
 
 
@@ -162,3 +163,59 @@ def test_two_rank_sharded_gemm_and_ao2mo_exchange_match_single_rank():
         assert p.exitcode == 0
     assert gemm_err < 1e-12
     assert ao2mo_err < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# afesp_gpu_set_eri_mo with a communicator (capi.cu): every rank uploads the slice [np*r/R, np*(r+1)/R) of the packed
+# array over its own PCIe link, then each slice is broadcast from its owner -- restated over gloo; and the in-place
+# sharded GEMM with beta (contract.cu: every rank updates ITS column slab of the replicated C in place, beta included,
+# then the slabs are broadcast): all ranks must end with the same, correct matrix.
+def _worker_slices(rank, world, port, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    npk = 1003                                    # not divisible by the world size
+    host = np.arange(npk, dtype=np.float64) * 0.5 + 1.0      # the array every rank can read (shared host copy)
+    dev = np.full(npk, np.nan)                    # this rank's "device" copy
+    ranges = [(npk * r // world, npk * (r + 1) // world) for r in range(world)]
+    lo, hi = ranges[rank]
+    dev[lo:hi] = host[lo:hi]                      # own share only
+    for r, (a, b) in enumerate(ranges):
+        t = torch.from_numpy(dev[a:b].copy())
+        dist.broadcast(t, src=r)
+        dev[a:b] = t.numpy()
+    ok_upload = bool(np.array_equal(dev, host)) and ranges[0][0] == 0 and ranges[-1][1] == npk
+    # column-sharded C = alpha A B + beta C, in place
+    rng = np.random.default_rng(3)
+    M, N, K, alpha, beta = 7, 200, 5, 0.5, -0.25
+    A, B, C0 = rng.standard_normal((M, K)), rng.standard_normal((K, N)), rng.standard_normal((M, N))
+    C = C0.copy()
+    cols = [partition.column_range(N, r, world, 64) for r in range(world)]
+    c0, c1 = cols[rank]
+    C[:, c0:c1] = alpha * A @ B[:, c0:c1] + beta * C[:, c0:c1]
+    for r, (a, b) in enumerate(cols):
+        if b > a:
+            t = torch.from_numpy(np.ascontiguousarray(C[:, a:b]))
+            dist.broadcast(t, src=r)
+            C[:, a:b] = t.numpy()
+    ok_gemm = bool(np.max(np.abs(C - (alpha * A @ B + beta * C0))) < 1e-14)
+    flag = torch.tensor([1.0 if (ok_upload and ok_gemm) else 0.0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out_q.put(float(flag.item()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sliced_upload_and_in_place_sharded_gemm():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_slices, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok == 1.0
