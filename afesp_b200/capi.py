@@ -34,6 +34,8 @@ SIGNATURES = {
     "afesp_gpu_comm_unique_id": [C.c_char_p],
     "afesp_gpu_comm_init": [_H, C.c_int, C.c_int, C.c_char_p],
     "afesp_gpu_set_partition": [_H, C.c_int, C.c_int],
+    "afesp_gpu_host_register": [C.c_void_p, C.c_longlong],
+    "afesp_gpu_host_unregister": [C.c_void_p],
     "afesp_gpu_triples_partition": [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)],
     "afesp_gpu_column_partition": [C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)],
     "afesp_gpu_dgemm_wrapper": [_H, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double],
@@ -262,6 +264,15 @@ class AfespGpu:
     def comm_init(self, rank, nranks, uid: bytes):
         assert len(uid) == 128
         self._check("comm_init", self.lib.afesp_gpu_comm_init(self.h, int(rank), int(nranks), uid))
+
+    @staticmethod
+    def host_register(arr) -> bool:
+        """Page-lock a NumPy array in place (cudaHostRegister); False when the driver refuses."""
+        return load_library().afesp_gpu_host_register(C.c_void_p(arr.ctypes.data), int(arr.nbytes)) == 0
+
+    @staticmethod
+    def host_unregister(arr) -> bool:
+        return load_library().afesp_gpu_host_unregister(C.c_void_p(arr.ctypes.data)) == 0
 
     def set_partition(self, rank, nranks):
         self._check("set_partition", self.lib.afesp_gpu_set_partition(self.h, int(rank), int(nranks)))

@@ -563,6 +563,20 @@ int afesp_gpu_comm_init(afesp_handle hv, int rank, int nranks, const char id[128
   });
 }
 
+int afesp_gpu_host_register(void* ptr, long long bytes) {
+  if (!ptr || bytes <= 0) return 1;
+  const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); return 2; }   // not sticky: the caller falls back to pageable transfers
+  return 0;
+}
+
+int afesp_gpu_host_unregister(void* ptr) {
+  if (!ptr) return 1;
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); return 2; }
+  return 0;
+}
+
 int afesp_gpu_set_partition(afesp_handle hv, int rank, int nranks) {
   return guarded(hv, [&](Handle& h) {
     AFESP_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "set_partition: bad arguments");

@@ -443,9 +443,10 @@ bool gemm_tma_selftest(cudaStream_t st) {
   if (std::getenv("AFESP_TMA_SELFTEST") && std::atoi(std::getenv("AFESP_TMA_SELFTEST")) == 0) { g_selftest_state = 1; return true; }
   const int force0 = gemm_force_config_get();
   struct Case { int M, N, K, batch, reps; double beta; };
-  const Case cases[] = {{64, 4096, 72, 48, 12, 0.0},      // (T)-shaped batch at v = 64, nbf = 72: K tail, 5 k-tiles
-                        {144, 13456, 144, 1, 4, 1.0},     // I_oooo . c with accumulate, edge M tile
-                        {180, 32400, 200, 4, 2, 0.0}};    // (T)-shaped batch of the default bench shape
+  // light guard since the round-2 soak (1.3e11 elements, 0 mismatches): one pass per case instead of 12 / 4 / 2
+  const Case cases[] = {{64, 4096, 72, 48, 2, 0.0},       // (T)-shaped batch at v = 64, nbf = 72: K tail, 5 k-tiles
+                        {144, 13456, 144, 1, 1, 1.0},     // I_oooo . c with accumulate, ragged M tile
+                        {180, 32400, 200, 4, 1, 0.0}};    // (T)-shaped batch of the default bench shape (ragged M, K tail)
   const int scope0 = g_tma_scope;
   unsigned long long total_bad = 0;
   try {

@@ -73,7 +73,7 @@ struct Dist {
   int (*group_end)() = nullptr;
   int (*bcast)(const void* send, void* recv, size_t count, int root, void* comm, cudaStream_t st) = nullptr;  // doubles
   int (*allgather)(const void* send, void* recv, size_t count_per_rank, void* comm, cudaStream_t st) = nullptr;  // doubles
-  bool use_allgather = true;   // sharded GEMMs: equal (padded) slabs + ONE in-place ncclAllGather instead of nranks grouped
+  bool use_allgather = false;  // sharded GEMMs: equal (padded) slabs + ONE in-place ncclAllGather instead of nranks grouped
                                // broadcasts (option "dist_allgather")
   int (*send)(const void* buf, size_t count, int peer, void* comm, cudaStream_t st) = nullptr;
   int (*recv)(void* buf, size_t count, int peer, void* comm, cudaStream_t st) = nullptr;

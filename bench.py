@@ -214,6 +214,8 @@ def run_shape(args, rank, world, local, n, o, steps, warmup, e2e_first=False, wa
         gpu.set_option("gemm_use_tma", args.tma)
     if args.dist_chunks > 0:
         gpu.set_option("dist_overlap_chunks", args.dist_chunks)
+    if os.environ.get("AFESP_DIST_ALLGATHER") is not None:   # A/B aid: 0 = grouped broadcasts, 1 = one all-gather
+        gpu.set_option("dist_allgather", float(os.environ["AFESP_DIST_ALLGATHER"]))
     tma_scope, tma_selftest = gpu.tma_status()
     peak = max(gpu.dmma_peak(), gpu.dmma_peak())
     npair = n * (n + 1) // 2
@@ -230,7 +232,9 @@ def run_shape(args, rank, world, local, n, o, steps, warmup, e2e_first=False, wa
         shm_path = "/dev/shm/afesp_bench_%s_%d.bin" % (os.environ.get("MASTER_PORT", "0"), n)
         try:
             st = os.statvfs("/dev/shm")
-            if st.f_bavail * st.f_frsize > npk * 8 * 1.1:
+            # (arrays above 4 GB stay on the proven path -- one pinned copy on rank 0 + NVLink broadcast: page-locking a
+            #  25.7 GB tmpfs mapping from 8 processes at once is where an nbf=400 run at N=8 stalled)
+            if npk * 8 <= (4 << 30) and st.f_bavail * st.f_frsize > npk * 8 * 1.1:
                 if rank == 0:
                     np.memmap(shm_path, dtype=np.float64, mode="w+", shape=(npk,)).flush()
                 ok = 1.0
@@ -240,18 +244,14 @@ def run_shape(args, rank, world, local, n, o, steps, warmup, e2e_first=False, wa
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if flag.item() > 0.5:
             src = np.memmap(shm_path, dtype=np.float64, mode="r+", shape=(npk,))
-            rc = torch.cuda.cudart().cudaHostRegister(src.ctypes.data, src.nbytes, 0)
-            rc = rc[0] if isinstance(rc, tuple) else rc
-            shm_registered = int(rc) == 0
-            if not shm_registered:
-                torch.cuda.cudart().cudaGetLastError()   # clear the (non-sticky) error
+            shm_registered = AfespGpu.host_register(src)   # False: the driver refused (error cleared inside)
         flag = torch.tensor([1.0 if shm_registered else 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if flag.item() < 0.5:
             # no page-locked shared mapping on this box (small /dev/shm, registration refused): one pinned copy on rank 0,
             # the other ranks receive the integrals over NVLink inside afesp_gpu_set_eri_mo
             if shm_registered:
-                torch.cuda.cudart().cudaHostUnregister(src.ctypes.data)
+                AfespGpu.host_unregister(src)
             shm_registered = False
             src = None
             if rank == 0:
@@ -442,7 +442,7 @@ def run_shape(args, rank, world, local, n, o, steps, warmup, e2e_first=False, wa
     gpu.close()
     if shm_path is not None:
         if shm_registered:
-            torch.cuda.cudart().cudaHostUnregister(src.ctypes.data)
+            AfespGpu.host_unregister(src)
         del src
         barrier()
         if rank == 0:
@@ -463,19 +463,7 @@ def run_ours(args, rank, world, local):
     n, o = args.nbf, args.nocc
     v = n - o
     m = run_shape(args, rank, world, local, n, o, args.steps, args.warmup)
-    target = None
-    if args.target and (n, o) != (400, 40):
-        try:
-            target = run_shape(args, rank, world, local, 400, 40, 1, 0, e2e_first=True, want_hbm=False)
-            if target is not None:
-                target.pop("hbm_kernels", None)
-                if not args.trajectory:
-                    target.pop("trajectory", None)
-                target["config"] = config_of(400, 40)
-                target["note"] = ("BASELINE.json configs[4], the north-star target shape: one e2e pass (which is also the "
-                                  "warm-up), then ONE device-timed step (W=0 after that pass, K=1)")
-        except Exception as ex:   # the target leg must never take the headline line down
-            target = {"error": f"{type(ex).__name__}: {ex}"}
+    line = None
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -502,11 +490,50 @@ def run_ours(args, rank, world, local):
                   "roofline", "e2e", "gpu_launches", "clocks", "tma", "hbm_kernels"):
             line[k] = m[k]
         line["cpu_baseline"] = cpu
-        line["target_config"] = target
+        line["target_config"] = None
         if args.trajectory:
             line["trajectory"] = m["trajectory"]
         if world > 1:
             line["exchange"] = "NCCL slab exchange of the column-sharded CCSD GEMMs; one allreduce of the six (T) sums"
+    # ---- the north-star target shape, once, AFTER the headline measurements are complete.  A watchdog on every rank
+    # guarantees that the headline line is printed even if this leg stalls (several ranks at this shape have had far
+    # less GPU time than the headline shape): at the limit rank 0 prints the line with an error note and all ranks leave.
+    tn, to = (int(x) for x in os.environ.get("AFESP_BENCH_TARGET_SHAPE", "400,40").split(","))   # (tests use a small one)
+    run_target = (args.target == 2 or (args.target == 1 and world == 1)) and (n, o) != (tn, to)
+    if args.target == 1 and world > 1 and line is not None:
+        line["target_config"] = {"skipped": "the nbf=400 target leg runs by default on one GPU only; --target 2 runs it on "
+                                            "every rank count (watchdog-limited)"}
+    if run_target:
+        import threading
+
+        limit = float(os.environ.get("AFESP_BENCH_TARGET_LIMIT_S", "600" if world == 1 else "300"))
+        done = threading.Event()
+
+        def watchdog():
+            if not done.wait(limit):
+                if line is not None:
+                    line["target_config"] = {"error": f"target leg did not finish within {limit:.0f} s: abandoned by the "
+                                                      f"watchdog (headline measurements above are complete)"}
+                    emit(line)
+                os._exit(0)
+
+        threading.Thread(target=watchdog, daemon=True).start()
+        target = None
+        try:
+            target = run_shape(args, rank, world, local, tn, to, 1, 0, e2e_first=True, want_hbm=False)
+            if target is not None:
+                target.pop("hbm_kernels", None)
+                if not args.trajectory:
+                    target.pop("trajectory", None)
+                target["config"] = config_of(tn, to)
+                target["note"] = ("BASELINE.json configs[4], the north-star target shape: one e2e pass (which is also the "
+                                  "warm-up), then ONE device-timed step (W=0 after that pass, K=1)")
+        except Exception as ex:   # the target leg must never take the headline line down
+            target = {"error": f"{type(ex).__name__}: {ex}"}
+        done.set()
+        if line is not None:
+            line["target_config"] = target
+    if line is not None:
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -522,7 +549,8 @@ def main():
     ap.add_argument("--nocc", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--target", type=int, default=int(os.environ.get("AFESP_BENCH_TARGET", "1")),
-                    help="1 (default): also run the nbf=400/nocc=40 target shape once and attach it as target_config")
+                    help="1 (default): on ONE GPU also run the nbf=400/nocc=40 target shape once and attach it as "
+                         "target_config; 2: at every rank count; 0: never")
     ap.add_argument("--trajectory", action="store_true", help="print the per-step (E_CCSD, e_T) list (pinning runs)")
     ap.add_argument("--tma", type=int, default=-1, help="gemm_use_tma: -1 library default (2: TMA-staged kernel for every "
                                                         "aligned GEMM), 1 the (T) batches only, 0 cp.async kernels only")

@@ -129,6 +129,11 @@ int afesp_gpu_ccsd_t_spinorb(afesp_handle h, double* e_T);
  * The 128-byte id comes from rank 0 and is broadcast by the host (MPI, torchrun...). */
 int afesp_gpu_comm_unique_id(char id[128]);
 int afesp_gpu_comm_init(afesp_handle h, int rank, int nranks, const char id[128]);
+/* Page-lock (and release) a host array the caller owns, e.g. int_store%eri_mo or a shared-memory mapping of it, so that
+ * the H2D / D2H copies of afesp_gpu_set_eri_mo / afesp_gpu_ccsd_finalize run at full PCIe speed.  Status 2 = the driver
+ * refused (the array then simply stays pageable); no handle needed, the calling thread's current device is used. */
+int afesp_gpu_host_register(void* ptr, long long bytes);
+int afesp_gpu_host_unregister(void* ptr);
 /* Without NCCL: give the handle a (rank, nranks) share only; the caller sums the partial results itself. */
 int afesp_gpu_set_partition(afesp_handle h, int rank, int nranks);
 /* Host-only: number of (i,j,k) work units per rank (no device needed). */

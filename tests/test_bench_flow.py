@@ -1,0 +1,52 @@
+"""Control flow of bench.py's GPU arm on a CPU-only machine, through tests/_bench_stub.py (a fake engine behind the
+AfespGpu interface): one rank and two ranks (gloo), the shared-memory host copy of the e2e leg, the target leg, and the
+watchdog that must get the headline line out when the target leg stalls.  The numbers mean nothing here; the contract
+keys, the single JSON line and the exit status do."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STUB = os.path.join(ROOT, "tests", "_bench_stub.py")
+KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+        "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "parity", "target_config"]
+
+
+def _run(cmd, env_extra, timeout=300):
+    env = dict(os.environ, AFESP_BENCH_TARGET_SHAPE="40,4", **env_extra)
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[-2000:]
+    return json.loads(lines[0])
+
+
+def test_single_rank_line_with_target_leg():
+    d = _run([sys.executable, STUB, "--gpus", "1", "--steps", "2", "--warmup", "1", "--nbf", "36", "--nocc", "4", "--no-cpu"], {})
+    for k in KEYS:
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["config"]["nbf"] == 36 and d["higher_is_better"] is False
+    assert set(d["config"]) == {"workload", "nbf", "nocc", "calc_type"}       # identical in both arms
+    t = d["target_config"]
+    assert t["config"]["nbf"] == 40 and t["steps"] == 1 and "e2e" in t and "roofline" in t and "parity" in t
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["roofline"]["traffic_source"] is None or "static" in d["roofline"]["traffic_source"]
+
+
+def test_watchdog_emits_the_headline_line_when_the_target_leg_stalls():
+    d = _run([sys.executable, STUB, "--gpus", "1", "--steps", "1", "--warmup", "1", "--nbf", "36", "--nocc", "4", "--no-cpu"],
+             {"AFESP_STUB_STALL": "1", "AFESP_BENCH_TARGET_LIMIT_S": "3"}, timeout=120)
+    assert d["value"] > 0 and "did not finish" in d["target_config"]["error"]
+
+
+def test_two_ranks_gloo_shared_host_copy_and_skipped_target():
+    port = 32500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), STUB, "--gpus", "2", "--steps", "2", "--warmup", "1", "--nbf", "36", "--nocc", "4",
+           "--no-cpu"]
+    d = _run(cmd, {})
+    assert d["n_gpus"] == 2 and "own PCIe link" in d["e2e"]["what"]       # the shared-memory + sliced-upload mode was taken
+    assert "skipped" in d["target_config"] and "exchange" in d
+    d = _run(cmd + ["--target", "2"], {})
+    assert d["target_config"]["config"]["nbf"] == 40 and d["target_config"]["e2e"]["value"] > 0
