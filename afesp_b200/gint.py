@@ -33,6 +33,17 @@ BASIS = {
             (1, [(17.70, 0.043018), (3.854, 0.228913), (1.046, 0.508728)]), (1, [(0.2753, 1.0)]),
             (2, [(1.185, 1.0)])],
     },
+    # Weigend & Ahlrichs 2005.  The reference's `sample_data/h2o-cc-pvdz` files were in fact generated with this basis
+    # (kinetic diagonal of its t.dat: d exponent 1.2, hydrogen p exponent 0.8), see tests/test_gint.py.
+    "def2-svp": {
+        1: [(0, [(13.0107010, 0.19682158e-01), (1.9622572, 0.13796524), (0.44453796, 0.47831935)]),
+            (0, [(0.12194962, 1.0)]), (1, [(0.8, 1.0)])],
+        8: [(0, [(2266.1767785, -0.53431809926e-02), (340.87010191, -0.39890039230e-01), (77.363135167, -0.17853911985),
+                 (21.479644940, -0.46427684959), (6.6589433124, -0.44309745172)]),
+            (0, [(0.80975975668, 1.0)]), (0, [(0.25530772234, 1.0)]),
+            (1, [(17.721504317, 0.43394573193e-01), (3.8635505440, 0.23094120765), (1.0480920883, 0.51375311064)]),
+            (1, [(0.27641544411, 1.0)]), (2, [(1.2, 1.0)])],
+    },
     "cc-pvtz": {
         1: [(0, [(33.87, 0.006068), (5.095, 0.045308), (1.159, 0.202822)]), (0, [(0.3258, 1.0)]), (0, [(0.1027, 1.0)]),
             (1, [(1.407, 1.0)]), (1, [(0.388, 1.0)]), (2, [(1.057, 1.0)])],

@@ -140,7 +140,7 @@ def read_inputs(dirpath) -> ElsInput:
         inp.eri = np.fromfile(bin_path, dtype="<f8")
         if inp.eri.size != npair * (npair + 1) // 2:
             raise ValueError("integrals::read_integrals_in: eri.bin does not hold npair(npair+1)/2 doubles for this basis")
-    else:
+    elif os.path.exists(os.path.join(dirpath, "eri.dat")):
         d = np.loadtxt(os.path.join(dirpath, "eri.dat"), ndmin=2)
         idx = d[:, :4].astype(np.int64) - 1
         eri = np.zeros(npair * (npair + 1) // 2)
@@ -150,6 +150,22 @@ def read_inputs(dirpath) -> ElsInput:
         toks = f.read().split()
     nat = int(toks[0])
     g = np.array(toks[1:1 + 4 * nat], dtype=float).reshape(nat, 4)
+    if inp.eri is None:
+        # extension: no eri.dat (the reference checkout ships none for sample_data/h2o-cc-pvtz).  With
+        # the basis set named -- one-line file basis.dat, or AFESP_BASIS -- the integrals are generated from geom.dat
+        # (afesp_b200/gint.py, Psi4 conventions) and must reproduce the overlap matrix of s.dat.
+        basis = None
+        if os.path.exists(os.path.join(dirpath, "basis.dat")):
+            basis = open(os.path.join(dirpath, "basis.dat")).read().split()[0]
+        basis = basis or os.environ.get("AFESP_BASIS")
+        if not basis:
+            raise FileNotFoundError("integrals::read_integrals_in: cannot open eri.dat")
+        from . import gint
+
+        res = gint.compute(g[:, 0], g[:, 1:], basis)
+        if res["nbf"] != n or np.max(np.abs(res["s"] - inp.ovlp)) > 1e-10:
+            raise ValueError(f"integrals::read_integrals_in: generated overlap matrix differs from s.dat (basis set {basis}?)")
+        inp.eri = res["eri"]
     set_geometry(inp, g[:, 0], g[:, 1:])
     if inp.scf_read_guess:
         inp.guess = read_scf_guess(os.path.join(dirpath, "guess_in.dat"), n)

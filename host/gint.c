@@ -1,7 +1,7 @@
 /* gint.c -- Gaussian one- and two-electron integrals over contracted, real solid-harmonic shells (s, p, d, f).
  *
  * Host-side tool of the drop-in: the reference reads s.dat / t.dat / v.dat / eri.dat produced by
- * Psi4 (tools/generate_integrals.py of the reference tree), and its checkout ships no eri.dat for
+ * Psi4 (utils/psi4_integrals_nosym.py of the reference tree), and its checkout ships no eri.dat for
  * sample_data/h2o-cc-pvtz (listed in .MISSING_LARGE_BLOBS).  This file regenerates all four from geom.dat and the public
  * basis-set parameters, in Psi4's conventions, so that the cc-pVTZ sample can be run: contracted functions normalised to
  * unit self-overlap, pure functions ordered m = 0, +1, -1, +2, -2, ... within a shell (p: z, x, y), shells in basis-file
@@ -381,4 +381,51 @@ int afesp_gint_compute(int natom, const double* Z, const double* xyz, int nshell
   }
   free(nrm); free(sh);
   return nbf;
+}
+
+/* ---- built-in basis sets (host/gint_basis.inc, generated from afesp_b200/gint.py) ------------------------------------
+ * afesp_gint_named: the same computation with the shells looked up by basis-set name ("cc-pvdz", "cc-pvtz", "def2-svp";
+ * H and O), atom by atom in basis-file order -- what the C++ host program uses when a run directory has geom.dat but
+ * no eri.dat.  Smat/Tmat/Vmat/eri may each be NULL (nothing written); returns nbf, -1 for a bad argument, -2 for an
+ * unknown basis / element.  Call with all outputs NULL to learn nbf. */
+#include "gint_basis.inc"
+#include <ctype.h>
+
+static int same_name(const char* a, const char* b) {
+  for (; *a && *b; ++a, ++b)
+    if (tolower((unsigned char)*a) != tolower((unsigned char)*b)) return 0;
+  return *a == *b;
+}
+
+int afesp_gint_named(int natom, const double* Z, const double* xyz, const char* basis, double* Smat, double* Tmat,
+                     double* Vmat, double* eri) {
+  if (natom <= 0 || !Z || !xyz || !basis) return -1;
+  int nshell = 0, nprim = 0, nbf = 0;
+  for (int at = 0; at < natom; ++at) {
+    int found = 0;
+    for (int q = 0; q < basis_table_len; ++q)
+      if (basis_table[q].Z == (int)(Z[at] + 0.5) && same_name(basis_table[q].basis, basis)) {
+        ++nshell; nprim += basis_table[q].nprim; nbf += 2 * basis_table[q].l + 1; found = 1;
+      }
+    if (!found) return -2;
+  }
+  if (!Smat && !Tmat && !Vmat && !eri) return nbf;
+  int* sh_atom = (int*)malloc(sizeof(int) * nshell * 4);
+  int *sh_l = sh_atom + nshell, *sh_np = sh_l + nshell, *sh_off = sh_np + nshell;
+  double* ex = (double*)malloc(sizeof(double) * nprim * 2);
+  double* co = ex + nprim;
+  int s = 0, off = 0;
+  for (int at = 0; at < natom; ++at)
+    for (int q = 0; q < basis_table_len; ++q)
+      if (basis_table[q].Z == (int)(Z[at] + 0.5) && same_name(basis_table[q].basis, basis)) {
+        sh_atom[s] = at; sh_l[s] = basis_table[q].l; sh_np[s] = basis_table[q].nprim; sh_off[s] = off;
+        for (int k = 0; k < basis_table[q].nprim; ++k) { ex[off + k] = basis_table[q].a[k]; co[off + k] = basis_table[q].c[k]; }
+        off += basis_table[q].nprim; ++s;
+      }
+  double* scratch = (double*)calloc((size_t)3 * nbf * nbf, sizeof(double));
+  const int rc = afesp_gint_compute(natom, Z, xyz, nshell, sh_atom, sh_l, sh_np, sh_off, ex, co,
+                                    Smat ? Smat : scratch, Tmat ? Tmat : scratch + (size_t)nbf * nbf,
+                                    Vmat ? Vmat : scratch + (size_t)2 * nbf * nbf, eri);
+  free(scratch); free(ex); free(sh_atom);
+  return rc;
 }

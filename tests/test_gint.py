@@ -68,3 +68,68 @@ def test_regenerated_cc_pvtz_integrals_reproduce_reference_scf(tmp_path):
         assert it == git and abs(e - ge) < 2e-9 and abs(rms - grms) < 2e-9
     assert np.max(np.abs(np.asarray(sysm.eps) - np.array(G["orbital_energies"]))) < 2e-8
     assert abs(sysm.e_hf + sysm.e_nuc - G["final"]["RHF energy"]) < 2e-9   # table energies are electronic; the final table adds E_nuc
+
+
+def _write_tz_dir(path, calc_type="RHF", with_basis_file=True):
+    """The reference checkout's sample_data/h2o-cc-pvtz directory as shipped: els.in, geom.dat, s/t/v.dat -- and NO eri.dat."""
+    import re
+
+    z = np.load(os.path.join(GOLDEN_DIR, "h2o_tz.npz"))
+    text = re.sub(r'calc_type\s*=\s*"[^"]*"', f'calc_type="{calc_type}"', str(z["els_in"]))
+    (path / "els.in").write_text(text)
+    with open(path / "geom.dat", "w") as f:
+        f.write("%d\n" % len(z["geom"]))
+        for row in z["geom"]:
+            f.write("%d\t%.15f\t%.15f\t%.15f\n" % (int(row[0]), row[1], row[2], row[3]))
+    n = z["ovlp"].shape[0]
+    for name, key in (("s.dat", "ovlp"), ("t.dat", "ke"), ("v.dat", "en")):
+        with open(path / name, "w") as f:
+            for i in range(n):
+                for j in range(i + 1):
+                    f.write("%d\t%d\t%.15f\n" % (i + 1, j + 1, z[key][i, j]))
+    if with_basis_file:
+        (path / "basis.dat").write_text("cc-pvtz\n")
+
+
+def test_hosts_run_the_cc_pvtz_directory_without_eri_dat(tmp_path):
+    """Both host programs take the run directory as the reference checkout ships it (no eri.dat), generate the two-electron
+    integrals from geom.dat once the basis set is named (basis.dat / AFESP_BASIS), and print the reference's 22 SCF
+    iterations of els_cpu.out.  RHF level only here (no GPU needed); the GPU suite runs the whole CCSD(T)."""
+    import subprocess
+
+    from afesp_b200 import host
+    from tests._fixtures import els_host_binary
+
+    G = golden()["h2o_tz"]
+    _write_tz_dir(tmp_path)
+    r = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rows = [ln.split() for ln in r.stdout.splitlines() if len(ln.split()) == 5 and ln.split()[0].isdigit()]
+    assert len(rows) == len(G["scf"]) == 22
+    for row, (git, ge, _, grms) in zip(rows, G["scf"]):
+        assert int(row[0]) == git and abs(float(row[1]) - ge) < 2e-9 and abs(float(row[3]) - grms) < 2e-9
+    # the whole SCF section (header, 22-line table, 58 orbital energies) is the reference's text, number by number
+    from tests._fixtures import compare_els_out
+
+    ref = open(os.path.join(GOLDEN_DIR, "h2o_tz_els_cpu_out.txt")).read().replace('calc_type="CCSD(T)_spinorb"',
+                                                                                   'calc_type="RHF"').splitlines()
+    stop = next(i for i, ln in enumerate(ref) if ln.startswith(" Time taken for restricted Hartree-Fock")) + 1
+    diffs = compare_els_out("\n".join(r.stdout.splitlines()[:stop]), "\n".join(ref[:stop]), ulps=1.0)
+    # (the reference printed spin-orbital counts for its CCSD(T)_spinorb run; an RHF run prints the spatial ones)
+    assert [d for d in diffs if "occupied orbitals" not in d and "virtual orbitals" not in d] == []
+    # Python host: same directory
+    inp = host.read_inputs(str(tmp_path))
+    assert inp.nbasis == 58 and inp.eri is not None
+    e_hf, _, eps, table, conv = host.rhf(inp)
+    assert conv and len(table) == 22 and abs(table[-1][1] - G["scf"][-1][1]) < 2e-9
+    # without a named basis the reference's own error stays
+    os.remove(tmp_path / "basis.dat")
+    r = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "cannot open eri.dat" in r.stderr
+    r = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, AFESP_BASIS="cc-pVTZ"))
+    assert r.returncode == 0
+    # a wrong basis is caught by the overlap check against s.dat
+    r = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=60,
+                       env=dict(os.environ, AFESP_BASIS="cc-pvdz"))
+    assert r.returncode != 0 and "does not match s.dat" in r.stderr
