@@ -260,7 +260,7 @@ int afesp_gpu_set_option(afesp_handle hv, const char* key, double value) {
       if ((int)value > 0) gemm_tma_selftest(h.s.eng.stream);
       gemm_tma_scope((int)value);
     }
-    else if (k == "dist_allgather") h.s.eng.dist.use_allgather = value != 0.0;
+    else if (k == "dist_allgather") h.s.eng.dist.use_allgather = value < 0.0 ? -1 : (value != 0.0 ? 1 : 0);
     else if (k == "dist_overlap_chunks") h.s.eng.dist.overlap_chunks = std::max(1, std::min(8, (int)value));
     else if (k == "dist_min_flops") h.s.eng.dist.min_flops = value;   // GEMMs below this stay replicated
     else if (k == "dist_ccsd") {   // 0: replicate CCSD / AO->MO, shard only (T)

@@ -135,7 +135,7 @@ void dgemm_sharded(Engine& e, char ta, char tb, int M, int N, int K, double alph
   }
   const bool tB = (tb == 'T' || tb == 't');
   int nch = std::max(1, std::min(d.overlap_chunks, 8));
-  if (nch == 1 && d.use_allgather && d.allgather) {
+  if (nch == 1 && d.allgather_on() && d.allgather) {
     // Equal slabs of `per` columns (the col_range unit, padded past N on the last ranks) in a scratch matrix
     // G(M x per*nranks): every rank computes its slab straight into its place (beta: its columns of C are copied in
     // first), ONE in-place ncclAllGather moves all slabs, and the N valid columns are copied back into C.

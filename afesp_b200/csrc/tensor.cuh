@@ -73,8 +73,10 @@ struct Dist {
   int (*group_end)() = nullptr;
   int (*bcast)(const void* send, void* recv, size_t count, int root, void* comm, cudaStream_t st) = nullptr;  // doubles
   int (*allgather)(const void* send, void* recv, size_t count_per_rank, void* comm, cudaStream_t st) = nullptr;  // doubles
-  bool use_allgather = false;  // sharded GEMMs: equal (padded) slabs + ONE in-place ncclAllGather instead of nranks grouped
-                               // broadcasts (option "dist_allgather")
+  int use_allgather = -1;      // sharded GEMMs: equal (padded) slabs + ONE in-place ncclAllGather instead of nranks grouped
+                               // broadcasts.  -1 (default) = from 8 ranks on (measured: same speed at 2 ranks, 16.4 ms per
+                               // CCSD iteration at 8 ranks, nbf=200), 0 / 1 = never / always (option "dist_allgather")
+  bool allgather_on() const { return use_allgather < 0 ? nranks >= 8 : use_allgather != 0; }
   int (*send)(const void* buf, size_t count, int peer, void* comm, cudaStream_t st) = nullptr;
   int (*recv)(void* buf, size_t count, int peer, void* comm, cudaStream_t st) = nullptr;
   double min_flops = 4e9;   // GEMMs below this stay replicated (exchange latency would dominate)

@@ -125,7 +125,9 @@ int afesp_gpu_ccsd_t_spinorb(afesp_handle h, double* e_T);
  * the (+/-)-symmetrised <ef|ab> ladder integrals -- and the computed slabs are exchanged over NVLink (grouped
  * ncclBroadcast; ncclSend/ncclRecv all-to-all between the two AO->MO half transforms).  Every call that touches the
  * communicator (ao2mo, ccsd_init, ccsd_iterate, ccsd_finalize, ccsd_t_*) is collective: all ranks make it with the
- * same arguments.  Options: "dist_ccsd" (1/0, default 1) and "dist_min_flops" (GEMMs below stay replicated).
+ * same arguments.  Options: "dist_ccsd" (1/0, default 1), "dist_min_flops" (GEMMs below stay replicated),
+ * "dist_allgather" (-1 default: one in-place ncclAllGather of padded equal slabs from 8 ranks on, grouped broadcasts
+ * below; 0 / 1 force) and "dist_overlap_chunks" (default 1: serial compute / exchange).
  * The 128-byte id comes from rank 0 and is broadcast by the host (MPI, torchrun...). */
 int afesp_gpu_comm_unique_id(char id[128]);
 int afesp_gpu_comm_init(afesp_handle h, int rank, int nranks, const char id[128]);
