@@ -24,6 +24,8 @@ SO = os.path.join(os.path.dirname(HERE), "host", "libafesp_gint.so")
 # element -> list of shells (l, [(exponent, coefficient), ...]); general contractions are listed as separate shells.
 _O_S_DZ = [11720.0, 1759.0, 400.8, 113.7, 37.03, 13.27, 5.025, 1.013]
 _O_S_TZ = [15330.0, 2299.0, 522.4, 147.3, 47.55, 16.76, 6.207, 0.6882]
+_N_S_DZ = [9046.0, 1357.0, 309.3, 87.73, 28.56, 10.21, 3.838, 0.7466]
+_F_S_DZ = [14710.0, 2207.0, 502.8, 142.6, 46.47, 16.70, 6.356, 1.316]
 BASIS = {
     "cc-pvdz": {
         1: [(0, [(13.01, 0.019685), (1.962, 0.137977), (0.4446, 0.478148)]), (0, [(0.122, 1.0)]), (1, [(0.727, 1.0)])],
@@ -32,6 +34,17 @@ BASIS = {
             (0, [(0.3023, 1.0)]),
             (1, [(17.70, 0.043018), (3.854, 0.228913), (1.046, 0.508728)]), (1, [(0.2753, 1.0)]),
             (2, [(1.185, 1.0)])],
+        # nitrogen and fluorine: reproduce every shipped integral of sample_data/n2-cc-pvdz and f2-cc-pvdz (tests/test_gint.py)
+        7: [(0, list(zip(_N_S_DZ, [0.000700, 0.005389, 0.027406, 0.103207, 0.278723, 0.448540, 0.278238, 0.015440]))),
+            (0, list(zip(_N_S_DZ, [-0.000153, -0.001208, -0.005992, -0.024544, -0.067459, -0.158078, -0.121831, 0.549003]))),
+            (0, [(0.2248, 1.0)]),
+            (1, [(13.55, 0.039919), (2.917, 0.217169), (0.7973, 0.510319)]), (1, [(0.2185, 1.0)]),
+            (2, [(0.817, 1.0)])],
+        9: [(0, list(zip(_F_S_DZ, [0.000721, 0.005553, 0.028267, 0.106444, 0.286814, 0.448641, 0.264761, 0.015333]))),
+            (0, list(zip(_F_S_DZ, [-0.000165, -0.001308, -0.006495, -0.026691, -0.073690, -0.170776, -0.112327, 0.562814]))),
+            (0, [(0.3897, 1.0)]),
+            (1, [(22.67, 0.044878), (4.977, 0.235718), (1.347, 0.508521)]), (1, [(0.3471, 1.0)]),
+            (2, [(1.640, 1.0)])],
     },
     # Weigend & Ahlrichs 2005.  The reference's `sample_data/h2o-cc-pvdz` files were in fact generated with this basis
     # (kinetic diagonal of its t.dat: d exponent 1.2, hydrogen p exponent 0.8), see tests/test_gint.py.

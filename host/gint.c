@@ -385,8 +385,8 @@ int afesp_gint_compute(int natom, const double* Z, const double* xyz, int nshell
 
 /* ---- built-in basis sets (host/gint_basis.inc, generated from afesp_b200/gint.py) ------------------------------------
  * afesp_gint_named: the same computation with the shells looked up by basis-set name ("cc-pvdz", "cc-pvtz", "def2-svp";
- * H and O), atom by atom in basis-file order -- what the C++ host program uses when a run directory has geom.dat but
- * no eri.dat.  Smat/Tmat/Vmat/eri may each be NULL (nothing written); returns nbf, -1 for a bad argument, -2 for an
+ * H and O; cc-pvdz also N and F), atom by atom in basis-file order -- what the C++ host program uses when a run directory
+ * has geom.dat but no eri.dat.  Smat/Tmat/Vmat/eri may each be NULL (nothing written); returns nbf, -1 for a bad argument, -2 for an
  * unknown basis / element.  Call with all outputs NULL to learn nbf. */
 #include "gint_basis.inc"
 #include <ctype.h>

@@ -5,6 +5,7 @@ files the reference ships (produced by Psi4, utils/psi4_integrals_nosym.py of th
     one-electron matrices are reproduced to 1e-13 (58 functions, s to f shells);
   * sample_data/h2o-cc-pvdz (whose files were in fact generated with def2-SVP: d exponent 1.2, H p exponent 0.8): s, t, v
     AND all 45150 packed two-electron integrals are reproduced to 1e-13;
+  * sample_data/n2-cc-pvdz and f2-cc-pvdz (true cc-pVDZ): s, t, v and all 82621 packed two-electron integrals to 2e-13;
   * the regenerated cc-pVTZ integrals, through the oracle's RHF, give the 22-iteration SCF table, the orbital energies and
     the RHF energy of the reference's own els_cpu.out.
 """
@@ -46,6 +47,34 @@ def test_all_integrals_match_shipped_h2o_dz_sample():
         assert np.max(np.abs(r[key] - ref)) < 1e-13, key
     # 8-fold packed order and the text writer: eri.dat lines are (i j k l value) in canonical order
     assert r["eri"].shape == z["eri"].shape
+
+
+def test_all_integrals_match_shipped_n2_and_f2_samples():
+    """sample_data/n2-cc-pvdz and f2-cc-pvdz (28 functions each, true cc-pVDZ: d exponents 0.817 / 1.640): s, t, v and all
+    82621 packed two-electron integrals from the built-in nitrogen and fluorine tables."""
+    for name in ("n2", "f2"):
+        z = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
+        r = gint.compute(z["geom"][:, 0], z["geom"][:, 1:], "cc-pvdz")
+        assert r["nbf"] == 28 and r["eri"].shape == z["eri"].shape == (82621,)
+        for key, ref in (("s", z["ovlp"]), ("t", z["ke"]), ("v", z["en"]), ("eri", z["eri"])):
+            assert np.max(np.abs(r[key] - ref)) < 2e-13, (name, key)
+
+
+def test_host_runs_the_f2_directory_without_eri_dat(tmp_path):
+    """The C++ host on the reference's F2 directory with eri.dat removed and the basis named: the SCF section of the
+    reference's els.out, number by number (generated integrals instead of Psi4's)."""
+    import subprocess
+
+    from tests._fixtures import compare_els_out, els_host_binary, golden_els_out, write_sample_dir
+
+    write_sample_dir("f2", str(tmp_path), calc_type="RHF")
+    os.remove(tmp_path / "eri.dat")
+    r = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, AFESP_BASIS="cc-pVDZ"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = golden_els_out("f2").replace('calc_type="CRCCSD(T)_spatial"', 'calc_type="RHF"').splitlines()
+    stop = next(i for i, ln in enumerate(ref) if ln.startswith(" Time taken for restricted Hartree-Fock")) + 1
+    assert compare_els_out("\n".join(r.stdout.splitlines()[:stop]), "\n".join(ref[:stop]), ulps=1.0) == []
 
 
 def test_regenerated_cc_pvtz_integrals_reproduce_reference_scf(tmp_path):
