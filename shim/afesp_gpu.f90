@@ -108,6 +108,146 @@ module afesp_gpu
          integer(c_int), value :: rank, nranks
          character(kind=c_char), dimension(128), intent(in) :: id
       end function
+      ! ---- the remaining exports of include/afesp_gpu.h (a host that keeps more of the work, measurement, multi-GPU without
+      !      NCCL); tests/test_shim_interfaces.py checks every interface of this block against the C prototypes
+      integer(c_int) function afesp_gpu_tma_status(h, scope, selftest) bind(C, name='afesp_gpu_tma_status')
+         import :: c_int, c_ptr
+         type(c_ptr), value :: h
+         integer(c_int), intent(out) :: scope, selftest
+      end function
+      integer(c_int) function afesp_gpu_counters(h, launches, gemm_flops) bind(C, name='afesp_gpu_counters')
+         import :: c_int, c_ptr, c_long_long, c_double
+         type(c_ptr), value :: h
+         integer(c_long_long), intent(out) :: launches
+         real(c_double), intent(out) :: gemm_flops
+      end function
+      integer(c_int) function afesp_gpu_synth_eri_ao(h, nbasis, naux, factors, coeff) bind(C, name='afesp_gpu_synth_eri_ao')
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: h
+         integer(c_int), value :: nbasis, naux
+         real(c_double), dimension(*), intent(in) :: factors, coeff
+      end function
+      integer(c_int) function afesp_gpu_get_eri_mo(h, eri_mo) bind(C, name='afesp_gpu_get_eri_mo')
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: h
+         real(c_double), dimension(*), intent(out) :: eri_mo
+      end function
+      integer(c_int) function afesp_gpu_release(h, what) bind(C, name='afesp_gpu_release')
+         import :: c_int, c_ptr, c_char
+         type(c_ptr), value :: h
+         character(kind=c_char), dimension(*), intent(in) :: what
+      end function
+      integer(c_int) function afesp_gpu_set_eri_mo(h, nbasis, eri_mo) bind(C, name='afesp_gpu_set_eri_mo')
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: h
+         integer(c_int), value :: nbasis
+         real(c_double), dimension(*), intent(in) :: eri_mo
+      end function
+      integer(c_int) function afesp_gpu_host_register(ptr, bytes) bind(C, name='afesp_gpu_host_register')
+         import :: c_int, c_ptr, c_long_long
+         type(c_ptr), value :: ptr          ! c_loc(int_store%eri_mo)
+         integer(c_long_long), value :: bytes
+      end function
+      integer(c_int) function afesp_gpu_host_unregister(ptr) bind(C, name='afesp_gpu_host_unregister')
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ptr
+      end function
+      integer(c_int) function afesp_gpu_set_partition(h, rank, nranks) bind(C, name='afesp_gpu_set_partition')
+         import :: c_int, c_ptr
+         type(c_ptr), value :: h
+         integer(c_int), value :: rank, nranks
+      end function
+      integer(c_int) function afesp_gpu_triples_partition(nocc_active, symmetric, strict, nranks, counts) &
+            bind(C, name='afesp_gpu_triples_partition')
+         import :: c_int, c_long_long
+         integer(c_int), value :: nocc_active, symmetric, strict, nranks
+         integer(c_long_long), dimension(*), intent(out) :: counts
+      end function
+      integer(c_int) function afesp_gpu_column_partition(ncols, nranks, granularity, lo, hi) &
+            bind(C, name='afesp_gpu_column_partition')
+         import :: c_int, c_long_long
+         integer(c_long_long), value :: ncols
+         integer(c_int), value :: nranks, granularity
+         integer(c_long_long), dimension(*), intent(out) :: lo, hi
+      end function
+      ! the operators of src/linalg.fpp on host arrays (dgemm_wrapper :58-89, omp_reshape :99-156)
+      integer(c_int) function afesp_gpu_dgemm_wrapper(h, transA, transB, outer_row, outer_col, inner_dim, A, B, C, alpha, beta) &
+            bind(C, name='afesp_gpu_dgemm_wrapper')
+         import :: c_int, c_ptr, c_char, c_double
+         type(c_ptr), value :: h
+         character(kind=c_char), value :: transA, transB
+         integer(c_int), value :: outer_row, outer_col, inner_dim
+         real(c_double), dimension(*), intent(in) :: A, B
+         real(c_double), dimension(*), intent(inout) :: C
+         real(c_double), value :: alpha, beta
+      end function
+      integer(c_int) function afesp_gpu_omp_reshape(h, out_arr, in_arr, in_dims, arr_order, has_beta, beta) &
+            bind(C, name='afesp_gpu_omp_reshape')
+         import :: c_int, c_ptr, c_char, c_double
+         type(c_ptr), value :: h
+         real(c_double), dimension(*), intent(inout) :: out_arr
+         real(c_double), dimension(*), intent(in) :: in_arr
+         integer(c_int), dimension(4), intent(in) :: in_dims
+         character(kind=c_char), dimension(4), intent(in) :: arr_order
+         integer(c_int), value :: has_beta
+         real(c_double), value :: beta
+      end function
+      ! measurement aids (bench.py uses them through ctypes)
+      integer(c_int) function afesp_gpu_bench_dgemm(h, transA, transB, M, N, K, beta, reps, ms) &
+            bind(C, name='afesp_gpu_bench_dgemm')
+         import :: c_int, c_ptr, c_char, c_double
+         type(c_ptr), value :: h
+         character(kind=c_char), value :: transA, transB
+         integer(c_int), value :: M, N, K
+         real(c_double), value :: beta
+         integer(c_int), value :: reps
+         real(c_double), intent(out) :: ms
+      end function
+      integer(c_int) function afesp_gpu_bench_hbm(h, what, nocc, nvirt, reps, ms, bytes) bind(C, name='afesp_gpu_bench_hbm')
+         import :: c_int, c_ptr, c_char, c_double
+         type(c_ptr), value :: h
+         character(kind=c_char), dimension(*), intent(in) :: what
+         integer(c_int), value :: nocc, nvirt, reps
+         real(c_double), intent(out) :: ms, bytes
+      end function
+      integer(c_int) function afesp_gpu_gemm_crosscheck(h, transA, transB, M, N, K, nbatch, beta, reps, mismatches, ms_tma, &
+            ms_cpasync) bind(C, name='afesp_gpu_gemm_crosscheck')
+         import :: c_int, c_ptr, c_char, c_double, c_long_long
+         type(c_ptr), value :: h
+         character(kind=c_char), value :: transA, transB
+         integer(c_int), value :: M, N, K, nbatch
+         real(c_double), value :: beta
+         integer(c_int), value :: reps
+         integer(c_long_long), intent(out) :: mismatches
+         real(c_double), intent(out) :: ms_tma, ms_cpasync
+      end function
+      integer(c_int) function afesp_gpu_dmma_peak(h, tflops) bind(C, name='afesp_gpu_dmma_peak')
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: h
+         real(c_double), intent(out) :: tflops
+      end function
+      integer(c_int) function afesp_gpu_last_stage_ms(h, ms) bind(C, name='afesp_gpu_last_stage_ms')
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: h
+         real(c_double), intent(out) :: ms
+      end function
+      integer(c_int) function afesp_gpu_timer(h, stop, ms) bind(C, name='afesp_gpu_timer')
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: h
+         integer(c_int), value :: stop
+         real(c_double), intent(out) :: ms
+      end function
+      integer(c_int) function afesp_gpu_gemm_time(h, ms, flops) bind(C, name='afesp_gpu_gemm_time')
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: h
+         real(c_double), intent(out) :: ms, flops
+      end function
+      integer(c_int) function afesp_gpu_gemm_stats(h, ms, flops, launches) bind(C, name='afesp_gpu_gemm_stats')
+         import :: c_int, c_ptr, c_double, c_long_long
+         type(c_ptr), value :: h
+         real(c_double), intent(out) :: ms, flops
+         integer(c_long_long), intent(out) :: launches
+      end function
    end interface
 
 contains
