@@ -359,7 +359,8 @@ def ccsd_loop(gpu: AfespGpu, nocc, restricted, eps, e_tol, t_tol, diis_n, maxite
             out.write(" Forming slices of antisymmetrised spinorbital ERIs\n Time taken: %8.6f s\n\n" % 0.0)
             out.write(" Initialise CC intermediate tensors and DIIS auxilliary arrays...\n"
                       " Forming energy denominator matrices...\n Allocating amplitude tensors...\n"
-                      " Forming initial amplitude guesses...\n Allocating stored intermediate tensors...\n")
+                      " Forming ERI slices...\n Forming initial amplitude guesses...\n"
+                      " Allocating stored intermediate tensors...\n")
         out.write(" Time taken: %8.6f s\n\n" % (time.perf_counter() - t_init))
         out.write(" Initialisation done, now entering iterative CC solver...\n")
         out.write("-" * 75 + "\n Iteration        Energy           deltaE          delta RMS T2      Time  \n" + "-" * 75 + "\n")
@@ -466,8 +467,9 @@ def run(inp: ElsInput, gpu: AfespGpu | None = None, device: int = 0, verbose: bo
                 gpu.close()
     out.write(final_table(inp, res))
     now = time.localtime()
-    out.write(" " + "=" * 64 + "\n Finished running on %02d/%02d/%04d at %02d:%02d:%02d\n\n" % (
+    out.write(" " + "=" * 64 + "\n Finished running on %02d/%02d/%04d at %02d:%02d:%02d\n" % (
         now.tm_mday, now.tm_mon, now.tm_year, now.tm_hour, now.tm_min, now.tm_sec))
+    out.write(" Total execution time: %16.8f\n" % (time.perf_counter() - t_glob))   # src/main.F90:185
     res.stdout = out.getvalue()
     if verbose:
         print(res.stdout)
@@ -493,6 +495,10 @@ def header_block(inp: ElsInput, when=None) -> str:
     """Program banner, integral read-in log, system information and the echo of els.in
     (src/main.F90:26-32, src/integrals.f90:75-163, 223-249), byte for byte apart from the date."""
     when = when or time.localtime()
+    if CALC_TYPES[inp.calc_type][1]:   # src/geometry.f90:40-46: spatial orbitals when restricted, spin-orbitals otherwise
+        nocc_print, nvirt_print = inp.nel // 2, inp.nbasis - inp.nel // 2
+    else:
+        nocc_print, nvirt_print = inp.nel, (inp.nbasis - inp.nel // 2) * 2
     L = [" " + "=" * 64, " A Fortran Electronic Structure Programme (AFESP)", " " + "=" * 64,
          " Started running on %02d/%02d/%04d at %02d:%02d:%02d" % (when.tm_mday, when.tm_mon, when.tm_year, when.tm_hour,
                                                                     when.tm_min, when.tm_sec),
@@ -502,8 +508,7 @@ def header_block(inp: ElsInput, when=None) -> str:
          " Reading two-body integrals...", " Done reading integrals!",
          " " + "-" * 20, " System information", " " + "-" * 20,
          " Number of electrons: %d" % inp.nel, " Number of basis functions: %d" % inp.nbasis,
-         " Number of occupied orbitals: %d" % (inp.nel // 2),
-         " Number of virtual orbitals: %d" % (inp.nbasis - inp.nel // 2),
+         " Number of occupied orbitals: %d" % nocc_print, " Number of virtual orbitals: %d" % nvirt_print,
          " E_nuc: " + _es_f(inp.e_nuc, 15, 8),
          " scf_e_tol: " + _es_f(inp.scf_e_tol, 8, 2), " scf_d_tol: " + _es_f(inp.scf_d_tol, 8, 2),
          " ccsd_e_tol: " + _es_f(inp.ccsd_e_tol, 8, 2), " ccsd_t_tol: " + _es_f(inp.ccsd_t_tol, 8, 2),
@@ -518,7 +523,8 @@ def header_block(inp: ElsInput, when=None) -> str:
 
 
 def _taken(label, seconds):
-    return " Time taken for %s: %7.4fs\n" % (label, seconds)
+    """'(1X, A, 1X, F16.8, A)' of src/main.F90:43-115 (the shipped N2/F2 logs predate it and print F7.4)."""
+    return " Time taken for %s: %16.8fs\n" % (label, seconds)
 
 
 def triples_calcname(paren, renorm, comp_renorm):

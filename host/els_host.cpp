@@ -492,7 +492,8 @@ void stamp(const char* what) {
               tmv.tm_hour, tmv.tm_min, tmv.tm_sec);
 }
 
-void taken(const std::string& label, double s) { std::printf(" Time taken for %s: %7.4fs\n", label.c_str(), s); }
+// '(1X, A, 1X, F16.8, A)' of src/main.F90:43-115 (the shipped N2/F2 logs predate it and print F7.4)
+void taken(const std::string& label, double s) { std::printf(" Time taken for %s: %16.8fs\n", label.c_str(), s); }
 std::string bar(int n, char c) { return std::string(n, c); }
 
 }  // namespace
@@ -525,7 +526,8 @@ int main(int argc, char** argv) {
               " ccsd_t_tol: %8.2E\n Number of SCF DIIS error matrices: %d\n Number of CCSD DIIS error matrices: %d\n"
               " Maximum number of SCF iterations: %d\n Maximum number of CCSD iterations: %d\n"
               " Printing out the input file...\n%s\n",
-              s.nel, n, nocc, n - nocc, s.e_nuc, s.scf_e_tol, s.scf_d_tol, s.ccsd_e_tol, s.ccsd_t_tol,
+              s.nel, n, s.restricted ? nocc : s.nel, s.restricted ? n - nocc : 2 * (n - nocc),   // src/geometry.f90:40-46
+              s.e_nuc, s.scf_e_tol, s.scf_d_tol, s.ccsd_e_tol, s.ccsd_t_tol,
               s.scf_diis_n_errmat, s.ccsd_diis_n_errmat, s.scf_maxiter, s.ccsd_maxiter, bar(30, '-').c_str());
   {
     std::istringstream in(s.els_in_text);
@@ -628,8 +630,7 @@ int main(int argc, char** argv) {
     check("ccsd_init", rc_init);
     std::printf(" Initialise CC intermediate tensors and DIIS auxilliary arrays...\n Forming energy denominator matrices...\n"
                 " Allocating amplitude tensors...\n");
-    if (s.restricted) std::printf(" Forming ERI slices...\n");
-    std::printf(" Forming initial amplitude guesses...\n Allocating stored intermediate tensors...\n");
+    std::printf(" Forming ERI slices...\n Forming initial amplitude guesses...\n Allocating stored intermediate tensors...\n");  // :477-526, both formulations
     std::printf(" Time taken: %8.6f s\n\n Initialisation done, now entering iterative CC solver...\n", since(ti));
     std::printf("%s\n Iteration        Energy           deltaE          delta RMS T2      Time  \n%s\n", bar(75, '-').c_str(),
                 bar(75, '-').c_str());
@@ -732,7 +733,6 @@ int main(int argc, char** argv) {
   line("Total energy:", e_hf + highest + s.e_nuc);
   std::printf(" %s\n", bar(64, '=').c_str());
   stamp("Finished");
-  std::printf("\n");
-  (void)t_glob;
+  std::printf(" Total execution time: %16.8f\n", since(t_glob));   // src/main.F90:185
   return 0;
 }

@@ -93,7 +93,7 @@ def _mask(line):
     line = line.rstrip()
     if re.match(r"^ (Started|Finished) running on ", line):
         return line.split(" on ")[0] + " on <date>"
-    if line.startswith(" Time taken"):
+    if line.startswith(" Time taken") or line.startswith(" Total execution time:"):
         return line.split(":")[0] + ": <time>"
     m = re.match(r"^(\s+\d+(?:\s+-?\d+\.\d+){3})\s+\d+\.\d+$", line)   # iteration row: last column is a time
     return m.group(1) if m else line
@@ -105,6 +105,10 @@ def compare_els_out(mine, ref, ulps=2.0, abs_tol=0.0):
     1e-9 Eh energy tolerance of the north star, for the 12-decimal CCSD table), whichever is larger.  Returns a list
     of differences (empty = same)."""
     a, b = [_mask(x) for x in mine.splitlines()], [_mask(x) for x in ref.splitlines()]
+    # the shipped N2/F2 logs (08/03/2022) end with a blank line where the checkout's main.F90:185 -- and the cc-pVTZ logs
+    # written one day later -- print 'Total execution time:': that one line is allowed to differ in this way only
+    if a and b and a[-1].startswith(" Total execution time:") and b[-1] == "":
+        a, b = a[:-1], b[:-1]
     diffs = []
     if len(a) != len(b):
         diffs.append(f"line count {len(a)} != {len(b)}")

@@ -146,6 +146,16 @@ def test_hosts_run_the_cc_pvtz_directory_without_eri_dat(tmp_path):
     diffs = compare_els_out("\n".join(r.stdout.splitlines()[:stop]), "\n".join(ref[:stop]), ulps=1.0)
     # (the reference printed spin-orbital counts for its CCSD(T)_spinorb run; an RHF run prints the spatial ones)
     assert [d for d in diffs if "occupied orbitals" not in d and "virtual orbitals" not in d] == []
+    # with the shipped calc_type the system block counts spin-orbitals (src/geometry.f90:40-46): the header up to the first
+    # time line is then the reference's text without exception (the run itself needs a GPU from MP2 on)
+    sub = tmp_path / "spinorb"
+    sub.mkdir()
+    _write_tz_dir(sub, calc_type="CCSD(T)_spinorb")
+    r2 = subprocess.run([els_host_binary(), str(sub)], capture_output=True, text=True, timeout=600)
+    ref2 = open(os.path.join(GOLDEN_DIR, "h2o_tz_els_cpu_out.txt")).read().splitlines()
+    stop2 = next(i for i, ln in enumerate(ref2) if ln.startswith(" Time taken for system initialisation")) + 1
+    assert compare_els_out("\n".join(r2.stdout.splitlines()[:stop2]), "\n".join(ref2[:stop2]), ulps=0.0) == []
+    assert " Number of occupied orbitals: 10" in r2.stdout and " Number of virtual orbitals: 106" in r2.stdout
     # Python host: same directory
     inp = host.read_inputs(str(tmp_path))
     assert inp.nbasis == 58 and inp.eri is not None

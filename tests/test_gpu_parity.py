@@ -455,3 +455,26 @@ def test_handle_and_state_guards(gpu):
         assert "finalised" in str(ei.value)
     finally:
         gpu.set_option("finalize_keep_ccsd", 0)
+
+
+# ---------------------------------------------------------------- whole-program spin-orbital output (kept last in this file)
+def test_whole_program_h2o_cc_pvtz_output_matches_els_cpu_out(gpu, tmp_path):
+    """Both hosts on the reference's cc-pVTZ water directory as shipped (no eri.dat; integrals generated on the fly) with
+    the shipped calc_type CCSD(T)_spinorb: the complete program output against the reference's own els_cpu.out line by
+    line (dates / times masked, numbers within 2 units of the last printed digit or 1e-9 Eh).  The CPU suite runs the same
+    comparison for the Python host over the oracle-backed test double (tests/test_host_program_flow.py)."""
+    import subprocess
+
+    from afesp_b200 import host
+    from tests._fixtures import GOLDEN_DIR, compare_els_out, els_host_binary
+    from tests.test_gint import _write_tz_dir
+
+    ref = open(os.path.join(GOLDEN_DIR, "h2o_tz_els_cpu_out.txt")).read()
+    res = host.run(load_els_input("h2o_tz", "CCSD(T)_spinorb"), gpu=gpu)
+    diffs = compare_els_out(res.stdout, ref, ulps=2.0, abs_tol=E_TOL)
+    assert diffs == [], "\n".join(diffs[:20])
+    _write_tz_dir(tmp_path, calc_type="CCSD(T)_spinorb")
+    r = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    diffs = compare_els_out(r.stdout, ref, ulps=2.0, abs_tol=E_TOL)
+    assert diffs == [], "\n".join(diffs[:20])

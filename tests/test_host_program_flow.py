@@ -129,3 +129,23 @@ def test_spin_orbital_program_flow(runs, oracle_runs):
     block = res.stdout.split(" Final energy breakdown\n", 1)[1]
     assert "CCSD[T]" not in block and "T1 diagnostic" not in block and " CCSD(T) energy:" in block
     assert eng.calls[-2:] == ["ccsd_finalize", "ccsd_t_spinorb"]
+
+
+def test_whole_program_spin_orbital_output_matches_the_reference_els_cpu_out(runs):
+    """sample_data/h2o-cc-pvtz/2.00_104.45/els_cpu.out (current code version, CCSD(T)_spinorb, 116 spin-orbitals; two-electron
+    integrals regenerated by afesp_b200/gint.py): every line of the program output -- the spin-orbital counts of the system
+    block (src/geometry.f90:40-46), the banners of src/ccsd.f90:106-220, the 19-row iteration table, E[CCSD(T)], the
+    unrestricted final block and the 'Total execution time' line -- with numbers within 2 units of the last printed digit
+    or 1e-9 Eh.  About 40 s."""
+    import os
+
+    from tests._fixtures import GOLDEN_DIR
+
+    inp, eng, res = runs("h2o_tz", "CCSD(T)_spinorb")
+    ref = open(os.path.join(GOLDEN_DIR, "h2o_tz_els_cpu_out.txt")).read()
+    diffs = compare_els_out(res.stdout, ref, ulps=2.0, abs_tol=1e-9)
+    assert not diffs, "\n".join(diffs[:20])
+    assert " Number of occupied orbitals: 10\n Number of virtual orbitals: 106\n" in res.stdout
+    assert res.stdout.rstrip().splitlines()[-1].startswith(" Total execution time:")
+    mine, want = _wrapper_energies(res.stdout), _wrapper_energies(ref)
+    assert want[4] < 0 and np.max(np.abs(mine - want)) < 1e-9
