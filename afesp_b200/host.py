@@ -340,7 +340,7 @@ def ccsd_loop(gpu: AfespGpu, nocc, restricted, eps, e_tol, t_tol, diis_n, maxite
             info = gpu.ccsd_init_info()
             out.write(" Forming antisymmetrised spinorbital ERIs...\n Time taken: %8.6f s\n\n" % info["slices_s"])
             out.write(" Checking that the permuational symmetry of the antisymmetrised integrals hold...\n")
-            out.write(" Permutational symmetry error: %15.6E\n" % info["symmetry_error"])
+            out.write(" Permutational symmetry error: %s\n" % _e_f(info["symmetry_error"], 15, 6))   # E15.6, :165
         raise
     table = [("MP1", e, e - 0.0, rms)]
     if out is not None:
@@ -484,6 +484,19 @@ def highest_energy(en, paren, renorm, comp_renorm):
         if comp_renorm:
             key = "e_crccsd_tt" if paren else "e_crccsd_t"
     return en[key]
+
+
+def _e_f(x, width, digits):
+    """Fortran Ew.d: mantissa in [0.1, 1), e.g. E15.6 of 3.5e-7 is '   0.350000E-06' (C's %E would print 3.500000E-07)."""
+    if x == 0.0 or not np.isfinite(x):
+        mant, ex = (0.0 if x == 0.0 else x), 0
+    else:
+        ex = int(np.floor(np.log10(abs(x)))) + 1
+        mant = x / 10.0 ** ex
+        if abs(float("%.*f" % (digits, mant))) >= 1.0:   # rounding carried into the leading digit
+            ex += 1
+            mant = x / 10.0 ** ex
+    return ("%.*fE%+03d" % (digits, mant, ex)).rjust(width)
 
 
 def _es_f(x, width, digits):

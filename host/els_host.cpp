@@ -495,6 +495,23 @@ void stamp(const char* what) {
 // '(1X, A, 1X, F16.8, A)' of src/main.F90:43-115 (the shipped N2/F2 logs predate it and print F7.4)
 void taken(const std::string& label, double s) { std::printf(" Time taken for %s: %16.8fs\n", label.c_str(), s); }
 std::string bar(int n, char c) { return std::string(n, c); }
+// Fortran Ew.d: mantissa in [0.1, 1), e.g. E15.6 of 3.5e-7 is "   0.350000E-06" (C's %E would print 3.500000E-07)
+std::string fortran_e(double x, int width, int digits) {
+  int ex = 0;
+  double mant = x;
+  if (x != 0.0 && std::isfinite(x)) {
+    ex = (int)std::floor(std::log10(std::fabs(x))) + 1;
+    mant = x / std::pow(10.0, ex);
+    char probe[64];
+    std::snprintf(probe, sizeof probe, "%.*f", digits, mant);
+    if (std::fabs(std::atof(probe)) >= 1.0) { ++ex; mant = x / std::pow(10.0, ex); }   // rounding carried into the leading digit
+  }
+  char buf[96];
+  std::snprintf(buf, sizeof buf, "%.*fE%+03d", digits, mant, ex);
+  std::string out(buf);
+  if ((int)out.size() < width) out.insert(0, (size_t)width - out.size(), ' ');
+  return out;
+}
 
 }  // namespace
 
@@ -619,7 +636,7 @@ int main(int argc, char** argv) {
       if (rc_init == 5) {
         std::printf(" Forming antisymmetrised spinorbital ERIs...\n Time taken: %8.6f s\n\n", info[1]);
         std::printf(" Checking that the permuational symmetry of the antisymmetrised integrals hold...\n");
-        std::printf(" Permutational symmetry error: %15.6E\n", info[0]);
+        std::printf(" Permutational symmetry error: %s\n", fortran_e(info[0], 15, 6).c_str());   // E15.6, src/ccsd.f90:165
         fail("ccsd::do_ccsd", "Permutational symmetry of antisymmetrised integrals does not hold");
       }
       check("ccsd_init", rc_init);

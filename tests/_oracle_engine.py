@@ -13,8 +13,9 @@ from oracle import afesp_oracle as orc
 
 
 class OracleEngine:
-    def __init__(self, q1=True, q3a=True, q3b=True):
+    def __init__(self, q1=True, q3a=True, q3b=True, force_symmetry_error=0.0):
         self.q1, self.q3a, self.q3b = q1, q3a, q3b
+        self.force_symmetry_error = force_symmetry_error   # > 0: ccsd_init fails the way the library's status 5 does
         self.calls = []          # the order in which the host drove the engine (asserted by the tests)
         self.eri_mo = None
         self.n = 0
@@ -61,6 +62,11 @@ class OracleEngine:
         else:
             asym = orc.spinorb_antisym(self.eri_mo, self.n)
             self.sym_err = orc.spinorb_symmetry_error(asym)
+            if self.force_symmetry_error > 0:
+                from afesp_b200.capi import AfespError
+
+                self.sym_err = self.force_symmetry_error
+                raise AfespError("ccsd_init", 5, "Permutational symmetry of antisymmetrised integrals does not hold")
             self.G = orc.spinorb_slices(asym, 2 * self.nocc)
             self.eps_so = np.repeat(self.eps, 2)
             self.D1, self.D2 = orc.denominators(self.eps_so, 2 * self.nocc)

@@ -149,3 +149,18 @@ def test_whole_program_spin_orbital_output_matches_the_reference_els_cpu_out(run
     assert res.stdout.rstrip().splitlines()[-1].startswith(" Total execution time:")
     mine, want = _wrapper_energies(res.stdout), _wrapper_energies(ref)
     assert want[4] < 0 and np.max(np.abs(mine - want)) < 1e-9
+
+
+def test_symmetry_assertion_block_is_printed_in_the_reference_format():
+    """Status 5 from ccsd_init: the banners, then 'Permutational symmetry error:' in Fortran E15.6 (mantissa in [0.1,1):
+    0.350000E-06, not C's 3.500000E-07), nothing after it (src/ccsd.f90:161-167); the exception carries the output so far."""
+    from afesp_b200.capi import AfespError
+
+    inp = load_els_input("h2o", "CCSD_spinorb")
+    with pytest.raises(AfespError) as ei:
+        host.run(inp, gpu=OracleEngine(force_symmetry_error=3.5e-7))
+    assert ei.value.code == 5
+    tail = ei.value.stdout.splitlines()[-4:]
+    assert tail[0].startswith(" Time taken:") and tail[1] == ""
+    assert tail[2] == " Checking that the permuational symmetry of the antisymmetrised integrals hold..."
+    assert tail[3] == " Permutational symmetry error:    0.350000E-06"
