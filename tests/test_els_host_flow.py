@@ -108,3 +108,32 @@ def test_els_host_and_python_host_print_the_same_program_output(double_env, calc
     res = host.run(inp, gpu=OracleEngine())
     diffs = compare_els_out(r.stdout, res.stdout, ulps=1.0, abs_tol=1e-10)
     assert diffs == [], "\n".join(diffs[:20])
+
+
+def test_els_host_writes_the_fcidump_the_python_writer_writes(double_env, tmp_path):
+    """write_fcidump = .true. (src/mp2.f90:451-487): the file els_host writes from the MO integrals the engine returns is the
+    file the Python writer produces from the oracle's transform (sign freedom of the eigenvectors aside), and the two
+    banner lines are printed around it."""
+    import re
+
+    from afesp_b200 import host
+    from oracle import afesp_oracle as orc
+    from tests._fixtures import load_els_input
+
+    text = write_sample_dir("h2o", str(tmp_path), calc_type="MP2_spatial")
+    text = re.sub(r"write_fcidump\s*=\s*\.false\.", "write_fcidump = .true.", text)
+    assert "write_fcidump = .true." in text
+    (tmp_path / "els.in").write_text(text)
+    r = _run(double_env, tmp_path)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = r.stdout.splitlines()
+    k = out.index(" Writing FCIDUMP file...")
+    assert out[k + 1] == " Done writing FCIDUMP file!" and out[k - 1].startswith(" MP2 correlation energy (Hartree):")
+    inp = load_els_input("h2o", "MP2_spatial")
+    _, C, eps, _, conv = host.rhf(inp)
+    ref_path = tmp_path / "FCIDUMP.ref"
+    host.write_fcidump(str(ref_path), orc.ao2mo_packed(inp.eri, C), inp.nbasis)
+    mine, ref = (tmp_path / "FCIDUMP").read_text().splitlines(), ref_path.read_text().splitlines()
+    key = lambda ln: (ln[:12], round(abs(float(ln[12:])), 7))
+    big = lambda lines: {key(ln) for ln in lines if abs(float(ln[12:])) > 1e-5}
+    assert len(big(ref)) > 1000 and big(mine) == big(ref)
