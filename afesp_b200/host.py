@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import io
 import os
+import re
 import time
 from dataclasses import dataclass, field
 
@@ -87,25 +88,68 @@ def pair_index(i, j):
     return hi * (hi + 1) // 2 + lo
 
 
+NAMELIST_KEYS = {"calc_type": str, "scf_e_tol": float, "scf_d_tol": float, "ccsd_e_tol": float, "ccsd_t_tol": float,
+                 "scf_diis_n_errmat": int, "ccsd_diis_n_errmat": int, "scf_maxiter": int, "ccsd_maxiter": int,
+                 "write_fcidump": bool, "scf_read_guess": bool, "scf_write_guess": bool}   # src/system.f90:96-97
+
+
 def parse_namelist(text):
-    out = {}
+    """`read(unit=ir, nml=elsinput)` of src/system.f90:105 with Fortran namelist rules: the group starts at `&elsinput` (any
+    case) and ends at the first `/` outside a string; `!` starts a comment; assignments are separated by commas, blanks or
+    line ends (several may share a line); names are case-insensitive; logicals are .true./.t./t... ; reals may carry a `d`
+    exponent.  Anything the compiler's runtime would refuse (no group, unknown name, malformed value) raises the
+    reference's error text (:107)."""
+    def bad():
+        return ValueError("system::read_system_in: invalid input file format!")
+
+    # strip comments (outside quotes) and find the group
+    body, quote = [], None
     for raw in text.splitlines():
-        line = raw.strip()
-        if not line or line[0] in "&/" or "=" not in line:
-            continue
-        k, v = [s.strip() for s in line.split("=", 1)]
-        v = v.rstrip(",").strip()
-        if v[:1] in "\"'":
-            out[k] = v.strip("\"'")
-        elif v.lower() in (".true.", ".t.", "t"):
-            out[k] = True
-        elif v.lower() in (".false.", ".f.", "f"):
-            out[k] = False
-        else:
-            try:
+        line = []
+        for ch in raw:
+            if quote:
+                if ch == quote:
+                    quote = None
+            elif ch in "\"'":
+                quote = ch
+            elif ch == "!":
+                break
+            line.append(ch)
+        body.append("".join(line))
+    flat = "\n".join(body)
+    m = re.search(r"&elsinput\b", flat, flags=re.I)
+    if not m:
+        raise bad()
+    rest, out, pos = flat[m.end():], {}, 0
+    tok = re.compile(r"\s*(?:,\s*)?(?:(/|&end\b)|([A-Za-z_]\w*)\s*=\s*(\"[^\"]*\"|'[^']*'|[^,\s/!]+))", flags=re.I)
+    while True:
+        t = tok.match(rest, pos)
+        if not t:
+            if rest[pos:].strip(" \t\r\n,") == "":
+                raise bad()   # group never closed
+            raise bad()
+        pos = t.end()
+        if t.group(1):
+            break
+        k, v = t.group(2).lower(), t.group(3)
+        kind = NAMELIST_KEYS.get(k)
+        if kind is None:
+            raise bad()
+        try:
+            if kind is str:
+                out[k] = v[1:-1] if v[:1] in "\"'" else v
+                out[k] = out[k].strip()
+            elif kind is bool:
+                w = v.lower().lstrip(".")
+                if w[:1] not in "tf":
+                    raise bad()
+                out[k] = w[0] == "t"
+            elif kind is int:
                 out[k] = int(v)
-            except ValueError:
+            else:
                 out[k] = float(v.lower().replace("d", "e"))
+        except ValueError:
+            raise bad() from None
     return out
 
 

@@ -17,6 +17,7 @@
 //
 // Everything from the AO->MO transform on runs on the GPU through the C ABI; there is no CPU fallback.
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -102,49 +103,95 @@ void read_system_in(Sys& s) {
   std::stringstream ss;
   ss << f.rdbuf();
   s.els_in_text = ss.str();
-  std::istringstream in(s.els_in_text);
-  std::string raw;
-  bool opened = false;
-  while (std::getline(in, raw)) {
-    std::string line = trim(raw);
-    if (line.empty()) continue;
-    if (line[0] == '&') { opened = lower(line).rfind("&elsinput", 0) == 0; continue; }
-    if (line[0] == '/') break;
-    size_t eq = line.find('=');
-    if (eq == std::string::npos) fail("system::read_system_in", "invalid input file format!");
-    std::string k = lower(trim(line.substr(0, eq))), v = trim(line.substr(eq + 1));
-    while (!v.empty() && v.back() == ',') v.pop_back();
-    v = trim(v);
-    auto as_bool = [&](const std::string& x) {
-      std::string y = lower(x);
-      if (y == ".true." || y == ".t." || y == "t") return true;
-      if (y == ".false." || y == ".f." || y == "f") return false;
-      fail("system::read_system_in", "invalid input file format!");
-    };
-    auto as_real = [&](std::string x) {
-      for (char& c : x) if (c == 'd' || c == 'D') c = 'e';
-      char* end = nullptr;
-      double r = std::strtod(x.c_str(), &end);
-      if (end == x.c_str()) fail("system::read_system_in", "invalid input file format!");
-      return r;
-    };
-    if (k == "calc_type") {
-      if (v.size() >= 2 && (v[0] == '"' || v[0] == '\'')) v = v.substr(1, v.size() - 2);
-      s.calc_type = trim(v);
-    } else if (k == "scf_e_tol") s.scf_e_tol = as_real(v);
+  // `read(unit=ir, nml=elsinput)` (src/system.f90:105) with Fortran namelist rules: the group starts at `&elsinput` (any
+  // case) and ends at the first `/` outside a string; `!` starts a comment; assignments are separated by commas, blanks
+  // or line ends; names are case-insensitive.  Whatever the runtime would refuse is the reference's error (:107).
+  auto bad = [&]() { fail("system::read_system_in", "invalid input file format!"); };
+  std::string flat;
+  {
+    char quote = 0;
+    bool comment = false;
+    for (char ch : s.els_in_text) {
+      if (ch == '\n') { comment = false; flat.push_back(ch); continue; }
+      if (comment) continue;
+      if (quote) { if (ch == quote) quote = 0; }
+      else if (ch == '"' || ch == '\'') quote = ch;
+      else if (ch == '!') { comment = true; continue; }
+      flat.push_back(ch);
+    }
+  }
+  const std::string lo = lower(flat);
+  size_t pos = lo.find("&elsinput");
+  if (pos == std::string::npos) bad();
+  pos += 9;
+  if (pos < lo.size() && (std::isalnum((unsigned char)lo[pos]) || lo[pos] == '_')) bad();
+  auto skip_sep = [&]() {
+    bool comma = false;
+    while (pos < flat.size() && (std::isspace((unsigned char)flat[pos]) || (flat[pos] == ',' && !comma))) {
+      if (flat[pos] == ',') comma = true;
+      ++pos;
+    }
+  };
+  auto as_bool = [&](const std::string& x) {
+    std::string y = lower(x);
+    while (!y.empty() && y[0] == '.') y.erase(0, 1);
+    if (y.empty() || (y[0] != 't' && y[0] != 'f')) bad();
+    return y[0] == 't';
+  };
+  auto as_real = [&](std::string x) {
+    for (char& c : x) if (c == 'd' || c == 'D') c = 'e';
+    char* end = nullptr;
+    double r = std::strtod(x.c_str(), &end);
+    if (end == x.c_str() || *end != 0) bad();
+    return r;
+  };
+  auto as_int = [&](const std::string& x) {
+    char* end = nullptr;
+    long r = std::strtol(x.c_str(), &end, 10);
+    if (end == x.c_str() || *end != 0) bad();
+    return (int)r;
+  };
+  bool closed = false;
+  while (!closed) {
+    skip_sep();
+    if (pos >= flat.size()) bad();   // group never closed
+    if (flat[pos] == '/') { closed = true; break; }
+    if (lo.compare(pos, 4, "&end") == 0) { closed = true; break; }
+    size_t k0 = pos;
+    while (pos < flat.size() && (std::isalnum((unsigned char)flat[pos]) || flat[pos] == '_')) ++pos;
+    if (pos == k0) bad();
+    const std::string k = lo.substr(k0, pos - k0);
+    while (pos < flat.size() && std::isspace((unsigned char)flat[pos])) ++pos;
+    if (pos >= flat.size() || flat[pos] != '=') bad();
+    ++pos;
+    while (pos < flat.size() && std::isspace((unsigned char)flat[pos])) ++pos;
+    std::string v;
+    if (pos < flat.size() && (flat[pos] == '"' || flat[pos] == '\'')) {
+      const char q = flat[pos++];
+      size_t e = flat.find(q, pos);
+      if (e == std::string::npos) bad();
+      v = flat.substr(pos, e - pos);
+      pos = e + 1;
+    } else {
+      size_t v0 = pos;
+      while (pos < flat.size() && !std::isspace((unsigned char)flat[pos]) && flat[pos] != ',' && flat[pos] != '/') ++pos;
+      v = flat.substr(v0, pos - v0);
+      if (v.empty()) bad();
+    }
+    if (k == "calc_type") s.calc_type = trim(v);
+    else if (k == "scf_e_tol") s.scf_e_tol = as_real(v);
     else if (k == "scf_d_tol") s.scf_d_tol = as_real(v);
     else if (k == "ccsd_e_tol") s.ccsd_e_tol = as_real(v);
     else if (k == "ccsd_t_tol") s.ccsd_t_tol = as_real(v);
-    else if (k == "scf_diis_n_errmat") s.scf_diis_n_errmat = (int)as_real(v);
-    else if (k == "ccsd_diis_n_errmat") s.ccsd_diis_n_errmat = (int)as_real(v);
-    else if (k == "scf_maxiter") s.scf_maxiter = (int)as_real(v);
-    else if (k == "ccsd_maxiter") s.ccsd_maxiter = (int)as_real(v);
+    else if (k == "scf_diis_n_errmat") s.scf_diis_n_errmat = as_int(v);
+    else if (k == "ccsd_diis_n_errmat") s.ccsd_diis_n_errmat = as_int(v);
+    else if (k == "scf_maxiter") s.scf_maxiter = as_int(v);
+    else if (k == "ccsd_maxiter") s.ccsd_maxiter = as_int(v);
     else if (k == "write_fcidump") s.write_fcidump = as_bool(v);
     else if (k == "scf_read_guess") s.scf_read_guess = as_bool(v);
     else if (k == "scf_write_guess") s.scf_write_guess = as_bool(v);
-    else fail("system::read_system_in", "invalid input file format!");
+    else bad();
   }
-  if (!opened) fail("system::read_system_in", "invalid input file format!");
   set_calc_type(s);
 }
 

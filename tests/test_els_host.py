@@ -67,3 +67,48 @@ def test_binary_packed_integrals_are_read_by_both_hosts(tmp_path):
     z["eri"][:-3].astype("<f8").tofile(str(tmp_path / "eri.bin"))
     r3 = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=60)
     assert r3.returncode != 0 and "eri.bin" in r3.stderr
+
+
+NAMELIST_CASES = [
+    # (els.in text, expected (calc_type, scf_maxiter, scf_e_tol) or None = the reference's 'invalid input file format!')
+    ('&elsinput\ncalc_type="RHF",\nscf_e_tol=1e-6,\nscf_maxiter = 77,\n/\n', ("RHF", 77, 1e-6)),
+    # several assignments per line, upper case, single quotes, d exponent, comments, text after the closing slash
+    ("! header comment\n &ELSINPUT CALC_TYPE = 'RHF' SCF_E_TOL=1d-8, scf_maxiter=5 ! trailing\n write_fcidump=T /\n junk = 1\n",
+     ("RHF", 5, 1e-8)),
+    ('&elsinput calc_type="RHF" scf_maxiter=3 /', ("RHF", 3, None)),
+    ('&elsinput\ncalc_type="RHF"\nscf_read_guess = .FALSE.\nscf_write_guess=.f.\n&end\n', ("RHF", None, None)),
+    ('calc_type="RHF"\n/\n', None),                         # no group
+    ('&elsinput\ncalc_type="RHF",\nbogus_key=1\n/\n', None),  # not a member of the namelist
+    ('&elsinput\ncalc_type="RHF",\nscf_maxiter=many\n/\n', None),
+    ('&elsinput\ncalc_type="RHF",\nscf_maxiter=5\n', None),   # group never closed
+]
+
+
+def test_namelist_reader_follows_fortran_rules_in_both_hosts(tmp_path):
+    """`read(unit=ir, nml=elsinput)` (src/system.f90:96-107): what a Fortran runtime accepts is accepted by both hosts with
+    the same values, what it refuses stops both with 'invalid input file format!'."""
+    import re
+
+    from afesp_b200 import host
+
+    write_sample_dir("f2", str(tmp_path), calc_type="RHF")
+    for text, want in NAMELIST_CASES:
+        (tmp_path / "els.in").write_text(text)
+        r = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=300)
+        if want is None:
+            assert r.returncode != 0 and "invalid input file format!" in r.stderr, text
+            try:
+                host.parse_namelist(text)
+                raise AssertionError("the Python host accepted: " + text)
+            except ValueError as ex:
+                assert "invalid input file format!" in str(ex)
+            continue
+        assert r.returncode == 0, (text, r.stderr)
+        got = host.parse_namelist(text)
+        assert got["calc_type"] == want[0]
+        if want[1] is not None:
+            assert got["scf_maxiter"] == want[1]
+            assert re.search(r"Maximum number of SCF iterations: %d\n" % want[1], r.stdout)
+        if want[2] is not None:
+            assert got["scf_e_tol"] == want[2]
+            assert (" scf_e_tol: %8.2E" % want[2]) in r.stdout
