@@ -1,12 +1,14 @@
 // Energy / convergence quantities and CC-DIIS shared by the spin-free and spin-orbital drivers.
+#include <algorithm>
 #include <cmath>
+#include <vector>
 
 #include "ccsd.cuh"
 
 namespace afesp {
 
 void CCDiis::init(int nerr_, int o, int v) {
-  AFESP_REQUIRE(nerr_ <= 8, "CC-DIIS: at most 8 error vectors are supported (ccsd_diis_n_errmat <= 8)");
+  AFESP_REQUIRE(nerr_ >= 0 && nerr_ <= 64, "CC-DIIS: ccsd_diis_n_errmat must lie in 0..64");   // (2 x nerr amplitude-sized arrays)
   nerr = nerr_;
   use = nerr >= 2;  // src/ccsd.f90:593-595
   slot = 0; n_active = 0;
@@ -92,18 +94,22 @@ void cc_diis_update(CCState& s) {
   AFESP_CUDA_CHECK(cudaMemcpyAsync(d.e2[k].p(), s.t2.p(), n2 * 8, cudaMemcpyDeviceToDevice, st));
   axpby(st, n1, -1.0, d.t1_s.p(), 1.0, d.e1[k].p());
   axpby(st, n2, -1.0, d.t2_s.p(), 1.0, d.e2[k].p());
-  // new row of B: e_k . e_j for all active j
-  const double* p1[8]; const double* p2[8];
-  AFESP_REQUIRE(n <= 8, "CC-DIIS supports at most 8 error vectors");
+  // new row of B: e_k . e_j for all active j (the reduction kernel takes up to 8 vectors per pass; the reference's usual
+  // depth of 8 is one pass, deeper histories take ceil(n/8))
+  const int npad = ((std::max(n, 1) + 7) / 8) * 8;
+  std::vector<const double*> p1(npad, nullptr), p2(npad, nullptr);
   for (int j = 0; j < n; ++j) { p1[j] = d.e1[j].p(); p2[j] = d.e2[j].p(); }
-  if (s.red_out.n < 16) s.red_out.alloc(16);
-  dotn(s.eng, n1, n, p1, d.e1[k].p(), s.red_out.p);
-  dotn(s.eng, n2, n, p2, d.e2[k].p(), s.red_out.p + 8);
-  double h[16];
-  AFESP_CUDA_CHECK(cudaMemcpyAsync(h, s.red_out.p, 16 * 8, cudaMemcpyDeviceToHost, st));
+  if (s.red_out.n < (size_t)std::max(16, 2 * npad)) s.red_out.alloc((size_t)std::max(16, 2 * npad));
+  for (int j0 = 0; j0 < n; j0 += 8) {
+    const int nx = std::min(8, n - j0);
+    dotn(s.eng, n1, nx, p1.data() + j0, d.e1[k].p(), s.red_out.p + j0);
+    dotn(s.eng, n2, nx, p2.data() + j0, d.e2[k].p(), s.red_out.p + npad + j0);
+  }
+  std::vector<double> h((size_t)2 * npad, 0.0);
+  AFESP_CUDA_CHECK(cudaMemcpyAsync(h.data(), s.red_out.p, (size_t)2 * npad * 8, cudaMemcpyDeviceToHost, st));
   AFESP_CUDA_CHECK(cudaStreamSynchronize(st));
   for (int j = 0; j < n; ++j) {
-    double val = h[j] + h[8 + j];
+    double val = h[j] + h[npad + j];
     d.B[(size_t)k * d.nerr + j] = val;
     d.B[(size_t)j * d.nerr + k] = val;
   }
@@ -115,10 +121,15 @@ void cc_diis_update(CCState& s) {
   rhs[n] = -1.0;
   if (!solve_dense(A, rhs, m)) throw Error(3, "ccsd::update_diis_cc: Linear solve failed!");
   // T <- sum_i c_i T_i
-  const double* q1[8]; const double* q2[8];
+  std::vector<const double*> q1(npad, nullptr), q2(npad, nullptr);
   for (int j = 0; j < n; ++j) { q1[j] = d.t1[j].p(); q2[j] = d.t2[j].p(); }
-  lincomb(st, n1, n, q1, rhs.data(), s.t1.p());
-  lincomb(st, n2, n, q2, rhs.data(), s.t2.p());
+  const int n_first = std::min(8, n);
+  lincomb(st, n1, n_first, q1.data(), rhs.data(), s.t1.p());
+  lincomb(st, n2, n_first, q2.data(), rhs.data(), s.t2.p());
+  for (int j = 8; j < n; ++j) {   // histories deeper than 8: the remaining terms are accumulated one by one
+    axpby(st, n1, rhs[j], q1[j], 1.0, s.t1.p());
+    axpby(st, n2, rhs[j], q2[j], 1.0, s.t2.p());
+  }
 }
 
 double cc_t1_norm2(CCState& s) {

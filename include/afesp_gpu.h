@@ -87,7 +87,8 @@ int afesp_gpu_mp2_energy(afesp_handle h, int nocc, const double* eps, double* e_
 
 /* CCSD: replaces do_ccsd_spatial (src/ccsd.f90:279-402) / do_ccsd_spinorb (src/ccsd.f90:71-277) ----------------- */
 /* init_cc + init_diis_cc_t + the first update_cc_energy: returns the "MP1" line (energy, sum dT2^2).
- * nocc = number of doubly occupied spatial orbitals (sys%nel/2) in both formulations. */
+ * nocc = number of doubly occupied spatial orbitals (sys%nel/2) in both formulations.  diis_n_errmat = sys%ccsd_diis_n_errmat,
+ * 0..64 (< 2 switches DIIS off as src/ccsd.f90:593-595 does; the history costs 2 x diis_n_errmat amplitude-sized arrays). */
 int afesp_gpu_ccsd_init(afesp_handle h, int nocc, int restricted, const double* eps, int diis_n_errmat,
                         double* e_mp1, double* rmst2);
 /* Spin-orbital integral preparation inside afesp_gpu_ccsd_init (restricted == 0), src/ccsd.f90:106-202: the nine

@@ -420,8 +420,8 @@ def test_synthetic_chain_matches_oracle_and_device_generated_integrals(gpu):
 
 # ---------------------------------------------------------------- handle / state guards
 def test_handle_and_state_guards(gpu):
-    """One handle per device and process; DIIS is refused on a finalised state and with more than 8 error vectors
-    (status codes, not crashes)."""
+    """One handle per device and process; DIIS is refused on a finalised state and with an absurd history depth (status
+    codes, not crashes)."""
     from afesp_b200 import AfespGpu, synthetic
     from afesp_b200.capi import AfespError
 
@@ -432,8 +432,8 @@ def test_handle_and_state_guards(gpu):
     eri, Cm, eps = synthetic.make(n, o, seed=2)
     gpu.ao2mo(n, eri, Cm, want_result=False)
     with pytest.raises(AfespError) as ei:
-        gpu.ccsd_init(o, True, eps, 9)
-    assert "at most 8 error vectors" in str(ei.value)
+        gpu.ccsd_init(o, True, eps, 65)
+    assert "ccsd_diis_n_errmat must lie in 0..64" in str(ei.value)
     gpu.ccsd_init(o, True, eps, 8)
     gpu.ccsd_iterate()
     gpu.ccsd_diis()
@@ -455,6 +455,24 @@ def test_handle_and_state_guards(gpu):
         assert "finalised" in str(ei.value)
     finally:
         gpu.set_option("finalize_keep_ccsd", 0)
+
+
+def test_diis_history_deeper_than_eight_matches_oracle(gpu):
+    """ccsd_diis_n_errmat is free in the reference (src/ccsd.f90:577-615 allocates n_errmat ring slots).  Depth 11 on N2:
+    the B-matrix row takes two passes of the 8-vector reduction kernel and the extrapolation accumulates the terms beyond
+    the eighth -- same table as the oracle at that depth (20 iterations; depth 8 takes the shipped 22)."""
+    from afesp_b200 import host
+
+    sysm = load_system("n2", "CCSD_spatial")
+    sysm.ccsd_diis_n_errmat = 11
+    r = orc.run(sysm)
+    inp = load_els_input("n2", "CCSD_spatial")
+    inp.ccsd_diis_n_errmat = 11
+    res = host.run(inp, gpu=gpu)
+    assert len(res.ccsd_table) == len(r["ccsd"]) == 21 and len(G["n2"]["ccsd"]) == 23
+    for (it, e, _, rms), (oit, oe, _, orms) in zip(res.ccsd_table, r["ccsd"]):
+        assert it == oit and abs(e - oe) < E_TOL and abs(rms - orms) < 1e-9
+    assert abs(res.e_ccsd - r["e_ccsd"]) < E_TOL
 
 
 # ---------------------------------------------------------------- whole-program spin-orbital output (kept last in this file)
