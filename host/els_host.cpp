@@ -603,7 +603,8 @@ int main(int argc, char** argv) {
   }
   std::printf("%s\n", bar(30, '-').c_str());
   taken("system initialisation", since(t0));
-  if (!s.restricted && s.level == 0) fail("main", "UHF is not implemented in the reference either (src/hf.f90:193)");
+  // calc_type "UHF": the reference has no UHF (do_uhf is a stub, src/hf.f90:193); its main program runs do_rhf for every
+  // unrestricted calc_type (src/main.F90:49-56) and, for "UHF", goes straight to the final table.  Same here.
 
   // ---- RHF
   t0 = Clock::now();

@@ -112,3 +112,23 @@ def test_namelist_reader_follows_fortran_rules_in_both_hosts(tmp_path):
         if want[2] is not None:
             assert got["scf_e_tol"] == want[2]
             assert (" scf_e_tol: %8.2E" % want[2]) in r.stdout
+
+
+def test_calc_type_uhf_runs_the_restricted_scf_as_the_reference_does(tmp_path):
+    """src/main.F90:49-56: every unrestricted calc_type starts with do_rhf (do_uhf is a stub, src/hf.f90:193); "UHF" then
+    goes straight to the final table.  The system block counts spin-orbitals (src/geometry.f90:40-46).  Both hosts."""
+    from afesp_b200 import host
+
+    write_sample_dir("f2", str(tmp_path), calc_type="UHF")
+    r = subprocess.run([els_host_binary(), str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert " Number of occupied orbitals: 18\n Number of virtual orbitals: 38\n" in r.stdout
+    assert " Time taken for restricted Hartree-Fock:" in r.stdout and " MP2" not in r.stdout
+    res = host.run(host.read_inputs(str(tmp_path)))
+    assert compare_els_out(r.stdout, res.stdout, ulps=1.0) == []
+    ref = golden_els_out("f2").splitlines()
+    rhf = next(ln for ln in ref if ln.startswith(" RHF energy:"))
+    assert rhf in r.stdout.splitlines()
+    block = r.stdout.split(" Final energy breakdown\n", 1)[1].splitlines()
+    assert [ln.split(":")[0].strip() for ln in block[:5]] == ["RHF energy", "-" * 47, "Total electronic energy",
+                                                               "Nuclear repulsion", "Total energy"]
