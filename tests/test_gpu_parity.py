@@ -457,6 +457,27 @@ def test_handle_and_state_guards(gpu):
         gpu.set_option("finalize_keep_ccsd", 0)
 
 
+@pytest.mark.parametrize("calc", ["CCSD(T)_spatial", "RCCSD(T)_spatial"])
+def test_h2o_cc_pvtz_spin_free_matches_oracle(gpu, calc):
+    """BASELINE.json configs[1]: H2O cc-pVTZ CCSD(T)_spatial (58 basis functions, o 5 / v 53; integrals regenerated, no
+    reference log exists for the spin-free calc_type on this molecule): iteration table, E_CCSD and the triples energies
+    against the oracle at 1e-9 Eh; RCCSD(T)_spatial adds the true (T) (quirk Q2) and the renormalised pair."""
+    from afesp_b200 import host
+
+    sysm = load_system("h2o_tz", calc)
+    ref = orc.run(sysm)
+    res = host.run(load_els_input("h2o_tz", calc), gpu=gpu)
+    assert abs(res.e_mp2 - ref["e_mp2"]) < E_TOL and abs(res.e_mp2 - G["h2o_tz"]["e_mp2_8"]) < 1e-8
+    assert len(res.ccsd_table) == len(ref["ccsd"])
+    for (it, e, _, rms), (oit, oe, _, orms) in zip(res.ccsd_table, ref["ccsd"]):
+        assert it == oit and abs(e - oe) < E_TOL and abs(rms - orms) < 1e-9
+    keys = ["e_ccsd_t", "e_ccsd_tt"] + (["e_rccsd_t", "e_rccsd_tt", "D_T"] if calc.startswith("R") else [])
+    for k in keys:
+        assert abs(res.energies[k] - ref[k]) < E_TOL, k
+    if not calc.startswith("R"):
+        assert abs(res.energies["e_ccsd_t"] - res.energies["e_ccsd_tt"]) < 1e-12   # Q2: plain CCSD(T)_spatial prints E(T) = E[T]
+
+
 def test_diis_history_deeper_than_eight_matches_oracle(gpu):
     """ccsd_diis_n_errmat is free in the reference (src/ccsd.f90:577-615 allocates n_errmat ring slots).  Depth 11 on N2:
     the B-matrix row takes two passes of the 8-vector reduction kernel and the extrapolation accumulates the terms beyond
