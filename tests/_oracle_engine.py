@@ -32,6 +32,9 @@ class OracleEngine:
 
     def set_option(self, key, value):
         self._log(f"set_option:{key}")
+        switches = {"q1_transposed_foo": "q1", "q3a_truncated_e": "q3a", "q3b_stale_intermediates": "q3b"}
+        if key in switches:   # the parity switches of include/afesp_gpu.h
+            setattr(self, switches[key], bool(value))
 
     # -- AO->MO + MP2 (src/mp2.f90:261-449)
     def ao2mo(self, nbasis, eri_ao=None, coeff=None, want_result=True):
