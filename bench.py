@@ -67,7 +67,10 @@ def run_reference(args, rank):
     from oracle import cpu_reference
 
     total = args.warmup + args.steps
-    budget = max(8.0, min(60.0, 300.0 / max(1, total)))    # CPU seconds per sample: the whole run ends within minutes
+    # CPU seconds per sample.  A sample with both naive o^3v^3 loop nests IN FULL costs ~17.5 s on 16 cores at nbf=200
+    # (11.3 s CCSD iteration + 6.1 s for one complete triple per thread): 480 s over the driver's K + W = 25 samples leaves
+    # room for that (19 s each, ~8 min in all); smaller budgets fall back to slabs of the nests' outer index, stated in `sample`
+    budget = max(8.0, min(60.0, 480.0 / max(1, total)))
     res = cpu_reference.run_subprocess(args.nbf, args.nocc, total, budget)
     samples = res["samples"][args.warmup:]
     vals = [s["value"] for s in samples]
