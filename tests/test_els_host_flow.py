@@ -10,35 +10,12 @@ same binary over the real library (tests/test_gpu_parity.py::test_els_host_*).
 """
 import os
 import subprocess
-import sys
-import sysconfig
 
 import pytest
 
 from tests._fixtures import GOLDEN_DIR, compare_els_out, els_host_binary, golden, golden_els_out, write_sample_dir
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-
-
-@pytest.fixture(scope="module")
-def double_env(tmp_path_factory):
-    """Build the double (never in-tree) and return the environment that puts it in front of the real library."""
-    inc = sysconfig.get_config_var("INCLUDEPY")
-    libdir = sysconfig.get_config_var("LIBDIR")
-    ver = sysconfig.get_config_var("LDVERSION")
-    if not (inc and os.path.exists(os.path.join(inc, "Python.h")) and sysconfig.get_config_var("Py_ENABLE_SHARED")):
-        pytest.skip("no embeddable Python (Python.h / libpython) in this environment")
-    out = tmp_path_factory.mktemp("double") / "afesp_gpu_test_double.so"
-    cmd = ["gcc", "-O1", "-shared", "-fPIC", "-I", inc, os.path.join(ROOT, "tests", "_double", "afesp_gpu_double.c"), "-o",
-           str(out), "-L", libdir, f"-lpython{ver}", f"-Wl,-rpath,{libdir}"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        pytest.skip("cannot build the test double: " + r.stderr[-400:])
-    env = dict(os.environ)
-    env["LD_PRELOAD"] = str(out)
-    env["PYTHONPATH"] = os.pathsep.join([ROOT] + [p for p in sys.path if p.endswith("site-packages")])
-    env.pop("AFESP_GPU_OPTIONS", None)
-    return env
 
 
 def _run(env, path, **extra):
