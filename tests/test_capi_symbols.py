@@ -50,3 +50,38 @@ def test_triples_partition_covers_every_triple_once():
         strict = o * (o - 1) * (o - 2) // 6
         assert sum(AfespGpu.triples_partition(o, 4, True, True)) == strict
         assert sum(AfespGpu.triples_partition(o, 4, False, False)) == o ** 3
+
+
+def test_library_depends_on_no_vendor_math_or_tensor_library():
+    """north_star: no cuBLAS / cuTENSOR / OpenACC runtime behind the boundary -- the contractions are the library's own
+    kernels.  The shared object may need only libc / libstdc++ / libm / libgcc (the CUDA runtime is linked statically, NCCL
+    is dlopen'ed by name on first use of afesp_gpu_comm_*)."""
+    import subprocess
+
+    from afesp_b200 import capi
+
+    needed = subprocess.run(["readelf", "-d", capi.LIB_PATH], capture_output=True, text=True).stdout
+    libs = re.findall(r"\(NEEDED\)\s+Shared library: \[([^\]]+)\]", needed)
+    assert libs, needed
+    for lib in libs:
+        assert re.match(r"(lib(c|m|dl|rt|pthread|stdc\+\+|gcc_s)\.so|ld-linux)", lib), lib
+    undefined = subprocess.run(["nm", "-D", "--undefined-only", capi.LIB_PATH], capture_output=True, text=True).stdout.lower()
+    for vendor in ("cublas", "cutensor", "cusolver", "cudnn", "acc_", "pgi_", "nvhpc"):
+        assert vendor not in undefined, vendor
+
+
+def test_product_code_never_touches_the_oracle():
+    """The oracle (oracle/, tests/_oracle_engine.py, tests/_double/) is test infrastructure: nothing under afesp_b200/, host/,
+    include/ or shim/ may import, link or mention it, and the Makefiles of the product build nothing from it."""
+    product = []
+    for top in ("afesp_b200", "host", "include", "shim"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            if "__pycache__" in dirpath or os.sep + "build" in dirpath or os.sep + "lib" in dirpath:
+                continue
+            product += [os.path.join(dirpath, f) for f in files if f.endswith((".py", ".cu", ".cuh", ".cpp", ".c", ".h",
+                                                                                ".f90", ".inc")) or f == "Makefile"]
+    assert len(product) > 25
+    for path in product:
+        text = open(path, errors="replace").read()
+        for needle in ("import oracle", "from oracle", "oracle/", "_oracle_engine", "afesp_gpu_double", "cpu_port", "cpu_ccsd"):
+            assert needle not in text, (path, needle)
