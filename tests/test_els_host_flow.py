@@ -67,7 +67,8 @@ def test_els_host_symmetry_assertion_prints_the_reference_block_and_stops(double
     assert "ccsd::do_ccsd" in r.stderr and "Permutational symmetry of antisymmetrised integrals does not hold" in r.stderr
 
 
-@pytest.mark.parametrize("calc,last_call", [("MP2_spatial", "mp2_energy"), ("CCSD_spatial", "ccsd_finalize"),
+@pytest.mark.parametrize("calc,last_call", [("MP2_spatial", "mp2_energy"), ("MP2_spinorb", "mp2_energy"),
+                                            ("CCSD_spinorb", "ccsd_finalize"), ("CCSD_spatial", "ccsd_finalize"),
                                             ("RCCSD[T]_spatial", "ccsd_t_spatial"), ("CCSD(T)_spinorb", "ccsd_t_spinorb")])
 def test_els_host_and_python_host_print_the_same_program_output(double_env, calc, last_call, tmp_path):
     """Both hosts over the same double on the water sample: identical text (times masked) for calc_types without a shipped
