@@ -147,8 +147,10 @@ def load_pins():
 
 
 def parity_block(n, o, e_mp2, e_mp1, traj):
-    """Energies of this run against the pinned single-GPU (replicated) values for the same shape: MP2 (also pinned by the
-    CPU oracle), MP1 and, step by step, E_CCSD and the (T) sum e_T.  Tolerance 1e-9 Eh (BASELINE.json north_star)."""
+    """Energies of this run against the pinned values for the same shape.  CPU-computed pins: MP2 (NumPy oracle), E_CCSD
+    after the first iteration (CPU port of the reference) and the (T) sum e_T of the first step (oracle, BLAS orbit form).
+    Pins from the single-GPU (replicated) run: MP1 and, step by step, E_CCSD and e_T (sharded vs replicated at N > 1).
+    Tolerance 1e-9 Eh (BASELINE.json north_star)."""
     pins = load_pins().get(f"nbf{n}_nocc{o}")
     if not pins:
         return {"pinned": False, "note": f"no pinned values for nbf={n} nocc={o} in tests/golden/bench_pinned.json"}
@@ -161,11 +163,19 @@ def parity_block(n, o, e_mp2, e_mp1, traj):
         diffs["e_mp2_vs_cpu_oracle"] = abs(e_mp2 - pins["e_mp2_oracle"])
     if "e_ccsd_iter1_cpu_port" in pins and traj:
         diffs["e_ccsd_iter1_vs_cpu_port"] = abs(traj[0][0] - pins["e_ccsd_iter1_cpu_port"])
+    if "e_T_step1_cpu_oracle" in pins and traj:   # the (T) sum of the first step, computed on the CPU (make_bench_pins.py cpu_T)
+        diffs["e_T_step1_vs_cpu_oracle"] = abs(traj[0][1] - pins["e_T_step1_cpu_oracle"])
     steps = pins.get("steps", [])
     k = min(len(traj), len(steps))
     if k:
         diffs["e_ccsd_max_over_steps"] = max(abs(traj[i][0] - steps[i][0]) for i in range(k))
         diffs["e_T_max_over_steps"] = max(abs(traj[i][1] - steps[i][1]) for i in range(k))
+    cpu_steps = pins.get("steps_cpu", [])   # the first steps computed entirely on the CPU (make_bench_pins.py cpu_traj)
+    kc = min(len(traj), len(cpu_steps))
+    if kc:
+        diffs["e_ccsd_vs_cpu_first_steps"] = max(abs(traj[i][0] - cpu_steps[i][0]) for i in range(kc))
+        diffs["e_T_vs_cpu_first_steps"] = max(abs(traj[i][1] - cpu_steps[i][1]) for i in range(kc))
+        out["steps_compared_with_cpu"] = kc
     out["steps_compared"] = k
     out["abs_diff"] = diffs
     out["ok"] = bool(diffs and all(d < tol for d in diffs.values()))

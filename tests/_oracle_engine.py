@@ -30,6 +30,9 @@ class OracleEngine:
     def last_stage_ms(self):
         return 0.0
 
+    def release(self, what):
+        self._log(f"release:{what}")
+
     def set_option(self, key, value):
         self._log(f"set_option:{key}")
         switches = {"q1_transposed_foo": "q1", "q3a_truncated_e": "q3a", "q3b_stale_intermediates": "q3b"}

@@ -2,6 +2,11 @@
 
     python tests/golden/make_bench_pins.py cpu                 # CPU-only part (here): MP2 from the NumPy oracle, E_CCSD after
                                                                # the first iteration from the CPU port of the reference
+    python tests/golden/make_bench_pins.py cpu_T               # CPU-only, ~15 min: e_T of the first step at nbf=200 through the
+                                                               # oracle's BLAS orbit form of the [T] accumulator
+    python tests/golden/make_bench_pins.py cpu_mp2 400 40      # CPU-only: MP2 of the target shape from the (ia|jb) block
+    python tests/golden/make_bench_pins.py cpu_traj 200 20 3   # CPU-only, ~17 min: the first three bench steps (CCSD iteration,
+                                                               # DIIS, [T] on the extrapolated amplitudes) entirely on the CPU
     python tests/golden/make_bench_pins.py gpu <bench.json>    # merge the per-step (E_CCSD, e_T) trajectory of a SINGLE-GPU
                                                                # (replicated, unsharded) `bench.py --trajectory` line
 
@@ -49,6 +54,119 @@ def cpu(nbf=200, nocc=20):
     print(key, pins[key]["e_mp2_oracle"], pins[key]["e_ccsd_iter1_cpu_port"])
 
 
+def cpu_mp2(nbf=400, nocc=40):
+    """MP2 of a shape whose packed MO integrals are too large to build on the host (nbf=400: 25.7 GB): only the (ia|jb) block,
+    from the factored form -- B_mo(i,a;P) = sum_mn C(i,m) B(mn,P) C(a,n), (ia|jb) = sum_P B_mo(ia,P) B_mo(jb,P) -- then the
+    expression of src/mp2.f90:418-438."""
+    e_mp2 = mp2_from_factors(nbf, nocc)
+    pins = load()
+    key = f"nbf{nbf}_nocc{nocc}"
+    pins.setdefault(key, {})
+    pins[key]["e_mp2_oracle"] = e_mp2
+    pins[key]["cpu_source"] = ("tests/golden/make_bench_pins.py cpu_mp2 (NumPy: (ia|jb) block from the factored form of the "
+                               "synthetic integrals, MP2 expression of src/mp2.f90:418-438)")
+    json.dump(pins, open(PATH, "w"), indent=1)
+    print(key, "e_mp2_oracle", e_mp2, "GPU-pinned:", pins[key].get("e_mp2"))
+
+
+def mp2_from_factors(nbf, nocc):
+    from afesp_b200 import synthetic
+
+    B, Cmo, eps = synthetic.make_factors(nbf, nocc)
+    n, o, v = nbf, nocc, nbf - nocc
+    ii, jj = np.tril_indices(n)
+    Bov = np.empty((o * v, B.shape[1]))
+    full = np.empty((n, n))
+    for P in range(B.shape[1]):
+        full[ii, jj] = B[:, P]
+        full[jj, ii] = B[:, P]
+        Bov[:, P] = (Cmo[:o] @ full @ Cmo[o:].T).ravel()       # (i, a) row-major
+    iajb = (Bov @ Bov.T).reshape(o, v, o, v)
+    D = eps[:o, None, None, None] + eps[None, None, :o, None] - eps[None, o:, None, None] - eps[None, None, None, o:]
+    return float(np.sum(iajb * (2.0 * iajb - iajb.transpose(0, 3, 2, 1)) / D))
+
+
+def cpu_T(nbf=200, nocc=20, limit=None):
+    """e_T of the bench's FIRST step on the CPU: amplitudes after one CCSD iteration of the CPU port (the DIIS extrapolation
+    that follows has a single history entry and returns them unchanged), then the [T] accumulator over all triples through
+    the oracle's BLAS orbit form (oracle/afesp_oracle.py: triples_bracket_T_orbit_form; ~15 CPU-minutes on 8 cores at
+    nbf=200).  Pins the headline-shape (T) of every bench line on a CPU computation instead of on a GPU run."""
+    import time
+
+    from oracle import afesp_oracle as orc
+    from oracle import cpu_port
+
+    lib = cpu_port.load()
+    cpu_port.set_threads(lib)
+    mo, Cmo, eps = cpu_port.synthetic_mo_integrals(nbf, nocc)
+    V = cpu_port.slices(lib, mo, nbf, nocc)
+    o = nocc
+    D1, D2 = orc.denominators(eps, o)
+    t2 = np.asfortranarray(V["v_oovv"] / D2)
+    t1 = np.zeros((o, nbf - o), order="F")
+    t1n, t2n, _, _ = cpu_port.ccsd_iter(lib, V, eps, t1, t2)
+    del V["v_vvvv"]
+    triples = None
+    if limit:
+        triples = [(i, j, k) for i in range(o) for j in range(i, o) for k in range(j, o)][:int(limit)]
+    t0 = time.perf_counter()
+    e_T = orc.triples_bracket_T_orbit_form(np.ascontiguousarray(t2n), np.ascontiguousarray(V["v_vvov"]),
+                                           np.ascontiguousarray(V["v_oovo"]), eps, triples=triples, progress=50)
+    print(f"e_T = {e_T!r}  ({time.perf_counter() - t0:.0f} s)")
+    if limit:
+        return
+    pins = load()
+    key = f"nbf{nbf}_nocc{nocc}"
+    pins.setdefault(key, {})
+    pins[key]["e_T_step1_cpu_oracle"] = e_T
+    pins[key]["cpu_T_source"] = ("tests/golden/make_bench_pins.py cpu_T (one CCSD iteration through oracle/cpu_ccsd.c, then the [T] "
+                                 "accumulator over all triples through the oracle's BLAS orbit form)")
+    json.dump(pins, open(PATH, "w"), indent=1)
+    print(key, "e_T_step1_cpu_oracle", e_T, "GPU-pinned step 1:", (pins[key].get("steps") or [[None, None]])[0][1])
+
+
+def cpu_traj(nbf=200, nocc=20, nsteps=3):
+    """The first `nsteps` steps of the bench trajectory on the CPU, in the bench's own order (bench.py step()): one CCSD
+    iteration (CPU port of the reference, energy from its output amplitudes), CC-DIIS extrapolation (the oracle's ring of
+    depth 8), then the [T] accumulator ON THE EXTRAPOLATED amplitudes (oracle BLAS orbit form).  ~5.5 CPU-minutes per step
+    on 8 cores at nbf=200.  Stored as steps_cpu = [[E_CCSD, e_T], ...]."""
+    import time
+
+    from oracle import afesp_oracle as orc
+    from oracle import cpu_port
+
+    lib = cpu_port.load()
+    cpu_port.set_threads(lib)
+    mo, Cmo, eps = cpu_port.synthetic_mo_integrals(nbf, nocc)
+    V = cpu_port.slices(lib, mo, nbf, nocc)
+    o = nocc
+    D1, D2 = orc.denominators(eps, o)
+    voovv = np.asarray(V["v_oovv"])
+    t2 = np.asfortranarray(voovv / D2)
+    t1 = np.zeros((o, nbf - o), order="F")
+    diis = orc.CCDiis(8, t1.shape, t2.shape)
+    vvov, oovo = np.ascontiguousarray(V["v_vvov"]), np.ascontiguousarray(V["v_oovo"])
+    steps = []
+    for it in range(int(nsteps)):
+        t0 = time.perf_counter()
+        diis.stash(np.asarray(t1), np.asarray(t2))
+        t1n, t2n, _, _ = cpu_port.ccsd_iter(lib, V, eps, np.asfortranarray(t1), np.asfortranarray(t2))
+        e_cc = orc.restricted_energy(np.asarray(t1n), np.asarray(t2n), voovv)
+        t1, t2 = diis.update(np.asarray(t1n), np.asarray(t2n))
+        e_T = orc.triples_bracket_T_orbit_form(np.ascontiguousarray(t2), vvov, oovo, eps)
+        steps.append([float(e_cc), float(e_T)])
+        print(f"step {it + 1}: E_CCSD {e_cc!r}  e_T {e_T!r}  ({time.perf_counter() - t0:.0f} s)", flush=True)
+    pins = load()
+    key = f"nbf{nbf}_nocc{nocc}"
+    pins.setdefault(key, {})
+    pins[key]["steps_cpu"] = steps
+    pins[key]["steps_cpu_source"] = ("tests/golden/make_bench_pins.py cpu_traj: per step one CCSD iteration through oracle/cpu_ccsd.c, "
+                                     "the oracle's CC-DIIS, the [T] accumulator through the oracle's BLAS orbit form")
+    json.dump(pins, open(PATH, "w"), indent=1)
+    for a, b in zip(steps, pins[key].get("steps", [])):
+        print("cpu", a, "gpu-pinned", b, "diff", abs(a[0] - b[0]), abs(a[1] - b[1]))
+
+
 def gpu(path):
     pins = load()
     d = json.loads(open(path).read().strip().splitlines()[-1])
@@ -70,5 +188,11 @@ def gpu(path):
 if __name__ == "__main__":
     if sys.argv[1] == "cpu":
         cpu(*[int(x) for x in sys.argv[2:4]])
+    elif sys.argv[1] == "cpu_mp2":
+        cpu_mp2(*[int(x) for x in sys.argv[2:4]])
+    elif sys.argv[1] == "cpu_traj":
+        cpu_traj(*[int(x) for x in sys.argv[2:5]])
+    elif sys.argv[1] == "cpu_T":
+        cpu_T(*[int(x) for x in sys.argv[2:5]])
     else:
         gpu(sys.argv[2])

@@ -50,3 +50,34 @@ def test_two_ranks_gloo_shared_host_copy_and_skipped_target():
     assert "skipped" in d["target_config"] and "exchange" in d
     d = _run(cmd + ["--target", "2"], {})
     assert d["target_config"]["config"]["nbf"] == 40 and d["target_config"]["e2e"]["value"] > 0
+
+
+def test_parity_block_uses_the_cpu_pins_and_the_pin_file_is_self_consistent():
+    """tests/golden/bench_pinned.json at the headline shape: the CPU-computed pins (MP2 by the NumPy oracle; E_CCSD after the
+    first iteration by the CPU port; the (T) sum of the first step and the first steps of the trajectory by the CPU port +
+    the oracle's BLAS orbit form, tests/golden/make_bench_pins.py) agree with the trajectory a single B200 produced to far
+    below the 1e-9 Eh tolerance -- so every bench line's `parity` block ties the GPU numbers at nbf=200 to CPU computations
+    of the reference algorithm, not only to an earlier GPU run -- and bench.parity_block reports them."""
+    pins = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_pinned.json")))["nbf200_nocc20"]
+    steps = pins["steps"]
+    assert len(steps) >= 25
+    assert abs(pins["e_mp2"] - pins["e_mp2_oracle"]) < 1e-12
+    assert abs(steps[0][0] - pins["e_ccsd_iter1_cpu_port"]) < 1e-12
+    assert abs(steps[0][1] - pins["e_T_step1_cpu_oracle"]) < 1e-12
+    assert len(pins["steps_cpu"]) >= 3
+    for cpu, gpu in zip(pins["steps_cpu"], steps):
+        assert abs(cpu[0] - gpu[0]) < 1e-11 and abs(cpu[1] - gpu[1]) < 1e-11
+    # the function the bench uses, fed with the pinned trajectory itself and with a perturbed one
+    code = ("import json, sys; sys.argv=['bench.py']; import bench; "
+            "p=bench.load_pins()['nbf200_nocc20']; "
+            "ok=bench.parity_block(200, 20, p['e_mp2'], p['e_mp1'], [s + [0.0] for s in p['steps']]); "
+            "bad=bench.parity_block(200, 20, p['e_mp2'], p['e_mp1'], [[s[0], s[1] + 2e-9, 0.0] for s in p['steps']]); "
+            "bench.emit({'ok': ok, 'bad': bad})")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["ok"]["ok"] is True and d["ok"]["steps_compared_with_cpu"] == len(pins["steps_cpu"])
+    for key in ("e_mp2_vs_cpu_oracle", "e_ccsd_iter1_vs_cpu_port", "e_T_step1_vs_cpu_oracle", "e_ccsd_vs_cpu_first_steps",
+                "e_T_vs_cpu_first_steps", "e_ccsd_max_over_steps", "e_T_max_over_steps"):
+        assert key in d["ok"]["abs_diff"], key
+    assert d["bad"]["ok"] is False and d["bad"]["abs_diff"]["e_T_step1_vs_cpu_oracle"] > 1e-9

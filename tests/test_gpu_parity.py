@@ -418,6 +418,45 @@ def test_synthetic_chain_matches_oracle_and_device_generated_integrals(gpu):
         assert abs(got[k] - en[k]) < E_TOL, k
 
 
+@pytest.mark.parametrize("n,o", [(120, 12), (101, 10)])
+def test_one_bench_step_at_a_multi_tile_shape_matches_the_cpu(gpu, n, o):
+    """One step of bench.py (CCSD iteration, DIIS, (T) on the extrapolated amplitudes) on synthetic integrals large enough for
+    several GEMM tiles per block -- v = 108: one full and one ragged m-tile, K = 120: a short K tail, i.e. the EDGE / KTAIL
+    variants of the TMA-staged kernel; v = 91: odd leading dimensions, the cp.async kernels -- against a CPU computation of
+    the same step: MP2 from the factored integrals, E_CCSD from the CPU port of the reference's iteration
+    (oracle/cpu_ccsd.c), the (T) sum from the oracle's BLAS orbit form.  The same recipe at nbf=200 is what
+    tests/golden/bench_pinned.json pins every bench line on."""
+    from afesp_b200 import synthetic
+    from oracle import cpu_port
+
+    eri, Cm, eps = synthetic.make(n, o)
+    gpu.ao2mo(n, eri, Cm, want_result=False)
+    gpu.release("eri_ao")
+    e_mp2 = gpu.mp2_energy(o, eps)
+    e_mp1, _ = gpu.ccsd_init(o, True, eps, 8)
+    e1, rms1 = gpu.ccsd_iterate()
+    gpu.ccsd_diis()
+    gpu.ccsd_finalize()
+    sums, _ = gpu.ccsd_t_spatial(True, False, False)
+    # CPU: same system through the factored form (no O(n^5) transform), one iteration of the reference's code path
+    lib = cpu_port.load()
+    cpu_port.set_threads(lib)
+    mo, C2, eps2 = cpu_port.synthetic_mo_integrals(n, o)
+    assert np.array_equal(eps, eps2) and np.array_equal(Cm, C2)
+    V = cpu_port.slices(lib, mo, n, o)
+    D1, D2 = orc.denominators(eps, o)
+    voovv = np.asarray(V["v_oovv"])
+    t2 = np.asfortranarray(voovv / D2)
+    want_mp2 = float(np.sum(voovv * (2.0 * voovv - voovv.transpose(0, 1, 3, 2)) / D2))
+    assert abs(e_mp2 - want_mp2) < E_TOL and abs(e_mp1 - want_mp2) < E_TOL
+    t1n, t2n, _, _ = cpu_port.ccsd_iter(lib, V, eps, np.zeros((o, n - o), order="F"), t2)
+    assert abs(e1 - orc.restricted_energy(np.asarray(t1n), np.asarray(t2n), voovv)) < E_TOL
+    assert abs(rms1 - float(np.sum((np.asarray(t2n) - np.asarray(t2)) ** 2))) < 1e-9
+    want_T = orc.triples_bracket_T_orbit_form(np.ascontiguousarray(t2n), np.ascontiguousarray(V["v_vvov"]),
+                                              np.ascontiguousarray(V["v_oovo"]), eps)
+    assert abs(sums[0] - want_T) < E_TOL and abs(sums[1] - want_T) < E_TOL      # plain (T): quirk Q2, e_TT = e_T
+
+
 # ---------------------------------------------------------------- handle / state guards
 def test_handle_and_state_guards(gpu):
     """One handle per device and process; DIIS is refused on a finalised state and with an absurd history depth (status
