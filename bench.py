@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "ccsd_iter_plus_T_seconds"
 UNIT = "s"
-PINNED = os.path.join(ROOT, "tests", "golden", "bench_pinned.json")
+PINNED = os.environ.get("AFESP_BENCH_PINS") or os.path.join(ROOT, "tests", "golden", "bench_pinned.json")   # (env: tests)
 
 
 # Keep stdout clean for the single JSON line: libraries loaded later (NCCL prints its version banner on stdout) write
@@ -180,6 +180,36 @@ def parity_block(n, o, e_mp2, e_mp1, traj):
     out["abs_diff"] = diffs
     out["ok"] = bool(diffs and all(d < tol for d in diffs.values()))
     return out
+
+
+def mp1_triples_check(gpu, n, o, eps, src, big, chk):
+    """(T) contributions of single unique triples, GPU against CPU, at a shape where no CPU CCSD iteration is affordable (the
+    target shape nbf=400): the state right after afesp_gpu_ccsd_init holds the MP1 amplitudes, afesp_gpu_set_partition(r, T)
+    makes the handle own exactly triple number r of the T unique (i <= j <= k) triples, and the CPU value of that orbit's [T]
+    accumulator comes from the factored form of the synthetic integrals (tests/golden/make_bench_pins.py cpu_mp1_triples).
+    Runs after all measurements (it re-initialises the CCSD state).  Relative tolerance 1e-9 (absolute floor 1e-15 Eh: the
+    i = j = k orbits vanish identically)."""
+    gpu.set_option("finalize_keep_ccsd", 0)
+    gpu.ccsd_finalize()          # drop what the device-timed loop kept (DIIS history, ladder integrals, intermediates)
+    gpu.release("scratch")
+    gpu.set_eri_mo(n, src)       # from here on the sequence of the e2e leg without the iteration
+    gpu.ccsd_init(o, True, eps, 8)
+    if big:
+        gpu.release("eri_mo")
+    gpu.ccsd_finalize()
+    got = []
+    try:
+        for r in chk["ranks"]:
+            gpu.set_partition(int(r), int(chk["ntriples"]))
+            sums, _ = gpu.ccsd_t_spatial(True, False, False)
+            got.append(float(sums[0]))
+    finally:
+        gpu.set_partition(0, 1)
+    diffs = [abs(a - b) for a, b in zip(got, chk["e_T"])]
+    ok = all(d <= max(1e-9 * abs(c), 1e-15) for d, c in zip(diffs, chk["e_T"]))
+    return {"what": "e_T of single (i<=j<=k) orbits on the MP1 amplitudes: GPU (set_partition(r, ntriples) + ccsd_t_spatial) "
+                    "against NumPy from the factored integrals", "ijk": chk["ijk"], "e_T_gpu": got, "e_T_cpu": chk["e_T"],
+            "abs_diff": diffs, "tolerance": "relative 1e-9, absolute floor 1e-15 Eh", "ok": bool(ok)}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -400,6 +430,14 @@ def run_shape(args, rank, world, local, n, o, steps, warmup, e2e_first=False, wa
                         "ms": ms, "algorithmic_bytes": by, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / hbm_peak}
                 except Exception as ex:
                     hbm["kernels"][f"{what} o={oo_} v={vv_}"] = {"error": str(ex)}
+    # ---- per-triple (T) check against CPU values (shapes with such pins: the target shape), after every measurement
+    mp1_check = None
+    chk = (load_pins().get(f"nbf{n}_nocc{o}") or {}).get("mp1_triples")
+    if chk and world == 1:
+        try:
+            mp1_check = mp1_triples_check(gpu, n, o, eps, src, big, chk)
+        except Exception as ex:   # a check, never a reason to lose the measurements
+            mp1_check = {"error": f"{type(ex).__name__}: {ex}"}
     out = None
     if rank == 0:
         traffic, traffic_source = None, None
@@ -452,6 +490,10 @@ def run_shape(args, rank, world, local, n, o, steps, warmup, e2e_first=False, wa
             "gpu_launches": int(l1 - l0), "clocks": clocks,
             "tma": {"scope": tma_scope, "selftest": tma_selftest}, "hbm_kernels": hbm,
         }
+    if out is not None and mp1_check is not None:
+        out["parity"]["mp1_triples_vs_cpu"] = mp1_check
+        if mp1_check.get("ok") is False:
+            out["parity"]["ok"] = False
     gpu.close()
     if shm_path is not None:
         if shm_registered:

@@ -30,6 +30,16 @@ class OracleEngine:
     def last_stage_ms(self):
         return 0.0
 
+    def set_eri_mo(self, nbasis, eri_mo):
+        self._log("set_eri_mo")
+        self.n = int(nbasis)
+        self.eri_mo = np.array(eri_mo, dtype=float)
+
+    def set_partition(self, rank, nranks):
+        """afesp_gpu_set_partition: the handle owns the unique (i <= j <= k) triples t with t % nranks == rank, in the
+        enumeration order of afesp_b200/csrc/triples.cu (my_triples)."""
+        self.partition = (int(rank), int(nranks))
+
     def release(self, what):
         self._log(f"release:{what}")
 
@@ -130,8 +140,15 @@ class OracleEngine:
         self._log("ccsd_t_spatial")
         assert self.finalized and self.restricted
         cr = self.cr if comp_renorm else (None, None)
+        triples = None
+        rank, nranks = getattr(self, "partition", (0, 1))
+        if nranks > 1:   # this share of the unique triples, each expanded into its distinct orderings (the reference's loop)
+            o = self.nocc
+            uniq = [(i, j, k) for i in range(o) for j in range(i, o) for k in range(j, o)]
+            mine = [t for n_t, t in enumerate(uniq) if n_t % nranks == rank]
+            triples = sorted({p for (i, j, k) in mine for p in [(i, j, k), (i, k, j), (j, i, k), (j, k, i), (k, i, j), (k, j, i)]})
         sums = orc.triples_spatial_sums(self.t1, self.t2, self.V["v_oovv"], self.V["v_vvov"], self.V["v_oovo"], self.eps,
-                                        paren, renorm, comp_renorm, cr[0], cr[1])
+                                        paren, renorm, comp_renorm, cr[0], cr[1], triples=triples)
         const = orc.triples_denominator_constant(self.t1, self.t2) if (renorm or comp_renorm) else 0.0
         return np.array(sums), const
 

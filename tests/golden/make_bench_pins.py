@@ -5,6 +5,8 @@
     python tests/golden/make_bench_pins.py cpu_T               # CPU-only, ~15 min: e_T of the first step at nbf=200 through the
                                                                # oracle's BLAS orbit form of the [T] accumulator
     python tests/golden/make_bench_pins.py cpu_mp2 400 40      # CPU-only: MP2 of the target shape from the (ia|jb) block
+    python tests/golden/make_bench_pins.py cpu_mp1_triples 400 40   # CPU-only: (T) contributions of six single triples on the
+                                                               # MP1 amplitudes at the target shape, from the factored integrals
     python tests/golden/make_bench_pins.py cpu_traj 200 20 3   # CPU-only, ~17 min: the first three bench steps (CCSD iteration,
                                                                # DIIS, [T] on the extrapolated amplitudes) entirely on the CPU
     python tests/golden/make_bench_pins.py gpu <bench.json>    # merge the per-step (E_CCSD, e_T) trajectory of a SINGLE-GPU
@@ -84,6 +86,70 @@ def mp2_from_factors(nbf, nocc):
     iajb = (Bov @ Bov.T).reshape(o, v, o, v)
     D = eps[:o, None, None, None] + eps[None, None, :o, None] - eps[None, o:, None, None] - eps[None, None, None, o:]
     return float(np.sum(iajb * (2.0 * iajb - iajb.transpose(0, 3, 2, 1)) / D))
+
+
+def unique_triples(o):
+    """Enumeration order of the library's unique (i <= j <= k) list (afesp_b200/csrc/triples.cu: my_triples): with
+    afesp_gpu_set_partition(h, r, ntriples) "rank" r owns exactly triple number r."""
+    return [(i, j, k) for i in range(o) for j in range(i, o) for k in range(j, o)]
+
+
+def mp1_triples_from_factors(nbf, nocc, picks):
+    """(T) contributions of single unique triples on the MP1 amplitudes (t1 = 0, t2 = <ij|ab> / D: the state right after
+    afesp_gpu_ccsd_init), everything from the factored form of the synthetic integrals -- so it also works at nbf=400, where
+    neither the packed MO integrals (25.7 GB) nor the v_vvov slice (15 GB) are built on the host:
+        t2(i,j,a,b) = (ia|jb) / D,   v_vovv(d,k,b,c) = (ck|bd),   v_oovo(r,q,c,l) = (rc|ql),   (pq|rs) = sum_P B(pq,P) B(rs,P).
+    Returns the list of e_T orbit contributions (oracle: triples_bracket_T_orbit_form)."""
+    from afesp_b200 import synthetic
+    from oracle import afesp_oracle as orc
+
+    B, Cmo, eps = synthetic.make_factors(nbf, nocc)
+    n, o, v = nbf, nocc, nbf - nocc
+    naux = B.shape[1]
+    ii, jj = np.tril_indices(n)
+    Boo, Bov, Bvv = np.empty((naux, o, o)), np.empty((naux, o, v)), np.empty((naux, v, v))
+    full = np.empty((n, n))
+    for P in range(naux):
+        full[ii, jj] = B[:, P]
+        full[jj, ii] = B[:, P]
+        m = Cmo @ full @ Cmo.T
+        Boo[P], Bov[P], Bvv[P] = m[:o, :o], m[:o, o:], m[o:, o:]
+    M = Bov.reshape(naux, o * v)
+    iajb = (M.T @ M).reshape(o, v, o, v)
+    D1, D2 = orc.denominators(eps, o)
+    t2 = np.ascontiguousarray(iajb.transpose(0, 2, 1, 3) / D2)
+    del iajb
+    Bvv2 = Bvv.reshape(naux, v * v)
+
+    def iv_block(k):      # [d, (b,c)] = (ck|bd) = sum_P Bov[P,k,c] Bvv[P,b,d]
+        x = (Bvv2.T @ Bov[:, k, :]).reshape(v, v, v)        # [b, d, c]
+        return np.ascontiguousarray(x.transpose(1, 0, 2)).reshape(v, v * v)
+
+    def io_block(r, q):   # [c, l] = (rc|ql) = sum_P Bov[P,r,c] Boo[P,q,l]
+        return Bov[:, r, :].T @ Boo[:, q, :]
+
+    return [orc.triples_bracket_T_orbit_form(t2, None, None, eps, triples=[t], iv_block=iv_block, io_block=io_block)
+            for t in picks], eps
+
+
+def cpu_mp1_triples(nbf=400, nocc=40):
+    """Pins for bench.py's per-triple (T) check at a shape where no CPU CCSD iteration is affordable (the target shape):
+    a handful of unique triples of all three orbit kinds (i=j=k, two equal, all different), spread over the list."""
+    o = nocc
+    all_t = unique_triples(o)
+    picks = [(0, 0, 0), (o // 6, o // 6, o // 2), (o // 8, o // 2, (4 * o) // 5), (o // 3, (2 * o) // 3, (2 * o) // 3),
+             (o - 3, o - 2, o - 1), (o - 1, o - 1, o - 1)]
+    e, _ = mp1_triples_from_factors(nbf, nocc, picks)
+    pins = load()
+    key = f"nbf{nbf}_nocc{nocc}"
+    pins.setdefault(key, {})
+    pins[key]["mp1_triples"] = {"ntriples": len(all_t), "ijk": [list(t) for t in picks], "ranks": [all_t.index(t) for t in picks],
+                                "e_T": [float(x) for x in e],
+                                "source": "tests/golden/make_bench_pins.py cpu_mp1_triples (NumPy from the factored integrals: "
+                                          "MP1 amplitudes, the [T] accumulator of single (i<=j<=k) orbits through the oracle's "
+                                          "BLAS orbit form)"}
+    json.dump(pins, open(PATH, "w"), indent=1)
+    print(key, pins[key]["mp1_triples"])
 
 
 def cpu_T(nbf=200, nocc=20, limit=None):
@@ -188,6 +254,8 @@ def gpu(path):
 if __name__ == "__main__":
     if sys.argv[1] == "cpu":
         cpu(*[int(x) for x in sys.argv[2:4]])
+    elif sys.argv[1] == "cpu_mp1_triples":
+        cpu_mp1_triples(*[int(x) for x in sys.argv[2:4]])
     elif sys.argv[1] == "cpu_mp2":
         cpu_mp2(*[int(x) for x in sys.argv[2:4]])
     elif sys.argv[1] == "cpu_traj":

@@ -81,3 +81,20 @@ def test_parity_block_uses_the_cpu_pins_and_the_pin_file_is_self_consistent():
                 "e_T_vs_cpu_first_steps", "e_ccsd_max_over_steps", "e_T_max_over_steps"):
         assert key in d["ok"]["abs_diff"], key
     assert d["bad"]["ok"] is False and d["bad"]["abs_diff"]["e_T_step1_vs_cpu_oracle"] > 1e-9
+
+
+def test_per_triple_check_of_the_target_leg_is_attached_and_cannot_take_the_line_down(tmp_path):
+    """bench.mp1_triples_check in the control flow (fake engine, so the numbers disagree): the target leg's parity block
+    carries the per-triple comparison and turns false; when the check itself fails the measurements are kept."""
+    pins = {"nbf40_nocc4": {"mp1_triples": {"ntriples": 20, "ijk": [[0, 1, 2], [1, 1, 3]], "ranks": [5, 11], "e_T": [-1e-6, -2e-6]}}}
+    path = tmp_path / "pins.json"
+    path.write_text(json.dumps(pins))
+    cmd = [sys.executable, STUB, "--gpus", "1", "--steps", "1", "--warmup", "1", "--nbf", "36", "--nocc", "4", "--no-cpu"]
+    d = _run(cmd, {"AFESP_BENCH_PINS": str(path)})
+    chk = d["target_config"]["parity"]["mp1_triples_vs_cpu"]
+    assert chk["ijk"] == [[0, 1, 2], [1, 1, 3]] and len(chk["e_T_gpu"]) == 2 and chk["ok"] is False
+    assert d["target_config"]["parity"]["ok"] is False and d["target_config"]["value"] > 0
+    pins["nbf40_nocc4"]["mp1_triples"]["ranks"] = ["not a number"]
+    path.write_text(json.dumps(pins))
+    d = _run(cmd, {"AFESP_BENCH_PINS": str(path)})
+    assert "error" in d["target_config"]["parity"]["mp1_triples_vs_cpu"] and d["target_config"]["value"] > 0
