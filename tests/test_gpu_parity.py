@@ -418,6 +418,41 @@ def test_synthetic_chain_matches_oracle_and_device_generated_integrals(gpu):
         assert abs(got[k] - en[k]) < E_TOL, k
 
 
+def test_single_triple_shares_on_mp1_amplitudes_match_cpu_values_from_the_factored_integrals(gpu):
+    """The per-triple check bench.py runs at the target shape (bench.mp1_triples_check), here at nbf=64 / nocc=6 where all 56
+    unique triples can be gone through: with afesp_gpu_set_partition(r, 56) the handle owns exactly triple number r of the
+    (i <= j <= k) list, and on the MP1 amplitudes (state after ccsd_init) its [T] sum equals the orbit value NumPy gets from
+    the factored form of the integrals -- for every orbit kind (6, 3 and 1 distinct orderings)."""
+    import sys
+
+    from afesp_b200 import synthetic
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_bench_pins as M
+
+    n, o = 64, 6
+    uniq = M.unique_triples(o)
+    assert len(uniq) == 56
+    want, eps = M.mp1_triples_from_factors(n, o, uniq)
+    eri, Cm, eps1 = synthetic.make(n, o)
+    assert np.array_equal(eps, eps1)
+    gpu.ao2mo(n, eri, Cm, want_result=False)
+    gpu.release("eri_ao")
+    gpu.ccsd_init(o, True, eps, 8)
+    gpu.ccsd_finalize()
+    try:
+        whole, _ = gpu.ccsd_t_spatial(True, False, False)
+        got = []
+        for r in range(len(uniq)):
+            gpu.set_partition(r, len(uniq))
+            got.append(gpu.ccsd_t_spatial(True, False, False)[0][0])
+    finally:
+        gpu.set_partition(0, 1)
+    for (i, j, k), g, w in zip(uniq, got, want):
+        assert abs(g - w) <= max(1e-9 * abs(w), 1e-15), ((i, j, k), g, w)
+    assert abs(sum(got) - whole[0]) < 1e-13 and abs(whole[0] - sum(want)) < 1e-12
+
+
 @pytest.mark.parametrize("n,o", [(120, 12), (101, 10)])
 def test_one_bench_step_at_a_multi_tile_shape_matches_the_cpu(gpu, n, o):
     """One step of bench.py (CCSD iteration, DIIS, (T) on the extrapolated amplitudes) on synthetic integrals large enough for
