@@ -5,6 +5,8 @@
     python tests/golden/make_bench_pins.py cpu_T               # CPU-only, ~15 min: e_T of the first step at nbf=200 through the
                                                                # oracle's BLAS orbit form of the [T] accumulator
     python tests/golden/make_bench_pins.py cpu_mp2 400 40      # CPU-only: MP2 of the target shape from the (ia|jb) block
+    python tests/golden/make_bench_pins.py cpu_ccsd_iter1 400 40    # CPU-only, ~20 min: E_CCSD after the first iteration at the
+                                                               # target shape, from the factored integrals
     python tests/golden/make_bench_pins.py cpu_mp1_triples 400 40   # CPU-only: (T) contributions of six single triples on the
                                                                # MP1 amplitudes at the target shape, from the factored integrals
     python tests/golden/make_bench_pins.py cpu_traj 200 20 3   # CPU-only, ~17 min: the first three bench steps (CCSD iteration,
@@ -132,6 +134,90 @@ def mp1_triples_from_factors(nbf, nocc, picks):
             for t in picks], eps
 
 
+def ccsd_iter1_from_factors(nbf, nocc, ladder_block=8, log=None):
+    """E_CCSD and sum (dT2)^2 after the FIRST spin-free CCSD iteration (input: t1 = 0, t2 = MP1), from the factored form of the
+    synthetic integrals, for shapes whose dense v_vvvv slice (nbf=400: 134 GB) rules out both the oracle's general functions
+    and the CPU port.  It is oracle.restricted_intermediates + restricted_amplitudes (src/ccsd.f90:1040-1312, 1538-1732) with
+    every term that carries a factor t1 dropped, the ladder <ef|ab> = sum_P B(ea,P) B(fb,P) built in slabs of b, and the one
+    v_vvov contraction of the T1 equation (:1618-1630) taken through the factors.  Checked against the general oracle
+    functions at small shapes (tests/test_cpu_port.py) and against the CPU port at nbf=200 (bench_pinned.json)."""
+    import time
+
+    from afesp_b200 import synthetic
+    from oracle import afesp_oracle as orc
+
+    t0 = time.perf_counter()
+    say = log or (lambda *a: None)
+    B, Cmo, eps = synthetic.make_factors(nbf, nocc)
+    n, o, v = nbf, nocc, nbf - nocc
+    naux = B.shape[1]
+    ii, jj = np.tril_indices(n)
+    Boo, Bov, Bvv = np.empty((naux, o, o)), np.empty((naux, o, v)), np.empty((naux, v, v))
+    full = np.empty((n, n))
+    for P in range(naux):
+        full[ii, jj] = B[:, P]
+        full[jj, ii] = B[:, P]
+        m = Cmo @ full @ Cmo.T
+        Boo[P], Bov[P], Bvv[P] = m[:o, :o], m[:o, o:], m[o:, o:]
+    del B, full
+    ein = lambda *a: np.einsum(*a, optimize=True)
+    # physicist slices <pq|rs> = (pr|qs)
+    v_oovv = ein("Pia,Pjb->ijab", Bov, Bov)
+    v_ovov = ein("Pij,Pab->iajb", Boo, Bvv)
+    v_oovo = ein("Pia,Pjl->ijal", Bov, Boo)
+    v_oooo = ein("Pik,Pjl->ijkl", Boo, Boo)
+    D1, D2 = orc.denominators(eps, o)
+    t2 = v_oovv / D2
+    asym = 2.0 * t2 - t2.transpose(1, 0, 2, 3)
+    A = 2.0 * v_oovv - v_oovv.transpose(0, 1, 3, 2)
+    say(f"slices + MP1 amplitudes {time.perf_counter() - t0:.0f} s")
+    # intermediates with t1 = 0 (c = t2, I_vo = 0)
+    I_vv = -ein("mneb,mnea->ba", A, t2)
+    I_oo = ein("jmfe,mief->ji", asym, v_oovv)
+    I_oooo = v_oooo + ein("klef,ijef->klij", t2, v_oovv)
+    I_ovov = v_ovov - 0.5 * ein("mibe,mjae->jbia", v_oovv, t2)
+    I_voov = 0.5 * ein("imbe,mjea->bjia", A, t2) - 0.5 * ein("imbe,mjae->bjia", v_oovv, t2) + v_oovv.transpose(3, 0, 1, 2)
+    say(f"intermediates {time.perf_counter() - t0:.0f} s")
+    # T1 equation: what survives t1 = 0 is  - v_oovo . asym  +  v_vvov . asym   (:1606-1630)
+    r1 = -ein("mien,mnea->ia", v_oovo, asym)
+    Y = ein("Pme,mief->Pif", Bov, asym)                      # v_vvov(e,f,m,a) = (em|fa) = sum_P Bov(P,m,e) Bvv(P,f,a)
+    r1 = r1 + ein("Pif,Pfa->ia", Y, Bvv)
+    # T2 equation
+    X = ein("ijae,eb->ijab", t2, I_vv) - ein("miba,jm->ijab", t2, I_oo)
+    X = X + 0.5 * ein("ijmn,mnab->ijab", I_oooo, t2)
+    X = X - ein("mjae,iemb->ijab", t2, I_ovov) - ein("iema,mjeb->ijab", I_ovov, t2) + ein("miea,ejmb->ijab", asym, I_voov)
+    say(f"ring terms {time.perf_counter() - t0:.0f} s")
+    c2 = np.ascontiguousarray(t2.reshape(o * o, v * v))       # c(ij, ef)
+    Bvv_ea = np.ascontiguousarray(Bvv.transpose(1, 2, 0).reshape(v * v, naux))      # [(e,a), P]
+    lad = np.empty((o * o, v, v))                             # [ij, a, b]
+    for b0 in range(0, v, ladder_block):
+        b1 = min(v, b0 + ladder_block)
+        W = (Bvv_ea @ Bvv[:, :, b0:b1].reshape(naux, -1)).reshape(v, v, v, b1 - b0)          # [e, a, f, b] = <ef|ab>
+        W = np.ascontiguousarray(W.transpose(0, 2, 1, 3)).reshape(v * v, v * (b1 - b0))      # [(e,f), (a,b)]
+        lad[:, :, b0:b1] = (c2 @ W).reshape(o * o, v, b1 - b0)
+    X = X + 0.5 * lad.reshape(o, o, v, v)
+    del lad, W
+    say(f"ladder {time.perf_counter() - t0:.0f} s")
+    X = X + X.transpose(1, 0, 3, 2) + v_oovv
+    t1n, t2n = r1 / D1, X / D2
+    e = orc.restricted_energy(t1n, t2n, v_oovv)
+    rms = float(np.sum((t2n - t2) ** 2))
+    e_mp2 = orc.restricted_energy(np.zeros_like(t1n), t2, v_oovv)
+    return float(e), rms, float(e_mp2)
+
+
+def cpu_ccsd_iter1(nbf=400, nocc=40):
+    e, rms, e_mp2 = ccsd_iter1_from_factors(nbf, nocc, log=lambda *a: print(*a, flush=True))
+    pins = load()
+    key = f"nbf{nbf}_nocc{nocc}"
+    pins.setdefault(key, {})
+    pins[key]["e_ccsd_iter1_cpu_port"] = e
+    pins[key]["iter1_cpu_source"] = ("tests/golden/make_bench_pins.py cpu_ccsd_iter1 (NumPy from the factored integrals: the oracle's "
+                                     "spin-free iteration with t1 = 0 on input, ladder integrals built in slabs)")
+    json.dump(pins, open(PATH, "w"), indent=1)
+    print(key, "E_CCSD after iteration 1 (CPU):", e, " rms:", rms, " GPU-pinned step 1:", (pins[key].get("steps") or [[None]])[0][0])
+
+
 def cpu_mp1_triples(nbf=400, nocc=40):
     """Pins for bench.py's per-triple (T) check at a shape where no CPU CCSD iteration is affordable (the target shape):
     a handful of unique triples of all three orbit kinds (i=j=k, two equal, all different), spread over the list."""
@@ -254,6 +340,8 @@ def gpu(path):
 if __name__ == "__main__":
     if sys.argv[1] == "cpu":
         cpu(*[int(x) for x in sys.argv[2:4]])
+    elif sys.argv[1] == "cpu_ccsd_iter1":
+        cpu_ccsd_iter1(*[int(x) for x in sys.argv[2:4]])
     elif sys.argv[1] == "cpu_mp1_triples":
         cpu_mp1_triples(*[int(x) for x in sys.argv[2:4]])
     elif sys.argv[1] == "cpu_mp2":

@@ -68,3 +68,34 @@ def test_cpu_port_cr_triples_match_numpy_oracle():
     ref = orc.triples_spatial_sums(cc["t1"], cc["t2"], V["v_oovv"], V["v_vvov"], V["v_oovo"], eps, True, False, True,
                                    cc["I_vovv_pp"], cc["I_ooov_pp"])
     assert np.max(np.abs(sums - np.array(ref))) < 1e-13
+
+
+def test_pin_recipes_from_the_factored_integrals_equal_the_general_oracle():
+    """tests/golden/make_bench_pins.py computes CPU pins for shapes where the dense slices cannot be built (nbf=400) straight
+    from the factored form of the synthetic integrals: the first CCSD iteration with the t1 = 0 terms dropped and the ladder
+    integrals in slabs, MP2 from the (ia|jb) block, and single-orbit (T) values on the MP1 amplitudes.  At a small shape each
+    recipe must equal the general oracle functions on the slices of the packed MO integrals."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_bench_pins as M
+
+    n, o = 37, 5
+    mo, C, eps = cpu_port.synthetic_mo_integrals(n, o)
+    V = orc.spatial_slices(mo, n, o)
+    D1, D2 = orc.denominators(eps, o)
+    t2 = V["v_oovv"] / D2
+    t1 = np.zeros_like(D1)
+    I = orc.restricted_intermediates(t1, t2, V)
+    t1n, t2n = orc.restricted_amplitudes(t1, t2, V, I, D1, D2)
+    e, rms, e_mp2 = M.ccsd_iter1_from_factors(n, o, ladder_block=5)
+    assert abs(e - orc.restricted_energy(t1n, t2n, V["v_oovv"])) < 1e-14
+    assert abs(rms - float(np.sum((t2n - t2) ** 2))) < 1e-15
+    assert abs(e_mp2 - orc.mp2_energy(mo, eps, o)) < 1e-14 and abs(M.mp2_from_factors(n, o) - e_mp2) < 1e-14
+    picks = [(0, 0, 0), (0, 0, 3), (1, 2, 4), (2, 4, 4)]
+    vals, _ = M.mp1_triples_from_factors(n, o, picks)
+    for t, x in zip(picks, vals):
+        assert abs(x - orc.triples_bracket_T_orbit_form(t2, V["v_vvov"], V["v_oovo"], eps, triples=[t])) < 1e-16
+    assert M.unique_triples(3) == [(0, 0, 0), (0, 0, 1), (0, 0, 2), (0, 1, 1), (0, 1, 2), (0, 2, 2), (1, 1, 1), (1, 1, 2),
+                                   (1, 2, 2), (2, 2, 2)]
