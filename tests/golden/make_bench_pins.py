@@ -220,11 +220,16 @@ def cpu_ccsd_iter1(nbf=400, nocc=40):
 
 def cpu_mp1_triples(nbf=400, nocc=40):
     """Pins for bench.py's per-triple (T) check at a shape where no CPU CCSD iteration is affordable (the target shape):
-    a handful of unique triples of all three orbit kinds (i=j=k, two equal, all different), spread over the list."""
+    sixteen unique triples of all three orbit kinds (i=j=k, two equal, all different), spread over the list."""
     o = nocc
     all_t = unique_triples(o)
     picks = [(0, 0, 0), (o // 6, o // 6, o // 2), (o // 8, o // 2, (4 * o) // 5), (o // 3, (2 * o) // 3, (2 * o) // 3),
-             (o - 3, o - 2, o - 1), (o - 1, o - 1, o - 1)]
+             (o - 3, o - 2, o - 1), (o - 1, o - 1, o - 1),
+             # ten more, spread over the list: the lowest and highest orbitals, neighbours, both two-equal patterns
+             (0, 1, 2), (0, 0, o - 1), (0, o - 1, o - 1), (0, o // 2, o - 1), (1, o // 4, o // 2), (o // 5, o // 5 + 1, o // 5 + 2),
+             (o // 2, o // 2, o // 2 + 1), (o // 2 - 1, o // 2, o - 2), ((3 * o) // 5, (7 * o) // 10, (9 * o) // 10),
+             (o // 10, (3 * o) // 4, (3 * o) // 4)]
+    assert len(set(picks)) == len(picks) and all(i <= j <= k < o for i, j, k in picks)
     e, _ = mp1_triples_from_factors(nbf, nocc, picks)
     pins = load()
     key = f"nbf{nbf}_nocc{nocc}"
