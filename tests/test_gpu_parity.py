@@ -418,6 +418,44 @@ def test_synthetic_chain_matches_oracle_and_device_generated_integrals(gpu):
         assert abs(got[k] - en[k]) < E_TOL, k
 
 
+@pytest.mark.parametrize("n,o", [(80, 6), (83, 6)])
+def test_crccsd_t_chain_at_a_multi_tile_shape_matches_the_cpu(gpu, n, o):
+    """The complete CRCCSD(T)_spatial chain -- CCSD to convergence with DIIS, CR intermediates, all six triples sums with the
+    M3 / y / z3 branches of the epilogue -- on synthetic integrals with more than one GEMM m-tile per block (v = 74: 64 + a
+    ragged 10 on the TMA-staged kernel; v = 77: odd leading dimensions, cp.async kernels), against the CPU: the oracle's
+    CCSD and CR intermediates, and the C port of the reference's own triples loop incl. the CR part (oracle/cpu_kernels.c:
+    afesp_ref_triples_cr, src/ccsd.f90:2152-2233) over all o^3 ordered triples.  The sample molecules (v <= 53) never leave
+    a single tile."""
+    from afesp_b200 import host, synthetic
+    from oracle import cpu_port
+
+    eri, Cm, eps = synthetic.make(n, o)
+    gpu.ao2mo(n, eri, Cm, want_result=False)
+    gpu.release("eri_ao")
+    table, conv, e, _ = host.ccsd_loop(gpu, o, True, eps, 1e-8, 1e-9, 8, 50)
+    t1_diag, _, _ = gpu.ccsd_finalize(want_cr=True)
+    sums, const = gpu.ccsd_t_spatial(True, False, True)
+    # CPU
+    mo, C2, eps2 = cpu_port.synthetic_mo_integrals(n, o)
+    assert np.array_equal(eps, eps2)
+    cc = orc.ccsd_spatial(mo, eps, o, 1e-8, 1e-9, 8, 50, want_cr=True)
+    assert conv and len(table) == len(cc["table"])
+    for (it, ee, _, rms), (oit, oe, _, orms) in zip(table, cc["table"]):
+        assert it == oit and abs(ee - oe) < E_TOL and abs(rms - orms) < 1e-9
+    assert abs(t1_diag - cc["t1_diag"]) < 1e-9
+    lib = cpu_port.load()
+    cpu_port.set_threads(lib)
+    V = cc["V"]
+    ijk = [(i, j, k) for i in range(o) for j in range(o) for k in range(o)]
+    want, _ = cpu_port.triples_cr(lib, cc["t1"], cc["t2"], V["v_oovv"], V["v_vvov"], V["v_oovo"], cc["I_vovv_pp"],
+                                  cc["I_ooov_pp"], eps, ijk, True)
+    assert np.max(np.abs(sums - want)) < E_TOL, (sums, want)
+    got = host.assemble_triples(e, sums, const, True, False, True)
+    ref = orc.assemble_triples(cc["e_ccsd"], tuple(want), orc.triples_denominator_constant(cc["t1"], cc["t2"]), True, False, True)
+    for k in ["e_ccsd_t", "e_ccsd_tt", "e_rccsd_t", "e_rccsd_tt", "e_crccsd_t", "e_crccsd_tt", "D_T", "D_TT"]:
+        assert abs(got[k] - ref[k]) < E_TOL, k
+
+
 def test_single_triple_shares_on_mp1_amplitudes_match_cpu_values_from_the_factored_integrals(gpu):
     """The per-triple check bench.py runs at the target shape (bench.mp1_triples_check), here at nbf=64 / nocc=6 where all 56
     unique triples can be gone through: with afesp_gpu_set_partition(r, 56) the handle owns exactly triple number r of the
