@@ -182,3 +182,31 @@ void afesp_ref_triples_cr(int o, int v, const double* t1, const double* t2, cons
 }
 
 int afesp_ref_threads(void) { return omp_get_max_threads(); }
+
+
+/* Epilogue of the BLAS orbit form of the [T] accumulator (oracle/afesp_oracle.py: triples_bracket_T_orbit_form) for large
+ * shapes (tests/golden/make_bench_pins.py cpu_T_fast): the six permuted products of one (i <= j <= k) orbit have been
+ * accumulated by dgemm (beta = 1) into three column-major buffers according to which virtual label indexes their rows,
+ *     W(a,b,c) = Y0(a; b,c) + Y1(b; a,c) + Y2(c; a,b),
+ * and the orbit's contribution is  sum_abc W(abc) / D3(abc) * [ 8 W(abc) - 4 (W(acb) + W(cba) + W(bac)) + 2 (W(cab) + W(bca)) ]
+ * (times orderings/6, applied by the caller).  w is a v^3 scratch array.  eo3 = eps_i + eps_j + eps_k. */
+double afesp_orbit_T_epilogue(int v, const double* y0, const double* y1, const double* y2, const double* ev, double eo3,
+                              double* w) {
+  const size_t n = (size_t)v, n2 = n * n;
+#pragma omp parallel for schedule(static)
+  for (int c = 0; c < v; ++c)
+    for (int b = 0; b < v; ++b)
+      for (int a = 0; a < v; ++a)
+        w[a + n * b + n2 * c] = y0[a + n * b + n2 * c] + y1[b + n * a + n2 * c] + y2[c + n * a + n2 * b];
+  double e = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : e)
+  for (int c = 0; c < v; ++c)
+    for (int b = 0; b < v; ++b)
+      for (int a = 0; a < v; ++a) {
+        const double wabc = w[a + n * b + n2 * c];
+        const double s = 8.0 * wabc - 4.0 * (w[a + n * c + n2 * b] + w[c + n * b + n2 * a] + w[b + n * a + n2 * c]) +
+                         2.0 * (w[c + n * a + n2 * b] + w[b + n * c + n2 * a]);
+        e += wabc * s / (eo3 - ev[a] - ev[b] - ev[c]);
+      }
+  return e;
+}

@@ -86,6 +86,8 @@ def load():
     lib.afesp_ref_ring.restype = None
     lib.afesp_ref_triples.argtypes = [C.c_int, C.c_int] + [_dp] * 7 + [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, _dp]
     lib.afesp_ref_triples.restype = None
+    lib.afesp_orbit_T_epilogue.argtypes = [C.c_int, _dp, _dp, _dp, _dp, C.c_double, _dp]
+    lib.afesp_orbit_T_epilogue.restype = C.c_double
     lib.afesp_ref_triples_bounded.argtypes = ([C.c_int, C.c_int] + [_dp] * 7 +
                                               [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, _dp])
     lib.afesp_ref_triples_bounded.restype = None
@@ -234,3 +236,67 @@ def synthetic_mo_integrals(nbf, nocc, seed=20260):
         packed[pos:pos + r + 1] = G[r, :r + 1]
         pos += r + 1
     return packed, Cmo, eps
+
+
+def orbit_T_fast(lib, t2, iv_block, v_oovo, eps, triples, progress=None, checkpoint=None):
+    """sum over the listed unique (i <= j <= k) triples of their [T] orbit contributions -- the same quantity as
+    oracle.afesp_oracle.triples_bracket_T_orbit_form, organised for large shapes (nbf=400: 11480 orbits of v^3 = 4.7e7
+    elements): operands pre-arranged once in column-major blocks, the twelve products of an orbit accumulated by dgemm
+    (beta = 1) into three buffers by row label, one C pass for the permuted sum and the energy expression
+    (cpu_kernels.c: afesp_orbit_T_epilogue).  t2: (o,o,v,v) C-order; iv_block(k) -> [d,(b,c)] matrix of v_vovv(d,k,b,c);
+    v_oovo: (o,o,v,o) C-order.  checkpoint = (path, every): partial sums are saved and a rerun resumes."""
+    import json
+    import os
+
+    o, v = t2.shape[0], t2.shape[2]
+    v3 = v ** 3
+    eo, ev = np.ascontiguousarray(eps[:o]), np.ascontiguousarray(eps[o:])
+    t2 = np.ascontiguousarray(t2)
+    v_oovo = np.ascontiguousarray(v_oovo)
+    used_k = sorted({x for t in triples for x in t})
+    VF = np.empty((v, v, v, o), order="F")      # VF[d,y,z,k] = v_vovv(d,k,y,z);  VFT[d,y,z,k] = v_vovv(d,k,z,y)
+    VFT = np.empty((v, v, v, o), order="F")
+    for k in used_k:
+        m = np.asarray(iv_block(k)).reshape(v, v, v)
+        VF[:, :, :, k] = m
+        VFT[:, :, :, k] = m.transpose(0, 2, 1)
+    TF = np.asfortranarray(t2.transpose(0, 2, 3, 1))      # TF[l,y,z,A] = t2[l,A,y,z]
+    TFT = np.asfortranarray(t2.transpose(0, 3, 2, 1))     # TFT[l,y,z,A] = t2[l,A,z,y]
+    Y = [np.empty(v3) for _ in range(3)]
+    W = np.empty(v3)
+    S3 = [(0, 1, 2), (1, 0, 2), (2, 1, 0), (0, 2, 1), (1, 2, 0), (2, 0, 1)]
+    ptr = lambda arr, off: C.cast(arr.ctypes.data + 8 * off, _dp)
+    total, start = 0.0, 0
+    if checkpoint and os.path.exists(checkpoint[0]):
+        ck = json.load(open(checkpoint[0]))
+        if ck.get("ntriples") == len(triples):
+            total, start = ck["total"], ck["next"]
+    t0 = time.perf_counter()
+    for n_done in range(start, len(triples)):
+        i, j, k = triples[n_done]
+        idx = (i, j, k)
+        first = [True, True, True]
+        for p in S3:
+            A, B, Cc = idx[p[0]], idx[p[1]], idx[p[2]]
+            # particle: Y[p0](x; y,z) += sum_d t2[A,B](x,d) v_vovv(d,Cc; j_p1, j_p2)   (columns in increasing label position)
+            cls = p[0]
+            Vsrc = VF if p[1] < p[2] else VFT
+            lib.afesp_ref_dgemm(b"T", b"N", v, v * v, v, ptr(t2, (A * o + B) * v * v), ptr(Vsrc, Cc * v3), ptr(Y[cls], 0), 1.0,
+                                0.0 if first[cls] else 1.0)
+            first[cls] = False
+        for p in S3:
+            A, B, Cc = idx[p[0]], idx[p[1]], idx[p[2]]
+            # hole: Y[p2](x; y,z) -= sum_l v_oovo[Cc,B](x,l) t2[l,A; j_p1, j_p0]
+            cls = p[2]
+            Tsrc = TF if p[1] < p[0] else TFT
+            lib.afesp_ref_dgemm(b"T", b"N", v, v * v, o, ptr(v_oovo, (Cc * o + B) * v * o), ptr(Tsrc, A * o * v * v), ptr(Y[cls], 0),
+                                -1.0, 1.0)
+        e = lib.afesp_orbit_T_epilogue(v, ptr(Y[0], 0), ptr(Y[1], 0), ptr(Y[2], 0), ptr(ev, 0), float(eo[i] + eo[j] + eo[k]),
+                                       ptr(W, 0))
+        total += e * len({(i, j, k), (i, k, j), (j, i, k), (j, k, i), (k, i, j), (k, j, i)}) / 6.0
+        if progress and (n_done + 1) % progress == 0:
+            dt = time.perf_counter() - t0
+            print(f"[orbit_T_fast] {n_done + 1} / {len(triples)} orbits, {dt / (n_done + 1 - start):.2f} s per orbit", flush=True)
+        if checkpoint and (n_done + 1) % checkpoint[1] == 0:
+            json.dump({"ntriples": len(triples), "next": n_done + 1, "total": total}, open(checkpoint[0], "w"))
+    return total

@@ -5,6 +5,7 @@
     python tests/golden/make_bench_pins.py cpu_T               # CPU-only, ~15 min: e_T of the first step at nbf=200 through the
                                                                # oracle's BLAS orbit form of the [T] accumulator
     python tests/golden/make_bench_pins.py cpu_mp2 400 40      # CPU-only: MP2 of the target shape from the (ia|jb) block
+    python tests/golden/make_bench_pins.py cpu_T_target 400 40      # CPU-only, ~3 h: e_T of the first step at the target shape
     python tests/golden/make_bench_pins.py cpu_ccsd_iter1 400 40    # CPU-only, ~20 min: E_CCSD after the first iteration at the
                                                                # target shape, from the factored integrals
     python tests/golden/make_bench_pins.py cpu_mp1_triples 400 40   # CPU-only: (T) contributions of six single triples on the
@@ -134,7 +135,7 @@ def mp1_triples_from_factors(nbf, nocc, picks):
             for t in picks], eps
 
 
-def ccsd_iter1_from_factors(nbf, nocc, ladder_block=8, log=None):
+def ccsd_iter1_from_factors(nbf, nocc, ladder_block=8, log=None, return_state=False):
     """E_CCSD and sum (dT2)^2 after the FIRST spin-free CCSD iteration (input: t1 = 0, t2 = MP1), from the factored form of the
     synthetic integrals, for shapes whose dense v_vvvv slice (nbf=400: 134 GB) rules out both the oracle's general functions
     and the CPU port.  It is oracle.restricted_intermediates + restricted_amplitudes (src/ccsd.f90:1040-1312, 1538-1732) with
@@ -203,6 +204,8 @@ def ccsd_iter1_from_factors(nbf, nocc, ladder_block=8, log=None):
     e = orc.restricted_energy(t1n, t2n, v_oovv)
     rms = float(np.sum((t2n - t2) ** 2))
     e_mp2 = orc.restricted_energy(np.zeros_like(t1n), t2, v_oovv)
+    if return_state:   # amplitudes after the iteration + the factor blocks (for the (T) of the first bench step)
+        return float(e), rms, float(e_mp2), {"t1": t1n, "t2": t2n, "Boo": Boo, "Bov": Bov, "Bvv": Bvv, "eps": eps}
     return float(e), rms, float(e_mp2)
 
 
@@ -216,6 +219,52 @@ def cpu_ccsd_iter1(nbf=400, nocc=40):
                                      "spin-free iteration with t1 = 0 on input, ladder integrals built in slabs)")
     json.dump(pins, open(PATH, "w"), indent=1)
     print(key, "E_CCSD after iteration 1 (CPU):", e, " rms:", rms, " GPU-pinned step 1:", (pins[key].get("steps") or [[None]])[0][0])
+
+
+def cpu_T_target(nbf=400, nocc=40, limit=None):
+    """e_T of the FIRST bench step at a shape without a CPU port iteration (the target shape): amplitudes after the first
+    CCSD iteration from ccsd_iter1_from_factors (the DIIS step that follows has one history entry and leaves them unchanged),
+    then the [T] accumulator over all unique triples through oracle/cpu_port.py: orbit_T_fast (dgemm-accumulated products + C
+    epilogue; ~0.9 s per orbit at nbf=400 on 8 cores, 11480 orbits: about three hours).  Checkpointed: a rerun resumes."""
+    import time
+
+    from oracle import cpu_port
+
+    t0 = time.perf_counter()
+    e1, rms, e_mp2, st = ccsd_iter1_from_factors(nbf, nocc, log=lambda *a: print(*a, flush=True), return_state=True)
+    o, v = nocc, nbf - nocc
+    naux = st["Bvv"].shape[0]
+    Bvv2 = st["Bvv"].reshape(naux, v * v)
+    Bov, Boo = st["Bov"], st["Boo"]
+
+    def iv_block(k):      # [d, (b,c)] = (ck|bd) = sum_P Bov[P,k,c] Bvv[P,b,d]
+        x = (Bvv2.T @ Bov[:, k, :]).reshape(v, v, v)        # [b, d, c]
+        return np.ascontiguousarray(x.transpose(1, 0, 2)).reshape(v, v * v)
+
+    v_oovo = np.einsum("Pia,Pjl->ijal", Bov, Boo, optimize=True)
+    lib = cpu_port.load()
+    cpu_port.set_threads(lib)
+    triples = unique_triples(o)
+    if limit:
+        triples = triples[:int(limit)]
+    print(f"E_CCSD after iteration 1: {e1!r}; operands for {len(triples)} orbits ...", flush=True)
+    ck = os.path.join(os.path.dirname(PATH), f"_cpu_T_checkpoint_nbf{nbf}.json")
+    e_T = cpu_port.orbit_T_fast(lib, np.ascontiguousarray(st["t2"]), iv_block, v_oovo, st["eps"], triples, progress=200,
+                                checkpoint=None if limit else (ck, 100))
+    print(f"e_T = {e_T!r}  ({time.perf_counter() - t0:.0f} s in all)", flush=True)
+    if limit:
+        return e_T
+    pins = load()
+    key = f"nbf{nbf}_nocc{nocc}"
+    pins.setdefault(key, {})
+    pins[key]["e_T_step1_cpu_oracle"] = e_T
+    pins[key]["cpu_T_source"] = ("tests/golden/make_bench_pins.py cpu_T_target (amplitudes after the first CCSD iteration from the "
+                                 "factored integrals; [T] accumulator over all unique triples: dgemm-accumulated products + C "
+                                 "epilogue, oracle/cpu_port.py orbit_T_fast)")
+    json.dump(pins, open(PATH, "w"), indent=1)
+    print(key, "e_T_step1_cpu_oracle", e_T, "GPU-pinned step 1:", (pins[key].get("steps") or [[None, None]])[0][1])
+    if os.path.exists(ck):
+        os.remove(ck)
 
 
 def cpu_mp1_triples(nbf=400, nocc=40):
@@ -345,6 +394,8 @@ def gpu(path):
 if __name__ == "__main__":
     if sys.argv[1] == "cpu":
         cpu(*[int(x) for x in sys.argv[2:4]])
+    elif sys.argv[1] == "cpu_T_target":
+        cpu_T_target(*[int(x) for x in sys.argv[2:5]])
     elif sys.argv[1] == "cpu_ccsd_iter1":
         cpu_ccsd_iter1(*[int(x) for x in sys.argv[2:4]])
     elif sys.argv[1] == "cpu_mp1_triples":
