@@ -67,9 +67,10 @@ def test_parity_block_uses_the_cpu_pins_and_the_pin_file_is_self_consistent():
     assert len(pins["steps_cpu"]) >= 3
     for cpu, gpu in zip(pins["steps_cpu"], steps):
         assert abs(cpu[0] - gpu[0]) < 1e-11 and abs(cpu[1] - gpu[1]) < 1e-11
-    # the target shape: no CPU (T) over 11480 triples, but MP2, the first CCSD iteration and six single-orbit (T) values
+    # the target shape: MP2, the first CCSD iteration, the (T) sum of the first step (100 CPU-minutes) and sixteen single-orbit values
     t = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_pinned.json")))["nbf400_nocc40"]
     assert abs(t["e_mp2"] - t["e_mp2_oracle"]) < 1e-12 and abs(t["steps"][0][0] - t["e_ccsd_iter1_cpu_port"]) < 1e-12
+    assert abs(t["steps"][0][1] - t["e_T_step1_cpu_oracle"]) < 1e-12          # the full (T) sum over all 11480 orbits
     m = t["mp1_triples"]
     assert m["ntriples"] == 40 * 41 * 42 // 6 and len(m["ranks"]) == len(m["e_T"]) == len(m["ijk"]) >= 5
     assert all(abs(x) < 1e-20 for x, ijk in zip(m["e_T"], m["ijk"]) if ijk[0] == ijk[2]) and min(m["e_T"]) < -1e-7
