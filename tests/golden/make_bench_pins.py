@@ -334,8 +334,8 @@ def cpu_T(nbf=200, nocc=20, limit=None):
 def cpu_traj(nbf=200, nocc=20, nsteps=3):
     """The first `nsteps` steps of the bench trajectory on the CPU, in the bench's own order (bench.py step()): one CCSD
     iteration (CPU port of the reference, energy from its output amplitudes), CC-DIIS extrapolation (the oracle's ring of
-    depth 8), then the [T] accumulator ON THE EXTRAPOLATED amplitudes (oracle BLAS orbit form).  ~5.5 CPU-minutes per step
-    on 8 cores at nbf=200.  Stored as steps_cpu = [[E_CCSD, e_T], ...]."""
+    depth 8), then the [T] accumulator ON THE EXTRAPOLATED amplitudes (orbit form: oracle/cpu_port.py orbit_T_fast, which equals the
+    oracle's NumPy orbit form and the literal loop).  ~2.5 CPU-minutes per step on 8 cores at nbf=200.  Stored as steps_cpu = [[E_CCSD, e_T], ...]."""
     import time
 
     from oracle import afesp_oracle as orc
@@ -352,6 +352,9 @@ def cpu_traj(nbf=200, nocc=20, nsteps=3):
     t1 = np.zeros((o, nbf - o), order="F")
     diis = orc.CCDiis(8, t1.shape, t2.shape)
     vvov, oovo = np.ascontiguousarray(V["v_vvov"]), np.ascontiguousarray(V["v_oovo"])
+    nv = nbf - nocc
+    ivb = lambda k: np.ascontiguousarray(vvov[:, :, k, :].transpose(2, 1, 0)).reshape(nv, nv * nv)
+    uniq = unique_triples(o)
     steps = []
     for it in range(int(nsteps)):
         t0 = time.perf_counter()
@@ -359,7 +362,7 @@ def cpu_traj(nbf=200, nocc=20, nsteps=3):
         t1n, t2n, _, _ = cpu_port.ccsd_iter(lib, V, eps, np.asfortranarray(t1), np.asfortranarray(t2))
         e_cc = orc.restricted_energy(np.asarray(t1n), np.asarray(t2n), voovv)
         t1, t2 = diis.update(np.asarray(t1n), np.asarray(t2n))
-        e_T = orc.triples_bracket_T_orbit_form(np.ascontiguousarray(t2), vvov, oovo, eps)
+        e_T = cpu_port.orbit_T_fast(lib, np.ascontiguousarray(t2), ivb, oovo, eps, uniq)
         steps.append([float(e_cc), float(e_T)])
         print(f"step {it + 1}: E_CCSD {e_cc!r}  e_T {e_T!r}  ({time.perf_counter() - t0:.0f} s)", flush=True)
     pins = load()
@@ -367,7 +370,7 @@ def cpu_traj(nbf=200, nocc=20, nsteps=3):
     pins.setdefault(key, {})
     pins[key]["steps_cpu"] = steps
     pins[key]["steps_cpu_source"] = ("tests/golden/make_bench_pins.py cpu_traj: per step one CCSD iteration through oracle/cpu_ccsd.c, "
-                                     "the oracle's CC-DIIS, the [T] accumulator through the oracle's BLAS orbit form")
+                                     "the oracle's CC-DIIS, the [T] accumulator over all triples in orbit form (oracle/cpu_port.py orbit_T_fast)")
     json.dump(pins, open(PATH, "w"), indent=1)
     for a, b in zip(steps, pins[key].get("steps", [])):
         print("cpu", a, "gpu-pinned", b, "diff", abs(a[0] - b[0]), abs(a[1] - b[1]))
