@@ -497,7 +497,7 @@ def test_one_bench_step_at_a_multi_tile_shape_matches_the_cpu(gpu, n, o):
     several GEMM tiles per block -- v = 108: one full and one ragged m-tile, K = 120: a short K tail, i.e. the EDGE / KTAIL
     variants of the TMA-staged kernel; v = 91: odd leading dimensions, the cp.async kernels -- against a CPU computation of
     the same step: MP2 from the factored integrals, E_CCSD from the CPU port of the reference's iteration
-    (oracle/cpu_ccsd.c), the (T) sum from the oracle's BLAS orbit form.  The same recipe at nbf=200 is what
+    (oracle/cpu_ccsd.c), the (T) sum over all triples in orbit form (oracle/cpu_port.py: orbit_T_fast, equal to the literal loop).  The same recipe at nbf=200 is what
     tests/golden/bench_pinned.json pins every bench line on."""
     from afesp_b200 import synthetic
     from oracle import cpu_port
@@ -525,8 +525,11 @@ def test_one_bench_step_at_a_multi_tile_shape_matches_the_cpu(gpu, n, o):
     t1n, t2n, _, _ = cpu_port.ccsd_iter(lib, V, eps, np.zeros((o, n - o), order="F"), t2)
     assert abs(e1 - orc.restricted_energy(np.asarray(t1n), np.asarray(t2n), voovv)) < E_TOL
     assert abs(rms1 - float(np.sum((np.asarray(t2n) - np.asarray(t2)) ** 2))) < 1e-9
-    want_T = orc.triples_bracket_T_orbit_form(np.ascontiguousarray(t2n), np.ascontiguousarray(V["v_vvov"]),
-                                              np.ascontiguousarray(V["v_oovo"]), eps)
+    vvov, nv = np.ascontiguousarray(V["v_vvov"]), n - o
+    want_T = cpu_port.orbit_T_fast(lib, np.ascontiguousarray(t2n),
+                                   lambda k: np.ascontiguousarray(vvov[:, :, k, :].transpose(2, 1, 0)).reshape(nv, nv * nv),
+                                   np.ascontiguousarray(V["v_oovo"]), eps,
+                                   [(i, j, k) for i in range(o) for j in range(i, o) for k in range(j, o)])
     assert abs(sums[0] - want_T) < E_TOL and abs(sums[1] - want_T) < E_TOL      # plain (T): quirk Q2, e_TT = e_T
 
 
