@@ -29,3 +29,8 @@ run(T.test_h2o_cc_pvtz_spinorbital_ccsd_t_matches_reference_els_cpu_out, OracleE
 for calc in ["CCSD(T)_spatial", "RCCSD(T)_spatial"]:
     run(T.test_h2o_cc_pvtz_spin_free_matches_oracle, OracleEngine(), calc)
 run(T.test_diis_history_deeper_than_eight_matches_oracle, OracleEngine())
+# the multi-tile tests, at small stand-in shapes (their CPU sides are the same code at any shape)
+for n, o in [(30, 4), (27, 3)]:
+    run(T.test_one_bench_step_at_a_multi_tile_shape_matches_the_cpu, OracleEngine(), n, o)
+run(T.test_crccsd_t_chain_at_a_multi_tile_shape_matches_the_cpu, OracleEngine(), 24, 4)
+run(T.test_single_triple_shares_on_mp1_amplitudes_match_cpu_values_from_the_factored_integrals, OracleEngine())
